@@ -1,0 +1,183 @@
+/* b200rec.h - C ABI of libb200rec.so, the B200 (sm_100a) BPR-MF training and
+ * scoring engine that drops in behind yoongi0428/RecSys_PyTorch's hot path.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) HOST-buffer drop-ins with the exact argument lists of the reference's own
+ *      native layer (what its Cython shims bind today).  Buffers are caller-owned
+ *      host memory; copies happen inside the call.
+ *  (2) DEVICE-pointer engine calls used by the host-side mirror of the
+ *      reference's model / generator / evaluator interface
+ *      (recsys_pytorch_b200/*.py).  Pointers come from torch.Tensor.data_ptr();
+ *      the caller owns all memory; `stream` is a cudaStream_t (0 = default).
+ *
+ * Conventions: every function returns 0 on success, a negative B200REC_E* code on
+ * failure, and never aborts; b200rec_last_error() returns a thread-local message.
+ * (The reference's native functions are `void` with no error reporting and UB on
+ * bad sizes - SURVEY section 8(b); the codes are an addition, the happy path is
+ * identical.)  One host thread per device at a time.  No CPU fallback exists:
+ * without a usable CUDA device every call returns B200REC_ECUDA.
+ *
+ * Embedding tables are row-major fp32 `[rows, ld]` with `ld >= d`, `ld % 4 == 0`,
+ * base 16-byte aligned, and columns d..ld-1 zero (they stay zero under every
+ * update).  Item / user ids are int32.  CSR = int64 indptr + int32 sorted indices.
+ */
+#ifndef B200REC_H
+#define B200REC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REC_OK 0
+#define B200REC_EINVAL (-1)  /* bad argument (null pointer, size, alignment)   */
+#define B200REC_ECUDA (-2)   /* CUDA runtime / launch failure, or no device    */
+#define B200REC_ENOMEM (-3)  /* workspace too small / allocation failed        */
+#define B200REC_EUNSUPPORTED (-4)
+
+const char *b200rec_last_error(void);
+int b200rec_version(void);            /* 100*major + minor */
+/* number of kernels this library has launched in the calling process */
+int64_t b200rec_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * (1) drop-ins for the reference's native evaluation layer (HOST buffers)
+ * ------------------------------------------------------------------------- */
+
+/* replaces c_top_k_array_index, evaluation/backend/cython/include/func.h:22-31
+ * (bound by evaluation/backend/cython/func.pyx:8-10,22).  scores: fp32
+ * [rows_num, columns_num] C-contiguous; rankings: int32 [rows_num, max_k], ids of
+ * the max_k largest scores, descending; ties -> smaller id first (upstream:
+ * unspecified).  Requires 1 <= max_k <= columns_num and max_k <= 1024. */
+int b200rec_top_k_array_index(const float *scores_pt, int columns_num, int rows_num,
+                              int max_k, int *rankings_pt);
+
+/* replaces evaluate_holdout, evaluation/backend/cython/include/holdout.h:20-103
+ * (bound by holdout_func.pyx:6-10,40).  results: fp32 [users_num, 3*K_len] laid
+ * out [Prec@Ks.., Recall@Ks.., NDCG@Ks..] per user. */
+int b200rec_evaluate_holdout(int users_num, const int *rankings, int max_k, const int *Ks,
+                             int K_len, int **ground_truths, const int *ground_truths_num,
+                             float *results);
+
+/* replaces evaluate_loo, evaluation/backend/cython/include/loo.h:20-85 (bound by
+ * loo_func.pyx:6-9,35).  results: fp32 [users_num, 2*K_len] = [HR@Ks.., NDCG@Ks..] */
+int b200rec_evaluate_loo(int users_num, const int *rankings, int max_k, const int *Ks,
+                         int K_len, int **ground_truths, float *results);
+
+/* ------------------------------------------------------------------------- *
+ * (2) device-pointer engine
+ * ------------------------------------------------------------------------- */
+
+/* models/MF.py:32-42 MF.forward: out[b] = sum_k U[users[b],k] * V[items[b],k] */
+int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int32_t *users,
+                       const int32_t *items, int n, float *out, void *stream);
+
+/* Sink of the fused BPR step */
+#define B200REC_SINK_UPDATE 0 /* tables updated in place: W += -lr*(grad)  (one fused kernel) */
+#define B200REC_SINK_STAGE 1  /* per-triple delta rows -> `stage` [B,3,ld]; apply with b200rec_bpr_apply */
+#define B200REC_SINK_GRAD 2   /* raw gradient rows accumulated into dense gU/gV (embedding_dense_backward) */
+#define B200REC_SINK_NONE 3   /* forward only: loss_sum / x_out (models/MF.py:99-107 without backward) */
+
+/* flags */
+#define B200REC_F_USERS_UNIQUE 1 /* no user id repeats inside the batch: user rows use plain vector stores */
+#define B200REC_F_TMA_GATHER 2   /* rows gathered with cp.async.bulk (TMA) into shared memory */
+
+typedef struct b200rec_bpr_args {
+    float *U;              /* [num_users, ld]  user_embedding.weight (models/MF.py:23)   */
+    float *V;              /* [num_items, ld]  item_embedding.weight (models/MF.py:24)   */
+    int32_t ld, d;
+    int32_t num_users, num_items;
+    const int32_t *users;  /* [B]  required                                               */
+    const int32_t *pos;    /* [B]  or NULL -> sampled on device from the CSR row          */
+    const int32_t *neg;    /* [B]  or NULL -> sampled on device (uniform over non-positives) */
+    int32_t B;
+    /* CSR of train positives, required when pos or neg is NULL (data/generators.py:168-201) */
+    const int64_t *csr_indptr;
+    const int32_t *csr_indices;
+    uint64_t seed, step;   /* counter RNG key (seed, step, triple index, draw) */
+    int32_t *out_pos, *out_neg; /* optional [B]: the triples actually used */
+    float lr;              /* SGD step size                                   */
+    float reg;             /* per-occurrence L2 (0 = the reference's loss)    */
+    int32_t sink;          /* B200REC_SINK_*                                  */
+    int32_t flags;         /* B200REC_F_*                                     */
+    float *stage;          /* SINK_STAGE: [B,3,ld] fp32                       */
+    float *gU, *gV;        /* SINK_GRAD: dense [num_users,ld], [num_items,ld] (caller zeroes) */
+    double *loss_sum;      /* optional device scalar, += sum_b -log sigmoid(x_b) */
+    float *x_out;          /* optional [B]: x_b = s(u,i) - s(u,j)             */
+} b200rec_bpr_args;
+
+/* models/MF.py:63-68 (zero_grad -> process_one_batch -> backward -> step) as ONE
+ * kernel: [sample] -> gather 3 rows -> warp dot pair -> g=-sigmoid(-x)/B ->
+ * scatter.  With SINK_UPDATE duplicates inside a batch see each other's partial
+ * updates (Hogwild inside a step); SINK_STAGE + b200rec_bpr_apply reproduces
+ * autograd's "all gradients from pre-step weights" semantics exactly. */
+int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream);
+
+/* data/generators.py:168-201 on the device, sampling only: for each users[t] draw
+ * (pos, neg) with the same counter RNG the fused step uses for (seed, step, t).
+ * out_pos[t] = out_neg[t] = -1 for users without positives. */
+int b200rec_sample_triples(const int32_t *users, int B, const int64_t *csr_indptr,
+                           const int32_t *csr_indices, int num_items, uint64_t seed, uint64_t step,
+                           int32_t *out_pos, int32_t *out_neg, void *stream);
+
+/* second phase of the exact step: W[row] += stage rows (vector atomics). */
+int b200rec_bpr_apply(float *U, float *V, int ld, const int32_t *users, const int32_t *pos,
+                      const int32_t *neg, int B, const float *stage, void *stream);
+
+/* dense SGD / Adam sweeps: torch.optim.SGD(lr) and torch.optim.Adam(lr, betas,
+ * eps, weight_decay=0) as constructed at models/MF.py:30 - every element moves. */
+int b200rec_sgd_dense(float *param, const float *grad, int64_t n, float lr, void *stream);
+int b200rec_adam_dense(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                       int64_t n, float lr, float beta1, float beta2, float eps, int step,
+                       void *stream);
+
+/* Scoring algorithms */
+#define B200REC_SCORE_EXACT 0 /* fp32 FMA chain in k order on CUDA cores (bit-exact vs oracle) */
+#define B200REC_SCORE_TC 1    /* tcgen05 bf16 candidate pass + exact fp32 re-rank               */
+
+/* models/MF.py:109-132 + func.h:12-31 fused: for each of n_users users,
+ * S = U[user] . V^T over all items, -inf at the user's mask row (train
+ * positives), top-k by (score desc, id asc).  out_idx int32 [n_users,k],
+ * out_score fp32 [n_users,k] (may be NULL).  mask CSR is indexed by user id and
+ * may be NULL.  workspace: device scratch of at least
+ * b200rec_score_topk_workspace() bytes. */
+int64_t b200rec_score_topk_workspace(int n_users, int num_items, int d, int k, int algo);
+int b200rec_score_topk(const float *U, const float *V, int ld, int d, const int32_t *users,
+                       int n_users, int num_items, const int64_t *mask_indptr,
+                       const int32_t *mask_indices, int k, int32_t *out_idx, float *out_score,
+                       void *workspace, int64_t workspace_bytes, int algo, void *stream);
+
+/* models/MF.py:109-130 for the dense predict() contract (small U only):
+ * out fp32 [n_users, num_items] = U[users] @ V^T with -inf at mask nonzeros. */
+int b200rec_predict_dense(const float *U, const float *V, int ld, int d, const int32_t *users,
+                          int n_users, int num_items, const int64_t *mask_indptr,
+                          const int32_t *mask_indices, float *out, void *stream);
+
+/* device-resident form of c_top_k_array_index (func.h:22-31) */
+int b200rec_topk_rows(const float *scores, int64_t row_stride, int rows, int cols, int k,
+                      int32_t *out_idx, void *stream);
+
+/* device-resident forms of evaluate_holdout / evaluate_loo.  truth CSR rows are
+ * addressed by row_ids[r] (or r when row_ids is NULL); indices need not be sorted.
+ * Ks: HOST array.  out: device fp32 [n, 3*K_len] / [n, 2*K_len]. */
+int b200rec_holdout_metrics(const int32_t *topk, int n, int max_k, const int32_t *row_ids,
+                            const int64_t *truth_indptr, const int32_t *truth_indices,
+                            const int *Ks, int K_len, float *out, void *stream);
+int b200rec_loo_metrics(const int32_t *topk, int n, int max_k, const int32_t *row_ids,
+                        const int64_t *truth_indptr, const int32_t *truth_indices,
+                        const int *Ks, int K_len, float *out, void *stream);
+/* utils/stats.py:29-32 column means of an fp32 [n, cols] device matrix -> out_host[cols] */
+int b200rec_column_means(const float *mat, int64_t n, int cols, double *out_host, void *stream);
+
+/* models/LightGCN.py:196 one propagation layer Y = A X for CSR A (fp32 values),
+ * optionally accumulating acc += scale * Y (the running layer mean of :198-200). */
+int b200rec_spmm_csr(const int64_t *indptr, const int32_t *indices, const float *values,
+                     int n_rows, const float *X, int ldx, int d, float *Y, int ldy, float *acc,
+                     int ldacc, float acc_scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REC_H */

@@ -1,0 +1,119 @@
+"""ctypes binding of libb200rec.so (include/b200rec.h).
+
+The library is the product; there is NO fallback: importing the engine without
+the built shared object, or calling it without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200rec.so")
+
+OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
+SINK_UPDATE, SINK_STAGE, SINK_GRAD, SINK_NONE = 0, 1, 2, 3
+F_USERS_UNIQUE, F_TMA_GATHER = 1, 2
+SCORE_EXACT, SCORE_TC = 0, 1
+
+
+class B200RecError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libb200rec error {code}: {msg}")
+        self.code = code
+
+
+class BprArgs(C.Structure):
+    """struct b200rec_bpr_args (include/b200rec.h)."""
+    _fields_ = [
+        ("U", C.c_void_p), ("V", C.c_void_p),
+        ("ld", C.c_int32), ("d", C.c_int32),
+        ("num_users", C.c_int32), ("num_items", C.c_int32),
+        ("users", C.c_void_p), ("pos", C.c_void_p), ("neg", C.c_void_p),
+        ("B", C.c_int32),
+        ("csr_indptr", C.c_void_p), ("csr_indices", C.c_void_p),
+        ("seed", C.c_uint64), ("step", C.c_uint64),
+        ("out_pos", C.c_void_p), ("out_neg", C.c_void_p),
+        ("lr", C.c_float), ("reg", C.c_float),
+        ("sink", C.c_int32), ("flags", C.c_int32),
+        ("stage", C.c_void_p), ("gU", C.c_void_p), ("gV", C.c_void_p),
+        ("loss_sum", C.c_void_p), ("x_out", C.c_void_p),
+    ]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_PROTOS = {
+    "b200rec_last_error": (C.c_char_p, []),
+    "b200rec_version": (_I, []),
+    "b200rec_launch_count": (_L, []),
+    "b200rec_top_k_array_index": (_I, [_P, _I, _I, _I, _P]),
+    "b200rec_evaluate_holdout": (_I, [_I, _P, _I, _P, _I, _P, _P, _P]),
+    "b200rec_evaluate_loo": (_I, [_I, _P, _I, _P, _I, _P, _P]),
+    "b200rec_mf_forward": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P]),
+    "b200rec_bpr_step": (_I, [C.POINTER(BprArgs), _P]),
+    "b200rec_sample_triples": (_I, [_P, _I, _P, _P, _I, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "b200rec_bpr_apply": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _P]),
+    "b200rec_sgd_dense": (_I, [_P, _P, _L, _F, _P]),
+    "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
+    "b200rec_score_topk_workspace": (_L, [_I, _I, _I, _I, _I]),
+    "b200rec_score_topk": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _P, _P, _L, _I, _P]),
+    "b200rec_predict_dense": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P, _P, _P]),
+    "b200rec_topk_rows": (_I, [_P, _L, _I, _I, _I, _P, _P]),
+    "b200rec_holdout_metrics": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
+    "b200rec_loo_metrics": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
+    "b200rec_column_means": (_I, [_P, _L, _I, _P, _P]),
+    "b200rec_spmm_csr": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _F, _P]),
+}
+EXPORTS = tuple(_PROTOS)
+
+_lib = None
+
+
+def lib():
+    """The loaded library (loads on first use; raises if it was never built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "recsys_pytorch_b200 has no CPU / PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(handle, name)      # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        raise B200RecError(code, lib().b200rec_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device/host address of a tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, name, dtype=None):
+    import torch
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise B200RecError(ECUDA, f"{name} must be a CUDA tensor: the engine has no CPU path")
+    if dtype is not None and t.dtype != dtype:
+        raise B200RecError(EINVAL, f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise B200RecError(EINVAL, f"{name} must be contiguous")
+    return t
+
+
+def launch_count() -> int:
+    return int(lib().b200rec_launch_count())

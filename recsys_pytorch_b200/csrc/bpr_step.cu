@@ -1,0 +1,552 @@
+// Fused BPR-MF training step for sm_100a.
+//
+// Replaces, as ONE kernel per batch, the reference's
+//   data/generators.py:168-201   negative sampling (uniform over non-positives)
+//   models/MF.py:32-42,99-107    4 embedding gathers, 2 mul+sum, sub/sigmoid/log/mean
+//   models/MF.py:67-68           autograd backward (dense [U,d],[I,d] grads) + optimizer.step
+// with: [counter-RNG sample against the CSR row] -> gather u/i/j rows once ->
+// warp-reduced x = u.(vi-vj) -> g = -sigmoid(-x)/B -> vector-atomic scatter of
+// the three row updates.  The dense gradient is never materialised.
+//
+// Work decomposition: a warp owns a CHUNK of <=32 consecutive triples whose ids
+// live one-per-lane (coalesced id loads / lane-parallel sampling); rows are then
+// processed by sub-groups of G lanes (G*16 B >= row bytes when d <= 128), i.e.
+// 32/G triples at a time, ids broadcast with shuffles.
+//
+// Two gather paths:
+//   LDG  : each lane loads its float4 of the three rows (prefetching the next
+//          triple while the current one is reduced).
+//   TMA  : warp-private ring of shared-memory stages filled by cp.async.bulk
+//          (UBLKCP) row copies that complete on a warp-private mbarrier - no CTA
+//          level synchronisation at all; many rows in flight per warp.
+#include <string.h>
+#include "common.cuh"
+
+namespace b200 {
+
+struct BprParams {
+    b200rec_bpr_args a;
+    float invB;
+    int chunk;       // triples per warp-chunk (multiple of 32/G, <= 32)
+    int64_t n_chunks;
+};
+
+__device__ __forceinline__ float softplus_neg(float x) {  // -log(sigmoid(x)) = log(1+exp(-x)), stable
+    return x > 0.f ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+}
+
+// lane-parallel triple fetch / on-device sampling (data/generators.py:168-201 semantics:
+// positive uniform in the user's CSR row, negative uniform over non-positives)
+__device__ __forceinline__ void fetch_triple(const b200rec_bpr_args &a, int64_t t, bool &valid, int &u, int &i,
+                                             int &j) {
+    u = i = j = 0;
+    if (!valid) return;
+    u = a.users[t];
+    const bool sample_pos = (a.pos == nullptr), sample_neg = (a.neg == nullptr);
+    if (!sample_pos) i = a.pos[t];
+    if (!sample_neg) j = a.neg[t];
+    if (sample_pos || sample_neg) {
+        const int64_t lo = a.csr_indptr[u], hi = a.csr_indptr[u + 1];
+        const uint32_t deg = (uint32_t)(hi - lo);
+        if (deg == 0 && sample_pos) {
+            valid = false;  // generators.py:186-189: a user without positives emits no triple
+        } else {
+            const int32_t *row = a.csr_indices + lo;
+            if (sample_pos) i = row[(uint32_t)(((uint64_t)rng_u32(a.seed, a.step, (uint64_t)t, 0) * deg) >> 32)];
+            if (sample_neg) {
+                for (uint32_t tries = 0; tries < 64; ++tries) {
+                    j = (int)(((uint64_t)rng_u32(a.seed, a.step, (uint64_t)t, 1 + tries) *
+                               (uint64_t)(uint32_t)a.num_items) >> 32);
+                    uint32_t l = 0, r = deg;  // lower_bound in the sorted row
+                    while (l < r) {
+                        uint32_t m = (l + r) >> 1;
+                        if (row[m] < j) l = m + 1; else r = m;
+                    }
+                    if (!(l < deg && row[l] == j)) break;
+                }
+            }
+        }
+        if (a.out_pos) a.out_pos[t] = valid ? i : -1;
+        if (a.out_neg) a.out_neg[t] = valid ? j : -1;
+    }
+}
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// scatter of one float4 column-chunk of the three rows of a triple
+template <int SINK>
+__device__ __forceinline__ void sink_chunk(const b200rec_bpr_args &a, int64_t t, int tu, int ti, int tj, int q,
+                                           float g, float regB, float4 ru, float4 ri, float4 rj, bool uniq) {
+    const float sc = (SINK == B200REC_SINK_GRAD) ? 1.f : -a.lr;
+    float4 du, di, dj;
+    du.x = sc * fmaf(g, ri.x - rj.x, regB * ru.x); du.y = sc * fmaf(g, ri.y - rj.y, regB * ru.y);
+    du.z = sc * fmaf(g, ri.z - rj.z, regB * ru.z); du.w = sc * fmaf(g, ri.w - rj.w, regB * ru.w);
+    di.x = sc * fmaf(g, ru.x, regB * ri.x); di.y = sc * fmaf(g, ru.y, regB * ri.y);
+    di.z = sc * fmaf(g, ru.z, regB * ri.z); di.w = sc * fmaf(g, ru.w, regB * ri.w);
+    dj.x = sc * fmaf(-g, ru.x, regB * rj.x); dj.y = sc * fmaf(-g, ru.y, regB * rj.y);
+    dj.z = sc * fmaf(-g, ru.z, regB * rj.z); dj.w = sc * fmaf(-g, ru.w, regB * rj.w);
+    const int64_t ld = a.ld;
+    if (SINK == B200REC_SINK_UPDATE) {
+        float *pu = a.U + (int64_t)tu * ld + q * 4;
+        if (uniq) st4(pu, make_float4(ru.x + du.x, ru.y + du.y, ru.z + du.z, ru.w + du.w));
+        else red4(pu, du);
+        red4(a.V + (int64_t)ti * ld + q * 4, di);
+        red4(a.V + (int64_t)tj * ld + q * 4, dj);
+    } else if (SINK == B200REC_SINK_STAGE) {
+        float *s = a.stage + (t * 3) * ld + q * 4;
+        st4(s, du); st4(s + ld, di); st4(s + 2 * ld, dj);
+    } else if (SINK == B200REC_SINK_GRAD) {
+        red4(a.gU + (int64_t)tu * ld + q * 4, du);
+        red4(a.gV + (int64_t)ti * ld + q * 4, di);
+        red4(a.gV + (int64_t)tj * ld + q * 4, dj);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// LDG gather path
+// ---------------------------------------------------------------------------
+template <int G, int CPL, int SINK>
+__global__ void __launch_bounds__(256) bpr_step_ldg_kernel(const BprParams p) {
+    const b200rec_bpr_args &a = p.a;
+    constexpr int TPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % G, sg = lane / G;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int d4 = a.ld >> 2;
+    const int64_t ld = a.ld;
+    const float regB = a.reg * p.invB;
+    const bool uniq = (a.flags & B200REC_F_USERS_UNIQUE) != 0;
+    const int iters = p.chunk / TPW;
+    float loss_local = 0.f;
+
+    for (int64_t c = warp_global; c < p.n_chunks; c += n_warps) {
+        const int64_t t_lane = c * p.chunk + lane;
+        bool valid = (lane < p.chunk) && (t_lane < a.B);
+        int u, i, j;
+        fetch_triple(a, t_lane, valid, u, i, j);
+
+        float4 nu[CPL], ni[CPL], nj[CPL];
+        int tu, ti, tj, tv;
+        auto issue = [&](int it) {
+            const int src = it * TPW + sg;
+            tu = __shfl_sync(0xffffffffu, u, src);
+            ti = __shfl_sync(0xffffffffu, i, src);
+            tj = __shfl_sync(0xffffffffu, j, src);
+            tv = __shfl_sync(0xffffffffu, (int)valid, src);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int q = sl + k * G;
+                if (tv && q < d4) {
+                    nu[k] = ld4(a.U + (int64_t)tu * ld + q * 4);
+                    ni[k] = ld4(a.V + (int64_t)ti * ld + q * 4);
+                    nj[k] = ld4(a.V + (int64_t)tj * ld + q * 4);
+                } else {
+                    nu[k] = ni[k] = nj[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        issue(0);
+        for (int it = 0; it < iters; ++it) {
+            float4 ru[CPL], ri[CPL], rj[CPL];
+            const int cu = tu, ci = ti, cj = tj, cv = tv;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) { ru[k] = nu[k]; ri[k] = ni[k]; rj[k] = nj[k]; }
+            if (it + 1 < iters) issue(it + 1);  // next triple's rows in flight while this one reduces
+            float part = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                part = fmaf(ru[k].x, ri[k].x - rj[k].x, part);
+                part = fmaf(ru[k].y, ri[k].y - rj[k].y, part);
+                part = fmaf(ru[k].z, ri[k].z - rj[k].z, part);
+                part = fmaf(ru[k].w, ri[k].w - rj[k].w, part);
+            }
+            const float x = group_sum<G>(part);
+            const float g = -p.invB / (1.f + expf(x));  // -sigmoid(-x)/B
+            const int64_t t = c * p.chunk + it * TPW + sg;
+            if (cv) {
+                if (sl == 0) {
+                    if (a.loss_sum) loss_local += softplus_neg(x);
+                    if (a.x_out) a.x_out[t] = x;
+                }
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int q = sl + k * G;
+                    if (q < d4) sink_chunk<SINK>(a, t, cu, ci, cj, q, g, regB, ru[k], ri[k], rj[k], uniq);
+                }
+            }
+        }
+    }
+    if (a.loss_sum) {
+        loss_local = group_sum<32>(loss_local);
+        if (lane == 0 && loss_local != 0.f) atomicAdd(a.loss_sum, (double)loss_local);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA (cp.async.bulk) gather path: warp-private stage ring + mbarriers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+constexpr int kTmaWarps = 8;   // warps per CTA
+constexpr int kTmaStages = 8;  // stages per warp
+
+template <int G, int CPL, int SINK>
+__global__ void __launch_bounds__(kTmaWarps * 32) bpr_step_tma_kernel(const BprParams p) {
+    const b200rec_bpr_args &a = p.a;
+    constexpr int TPW = 32 / G;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sl = lane % G, sg = lane / G;
+    const int64_t ld = a.ld;
+    const int d4 = a.ld >> 2;
+    const uint32_t row_bytes = (uint32_t)a.ld * 4u;
+    const uint32_t stage_bytes = row_bytes * 3u * TPW;
+    // layout: [warps][stages] mbarriers (8 B each) then [warps][stages][TPW][3][ld] floats
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + wid * kTmaStages;
+    const uint32_t data_off = (uint32_t)(kTmaWarps * kTmaStages * 8);
+    float *wdata = reinterpret_cast<float *>(smem_raw + data_off + (size_t)wid * kTmaStages * stage_bytes);
+    if (lane < kTmaStages) mbar_init(smem_u32(bars + lane), TPW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    const int64_t warp_global = (int64_t)blockIdx.x * kTmaWarps + wid;
+    const int64_t n_warps = (int64_t)gridDim.x * kTmaWarps;
+    const float regB = a.reg * p.invB;
+    const bool uniq = (a.flags & B200REC_F_USERS_UNIQUE) != 0;
+    const int iters = p.chunk / TPW;
+    float loss_local = 0.f;
+    uint32_t n_consumed = 0;  // running stage counter -> slot and phase parity
+
+    for (int64_t c = warp_global; c < p.n_chunks; c += n_warps) {
+        const int64_t t_lane = c * p.chunk + lane;
+        bool valid = (lane < p.chunk) && (t_lane < a.B);
+        int u, i, j;
+        fetch_triple(a, t_lane, valid, u, i, j);
+
+        // the sub-group leader (sl==0) of triple-slot sg issues that triple's three row copies
+        auto issue = [&](int it, uint32_t n_slot) {
+            const int src = it * TPW + sg;
+            const int tu = __shfl_sync(0xffffffffu, u, src);
+            const int ti = __shfl_sync(0xffffffffu, i, src);
+            const int tj = __shfl_sync(0xffffffffu, j, src);
+            if (sl == 0) {
+                const uint32_t slot = n_slot % kTmaStages;
+                const uint32_t bar = smem_u32(bars + slot);
+                const uint32_t dst = smem_u32(wdata) + slot * stage_bytes + (uint32_t)sg * 3u * row_bytes;
+                mbar_expect_tx(bar, 3u * row_bytes);
+                bulk_g2s(dst, a.U + (int64_t)tu * ld, row_bytes, bar);
+                bulk_g2s(dst + row_bytes, a.V + (int64_t)ti * ld, row_bytes, bar);
+                bulk_g2s(dst + 2u * row_bytes, a.V + (int64_t)tj * ld, row_bytes, bar);
+            }
+        };
+        const int pre = iters < kTmaStages ? iters : kTmaStages;
+        for (int it = 0; it < pre; ++it) issue(it, n_consumed + it);
+
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t slot = n_consumed % kTmaStages;
+            const uint32_t parity = (n_consumed / kTmaStages) & 1u;
+            const int src = it * TPW + sg;
+            const int cu = __shfl_sync(0xffffffffu, u, src);
+            const int ci = __shfl_sync(0xffffffffu, i, src);
+            const int cj = __shfl_sync(0xffffffffu, j, src);
+            const int cv = __shfl_sync(0xffffffffu, (int)valid, src);
+            mbar_wait(smem_u32(bars + slot), parity);
+            const float *st = wdata + (size_t)slot * (stage_bytes / 4) + (size_t)sg * 3 * ld;
+            float4 ru[CPL], ri[CPL], rj[CPL];
+            float part = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int q = sl + k * G;
+                if (q < d4) {
+                    ru[k] = ld4(st + q * 4); ri[k] = ld4(st + ld + q * 4); rj[k] = ld4(st + 2 * ld + q * 4);
+                } else {
+                    ru[k] = ri[k] = rj[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                part = fmaf(ru[k].x, ri[k].x - rj[k].x, part);
+                part = fmaf(ru[k].y, ri[k].y - rj[k].y, part);
+                part = fmaf(ru[k].z, ri[k].z - rj[k].z, part);
+                part = fmaf(ru[k].w, ri[k].w - rj[k].w, part);
+            }
+            const float x = group_sum<G>(part);  // every lane's smem reads are complete after this exchange
+            ++n_consumed;
+            __syncwarp();
+            if (it + kTmaStages < iters) issue(it + kTmaStages, n_consumed - 1 + kTmaStages);  // refill this slot
+            const float g = -p.invB / (1.f + expf(x));
+            const int64_t t = c * p.chunk + it * TPW + sg;
+            if (cv) {
+                if (sl == 0) {
+                    if (a.loss_sum) loss_local += softplus_neg(x);
+                    if (a.x_out) a.x_out[t] = x;
+                }
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int q = sl + k * G;
+                    if (q < d4) sink_chunk<SINK>(a, t, cu, ci, cj, q, g, regB, ru[k], ri[k], rj[k], uniq);
+                }
+            }
+        }
+    }
+    if (a.loss_sum) {
+        loss_local = group_sum<32>(loss_local);
+        if (lane == 0 && loss_local != 0.f) atomicAdd(a.loss_sum, (double)loss_local);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// second phase of the exact step, forward, dense optimisers
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bpr_apply_kernel(float *U, float *V, int ld, const int32_t *users,
+                                                        const int32_t *pos, const int32_t *neg, int B,
+                                                        const float *stage) {
+    const int d4 = ld >> 2;
+    const int64_t total = (int64_t)B * 3 * d4;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(e % d4);
+        const int64_t rowi = e / d4;
+        const int r = (int)(rowi % 3);
+        const int64_t t = rowi / 3;
+        float *dst = (r == 0) ? U + (int64_t)users[t] * ld : V + (int64_t)((r == 1) ? pos[t] : neg[t]) * ld;
+        red4(dst + q * 4, ld4(stage + rowi * ld + q * 4));
+    }
+}
+
+// sampling only (same draws as the fused kernel for the same (seed, step, t))
+__global__ void __launch_bounds__(256) sample_triples_kernel(const b200rec_bpr_args a) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.B; t += (int64_t)gridDim.x * blockDim.x) {
+        bool valid = true;
+        int u, i, j;
+        fetch_triple(a, t, valid, u, i, j);
+    }
+}
+
+__global__ void __launch_bounds__(256) mf_forward_kernel(const float *U, const float *V, int ld, int d,
+                                                         const int32_t *users, const int32_t *items, int n,
+                                                         float *out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int d4 = ld >> 2;
+    for (int64_t t = w; t < n; t += nw) {
+        const float *pu = U + (int64_t)users[t] * ld, *pv = V + (int64_t)items[t] * ld;
+        float acc = 0.f;
+        for (int q = lane; q < d4; q += 32) {
+            const float4 x = ld4(pu + q * 4), y = ld4(pv + q * 4);
+            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+        }
+        acc = group_sum<32>(acc);
+        if (lane == 0) out[t] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) sgd_dense_kernel(float *p, const float *g, int64_t n, float lr) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        p[e] = p[e] - lr * g[e];
+}
+
+// torch.optim.Adam single-tensor update (no amsgrad, no weight decay, not maximize):
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adam_dense_kernel(float *p, const float *g, float *m, float *v, int64_t n,
+                                                         float b1, float b2, float eps, float step_size,
+                                                         float bc2_sqrt) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const float gg = g[e];
+        const float mm = m[e] * b1 + (1.f - b1) * gg;              // lerp form used by torch: m + (g-m)*(1-b1)
+        const float vv = v[e] * b2 + (1.f - b2) * gg * gg;
+        m[e] = mm; v[e] = vv;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        p[e] = p[e] - step_size * (mm / denom);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+template <int G, int CPL>
+static int launch_bpr(const BprParams &p, cudaStream_t s) {
+    const bool tma = (p.a.flags & B200REC_F_TMA_GATHER) != 0;
+    const int sms = sm_count();
+    constexpr int TPW = 32 / G;
+#define B200_LAUNCH_SINK(SINKV)                                                                              \
+    if (tma) {                                                                                               \
+        auto kern = bpr_step_tma_kernel<G, CPL, SINKV>;                                                      \
+        const size_t smem = (size_t)kTmaWarps * kTmaStages * (8 + (size_t)p.a.ld * 4 * 3 * TPW);             \
+        B200_REQUIRE(smem <= 227 * 1024, B200REC_EUNSUPPORTED, "bpr_step TMA path: row too large (ld=%d)",   \
+                     p.a.ld);                                                                                \
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        int occ = 0;                                                                                         \
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTmaWarps * 32, smem));          \
+        if (occ < 1) occ = 1;                                                                                \
+        int64_t need = (p.n_chunks + kTmaWarps - 1) / kTmaWarps;                                             \
+        int grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);                             \
+        if (grid < 1) grid = 1;                                                                              \
+        kern<<<grid, kTmaWarps * 32, smem, s>>>(p);                                                          \
+    } else {                                                                                                 \
+        auto kern = bpr_step_ldg_kernel<G, CPL, SINKV>;                                                      \
+        int occ = 0;                                                                                         \
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));                        \
+        if (occ < 1) occ = 1;                                                                                \
+        int64_t need = (p.n_chunks + 7) / 8;                                                                 \
+        int grid = (int)(need < (int64_t)sms * occ ? need : (int64_t)sms * occ);                             \
+        if (grid < 1) grid = 1;                                                                              \
+        kern<<<grid, 256, 0, s>>>(p);                                                                        \
+    }
+    switch (p.a.sink) {
+        case B200REC_SINK_UPDATE: { B200_LAUNCH_SINK(B200REC_SINK_UPDATE) } break;
+        case B200REC_SINK_STAGE: { B200_LAUNCH_SINK(B200REC_SINK_STAGE) } break;
+        case B200REC_SINK_GRAD: { B200_LAUNCH_SINK(B200REC_SINK_GRAD) } break;
+        default: { B200_LAUNCH_SINK(B200REC_SINK_NONE) } break;
+    }
+#undef B200_LAUNCH_SINK
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
+    B200_REQUIRE(args != nullptr, B200REC_EINVAL, "bpr_step: args is NULL");
+    const b200rec_bpr_args &a = *args;
+    B200_REQUIRE(a.U && a.V && a.users, B200REC_EINVAL, "bpr_step: U, V and users are required");
+    B200_REQUIRE(a.B >= 0 && a.d >= 1 && a.ld >= a.d && (a.ld % 4) == 0 && a.ld <= 512, B200REC_EINVAL,
+                 "bpr_step: need 1 <= d <= ld <= 512, ld %% 4 == 0 (d=%d ld=%d)", a.d, a.ld);
+    B200_REQUIRE(((uintptr_t)a.U % 16) == 0 && ((uintptr_t)a.V % 16) == 0, B200REC_EINVAL,
+                 "bpr_step: tables must be 16-byte aligned");
+    B200_REQUIRE((a.pos && a.neg) || (a.csr_indptr && a.csr_indices && a.num_items > 0), B200REC_EINVAL,
+                 "bpr_step: on-device sampling needs the CSR of positives");
+    B200_REQUIRE(a.sink >= 0 && a.sink <= 3, B200REC_EINVAL, "bpr_step: bad sink %d", a.sink);
+    B200_REQUIRE(a.sink != B200REC_SINK_STAGE || a.stage, B200REC_EINVAL, "bpr_step: SINK_STAGE needs stage");
+    B200_REQUIRE(a.sink != B200REC_SINK_GRAD || (a.gU && a.gV), B200REC_EINVAL, "bpr_step: SINK_GRAD needs gU,gV");
+    if (a.B == 0) return B200REC_OK;
+
+    const int d4 = a.ld / 4;
+    int G = 1;
+    while (G < d4 && G < 32) G <<= 1;
+    const int CPL = (d4 + G - 1) / G;
+    const int TPW = 32 / G;
+    BprParams p;
+    p.a = a;
+    p.invB = 1.0f / (float)a.B;
+    // chunk: as large as 32 triples, shrunk (to a multiple of TPW) until every warp slot has work
+    const int64_t slots = (int64_t)sm_count() * 48;
+    int chunk = 32;
+    while (chunk > TPW && chunk > 4 && ((int64_t)a.B + chunk - 1) / chunk < slots) chunk >>= 1;
+    if (chunk < TPW) chunk = TPW;
+    p.chunk = chunk;
+    p.n_chunks = ((int64_t)a.B + chunk - 1) / chunk;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (G) {
+        case 1: return launch_bpr<1, 1>(p, s);
+        case 2: return launch_bpr<2, 1>(p, s);
+        case 4: return launch_bpr<4, 1>(p, s);
+        case 8: return launch_bpr<8, 1>(p, s);
+        case 16: return launch_bpr<16, 1>(p, s);
+        default:
+            switch (CPL) {
+                case 1: return launch_bpr<32, 1>(p, s);
+                case 2: return launch_bpr<32, 2>(p, s);
+                case 3: return launch_bpr<32, 3>(p, s);
+                default: return launch_bpr<32, 4>(p, s);
+            }
+    }
+}
+
+extern "C" int b200rec_bpr_apply(float *U, float *V, int ld, const int32_t *users, const int32_t *pos,
+                                 const int32_t *neg, int B, const float *stage, void *stream) {
+    B200_REQUIRE(U && V && users && pos && neg && stage, B200REC_EINVAL, "bpr_apply: null argument");
+    B200_REQUIRE(ld > 0 && ld % 4 == 0, B200REC_EINVAL, "bpr_apply: ld %% 4 != 0");
+    if (B <= 0) return B200REC_OK;
+    const int64_t total = (int64_t)B * 3 * (ld / 4);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    bpr_apply_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(U, V, ld, users, pos, neg,
+                                                                                           B, stage);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+extern "C" int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int32_t *users,
+                                  const int32_t *items, int n, float *out, void *stream) {
+    B200_REQUIRE(U && V && users && items && out, B200REC_EINVAL, "mf_forward: null argument");
+    B200_REQUIRE(d >= 1 && ld >= d && ld % 4 == 0, B200REC_EINVAL, "mf_forward: bad d/ld");
+    if (n <= 0) return B200REC_OK;
+    int64_t blocks = ((int64_t)n + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    mf_forward_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(U, V, ld, d, users, items,
+                                                                                            n, out);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+extern "C" int b200rec_sgd_dense(float *param, const float *grad, int64_t n, float lr, void *stream) {
+    B200_REQUIRE(param && grad, B200REC_EINVAL, "sgd_dense: null argument");
+    if (n <= 0) return B200REC_OK;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    sgd_dense_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(param, grad, n, lr);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+extern "C" int b200rec_adam_dense(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
+                                  float lr, float beta1, float beta2, float eps, int step, void *stream) {
+    B200_REQUIRE(param && grad && exp_avg && exp_avg_sq, B200REC_EINVAL, "adam_dense: null argument");
+    B200_REQUIRE(step >= 1, B200REC_EINVAL, "adam_dense: step counts from 1");
+    if (n <= 0) return B200REC_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    adam_dense_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, (float)((double)lr / bc1), (float)sqrt(bc2));
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+extern "C" int b200rec_sample_triples(const int32_t *users, int B, const int64_t *csr_indptr,
+                                      const int32_t *csr_indices, int num_items, uint64_t seed, uint64_t step,
+                                      int32_t *out_pos, int32_t *out_neg, void *stream) {
+    B200_REQUIRE(users && csr_indptr && csr_indices && out_pos && out_neg && num_items > 0, B200REC_EINVAL,
+                 "sample_triples: null argument");
+    if (B <= 0) return B200REC_OK;
+    b200rec_bpr_args a;
+    memset(&a, 0, sizeof(a));
+    a.users = users; a.B = B; a.csr_indptr = csr_indptr; a.csr_indices = csr_indices; a.num_items = num_items;
+    a.seed = seed; a.step = step; a.out_pos = out_pos; a.out_neg = out_neg;
+    int64_t blocks = ((int64_t)B + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    sample_triples_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}

@@ -1,0 +1,115 @@
+// CSR SpMM for LightGCN propagation (sm_100a):  Y = A X,  acc += scale * Y.
+//
+// Replaces models/LightGCN.py:196 `torch.sparse.mm(g_droped, all_emb)` (cuSPARSE
+// COO SpMM) and the stack+mean of :198-200 (fused here as a running accumulation).
+// HBM-bound gather: one sub-group of G lanes per output row (G*16 B >= row bytes
+// when d <= 128); (col,val) pairs are loaded coalesced by the sub-group and
+// broadcast with shuffles; 4 neighbour rows in flight per lane.
+#include "common.cuh"
+
+namespace b200 {
+
+template <int G, int CPL>
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const int64_t *__restrict__ indptr,
+                                                       const int32_t *__restrict__ indices,
+                                                       const float *__restrict__ values, int n_rows,
+                                                       const float *__restrict__ X, int ldx, int d4,
+                                                       float *__restrict__ Y, int ldy, float *__restrict__ acc,
+                                                       int ldacc, float acc_scale) {
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % G, sg = lane / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sg * G));
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t rb = warp_global * RPW; rb < n_rows; rb += n_warps * RPW) {
+        const int64_t row = rb + sg;
+        if (row >= n_rows) continue;  // whole sub-group leaves together
+        const int64_t start = indptr[row], end = indptr[row + 1];
+        float4 a[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t base = start; base < end; base += G) {
+            const int64_t mp = base + sl;
+            int c = 0;
+            float v = 0.f;
+            if (mp < end) { c = indices[mp]; v = values[mp]; }
+            const int cnt = (int)((end - base) < G ? (end - base) : G);
+            for (int t = 0; t < cnt; ++t) {
+                const int cc = __shfl_sync(gmask, c, sg * G + t);
+                const float vv = __shfl_sync(gmask, v, sg * G + t);
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int q = sl + k * G;
+                    if (q < d4) {
+                        const float4 x = ld4(X + (int64_t)cc * ldx + q * 4);
+                        a[k].x = fmaf(vv, x.x, a[k].x); a[k].y = fmaf(vv, x.y, a[k].y);
+                        a[k].z = fmaf(vv, x.z, a[k].z); a[k].w = fmaf(vv, x.w, a[k].w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const int q = sl + k * G;
+            if (q < d4) {
+                if (Y) st4(Y + row * ldy + q * 4, a[k]);
+                if (acc) {
+                    float *pa = acc + row * ldacc + q * 4;
+                    float4 o = ld4(pa);
+                    o.x = fmaf(acc_scale, a[k].x, o.x); o.y = fmaf(acc_scale, a[k].y, o.y);
+                    o.z = fmaf(acc_scale, a[k].z, o.z); o.w = fmaf(acc_scale, a[k].w, o.w);
+                    st4(pa, o);
+                }
+            }
+        }
+    }
+}
+
+template <int G, int CPL>
+static int launch_spmm(const int64_t *indptr, const int32_t *indices, const float *values, int n_rows, const float *X,
+                       int ldx, int d4, float *Y, int ldy, float *acc, int ldacc, float sc, cudaStream_t s) {
+    constexpr int RPW = 32 / G;
+    int64_t blocks = ((int64_t)n_rows + 8 * RPW - 1) / (8 * RPW);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    spmm_csr_kernel<G, CPL><<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(indptr, indices, values, n_rows, X, ldx,
+                                                                               d4, Y, ldy, acc, ldacc, sc);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200rec_spmm_csr(const int64_t *indptr, const int32_t *indices, const float *values, int n_rows,
+                                const float *X, int ldx, int d, float *Y, int ldy, float *acc, int ldacc,
+                                float acc_scale, void *stream) {
+    B200_REQUIRE(indptr && indices && values && X && (Y || acc), B200REC_EINVAL, "spmm_csr: null argument");
+    B200_REQUIRE(d >= 1 && ldx >= d && ldx % 4 == 0 && ldx <= 512, B200REC_EINVAL, "spmm_csr: bad d/ldx");
+    B200_REQUIRE((!Y || (ldy >= d && ldy % 4 == 0)) && (!acc || (ldacc >= d && ldacc % 4 == 0)), B200REC_EINVAL,
+                 "spmm_csr: bad ldy/ldacc");
+    B200_REQUIRE(X != Y, B200REC_EINVAL, "spmm_csr: in-place propagation is not supported");
+    if (n_rows <= 0) return B200REC_OK;
+    const int d4 = (d + 3) / 4;
+    int G = 1;
+    while (G < d4 && G < 32) G <<= 1;
+    const int CPL = (d4 + G - 1) / G;
+    cudaStream_t s = (cudaStream_t)stream;
+#define B200_SPMM(GG, CC) return launch_spmm<GG, CC>(indptr, indices, values, n_rows, X, ldx, d4, Y, ldy, acc, ldacc, acc_scale, s)
+    switch (G) {
+        case 1: B200_SPMM(1, 1);
+        case 2: B200_SPMM(2, 1);
+        case 4: B200_SPMM(4, 1);
+        case 8: B200_SPMM(8, 1);
+        case 16: B200_SPMM(16, 1);
+        default:
+            switch (CPL) {
+                case 1: B200_SPMM(32, 1);
+                case 2: B200_SPMM(32, 2);
+                case 3: B200_SPMM(32, 3);
+                default: B200_SPMM(32, 4);
+            }
+    }
+#undef B200_SPMM
+}

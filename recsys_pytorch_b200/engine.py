@@ -1,0 +1,191 @@
+"""Thin tensor-level wrappers over the C ABI (include/b200rec.h).
+
+Everything here takes CUDA tensors, passes raw device pointers + the current
+torch stream to libb200rec.so, and returns CUDA tensors.  PyTorch is used for
+memory and streams only; no torch op computes anything on the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (B200RecError, BprArgs, F_TMA_GATHER, F_USERS_UNIQUE, SCORE_EXACT, SCORE_TC, SINK_GRAD,
+                   SINK_STAGE, SINK_UPDATE, check, current_stream, ptr, require_cuda)
+
+__all__ = ["DeviceCSR", "padded_dim", "alloc_table", "mf_forward", "bpr_step", "bpr_apply", "sample_triples",
+           "sgd_dense", "adam_dense", "score_topk", "predict_dense", "topk_rows", "holdout_metrics", "loo_metrics",
+           "column_means", "spmm_csr"]
+
+
+def padded_dim(d: int) -> int:
+    """Row stride (floats): rows are 16-byte multiples so they move as float4 / TMA bulk."""
+    return (int(d) + 3) // 4 * 4
+
+
+def alloc_table(rows: int, d: int, device, std: float = 1.0, generator=None):
+    """fp32 [rows, ld] storage, N(0, std) in the first d columns (nn.Embedding's
+    default init is N(0,1), models/MF.py:23-24), zeros in the pad columns."""
+    ld = padded_dim(d)
+    store = torch.zeros((rows, ld), dtype=torch.float32, device=device)
+    if std > 0:
+        store[:, :d].normal_(0.0, std, generator=generator)
+    return store
+
+
+class DeviceCSR:
+    """int64 indptr + int32 sorted column indices on the device (implicit 1.0 values)."""
+
+    def __init__(self, indptr, indices, shape):
+        self.indptr = require_cuda(indptr, "indptr", torch.int64)
+        self.indices = require_cuda(indices, "indices", torch.int32)
+        self.shape = (int(shape[0]), int(shape[1]))
+
+    @classmethod
+    def from_scipy(cls, mat, device):
+        mat = mat.tocsr()
+        if not mat.has_sorted_indices:
+            mat = mat.copy()
+            mat.sort_indices()
+        return cls(torch.from_numpy(np.ascontiguousarray(mat.indptr, np.int64)).to(device),
+                   torch.from_numpy(np.ascontiguousarray(mat.indices, np.int32)).to(device), mat.shape)
+
+    @property
+    def nnz(self):
+        return int(self.indices.numel())
+
+
+def _i32(t, name):
+    return require_cuda(t, name, torch.int32)
+
+
+def mf_forward(U, V, d, users, items):
+    """models/MF.py:38-42."""
+    require_cuda(U, "U", torch.float32); require_cuda(V, "V", torch.float32)
+    out = torch.empty(users.numel(), dtype=torch.float32, device=U.device)
+    check(_lib.lib().b200rec_mf_forward(ptr(U), ptr(V), U.shape[1], d, ptr(_i32(users, "users")),
+                                        ptr(_i32(items, "items")), users.numel(), ptr(out), current_stream()))
+    return out
+
+
+def bpr_step(U, V, d, users, pos=None, neg=None, csr: DeviceCSR | None = None, lr=0.0, reg=0.0, sink=SINK_UPDATE,
+             flags=0, seed=0, step=0, loss_sum=None, x_out=None, out_pos=None, out_neg=None, stage=None, gU=None,
+             gV=None):
+    """models/MF.py:63-68 as one fused kernel (see b200rec_bpr_step)."""
+    require_cuda(U, "U", torch.float32); require_cuda(V, "V", torch.float32)
+    a = BprArgs()
+    a.U, a.V, a.ld, a.d = ptr(U), ptr(V), U.shape[1], d
+    a.num_users, a.num_items = U.shape[0], V.shape[0]
+    a.users = ptr(_i32(users, "users"))
+    a.pos = ptr(_i32(pos, "pos")) if pos is not None else None
+    a.neg = ptr(_i32(neg, "neg")) if neg is not None else None
+    a.B = users.numel()
+    if csr is not None:
+        a.csr_indptr, a.csr_indices = ptr(csr.indptr), ptr(csr.indices)
+    a.seed, a.step = int(seed) & (2**64 - 1), int(step) & (2**64 - 1)
+    a.out_pos = ptr(_i32(out_pos, "out_pos")) if out_pos is not None else None
+    a.out_neg = ptr(_i32(out_neg, "out_neg")) if out_neg is not None else None
+    a.lr, a.reg, a.sink, a.flags = float(lr), float(reg), int(sink), int(flags)
+    a.stage = ptr(require_cuda(stage, "stage", torch.float32)) if stage is not None else None
+    a.gU = ptr(require_cuda(gU, "gU", torch.float32)) if gU is not None else None
+    a.gV = ptr(require_cuda(gV, "gV", torch.float32)) if gV is not None else None
+    a.loss_sum = ptr(require_cuda(loss_sum, "loss_sum", torch.float64)) if loss_sum is not None else None
+    a.x_out = ptr(require_cuda(x_out, "x_out", torch.float32)) if x_out is not None else None
+    check(_lib.lib().b200rec_bpr_step(C.byref(a), current_stream()))
+
+
+def bpr_apply(U, V, users, pos, neg, stage):
+    check(_lib.lib().b200rec_bpr_apply(ptr(U), ptr(V), U.shape[1], ptr(_i32(users, "users")), ptr(_i32(pos, "pos")),
+                                       ptr(_i32(neg, "neg")), users.numel(), ptr(stage), current_stream()))
+
+
+def sample_triples(users, csr: DeviceCSR, seed, step):
+    """data/generators.py:168-201 on the device; returns (pos, neg) int32."""
+    users = _i32(users, "users")
+    pos = torch.empty_like(users); neg = torch.empty_like(users)
+    check(_lib.lib().b200rec_sample_triples(ptr(users), users.numel(), ptr(csr.indptr), ptr(csr.indices),
+                                            csr.shape[1], int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
+                                            ptr(pos), ptr(neg), current_stream()))
+    return pos, neg
+
+
+def sgd_dense(param, grad, lr):
+    check(_lib.lib().b200rec_sgd_dense(ptr(param), ptr(grad), param.numel(), float(lr), current_stream()))
+
+
+def adam_dense(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.lib().b200rec_adam_dense(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(),
+                                        float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                        current_stream()))
+
+
+def score_topk(U, V, d, users, mask: DeviceCSR | None, k, algo=SCORE_EXACT, want_scores=True):
+    """models/MF.py:109-132 + func.h:12-31 fused: (idx int32 [n,k], score fp32 [n,k])."""
+    require_cuda(U, "U", torch.float32); require_cuda(V, "V", torch.float32)
+    users = _i32(users, "users")
+    n, ni = users.numel(), V.shape[0]
+    idx = torch.empty((n, k), dtype=torch.int32, device=U.device)
+    sc = torch.empty((n, k), dtype=torch.float32, device=U.device) if want_scores else None
+    ws_bytes = int(_lib.lib().b200rec_score_topk_workspace(n, ni, d, k, algo))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=U.device)
+    check(_lib.lib().b200rec_score_topk(ptr(U), ptr(V), U.shape[1], d, ptr(users), n, ni,
+                                        ptr(mask.indptr) if mask is not None else None,
+                                        ptr(mask.indices) if mask is not None else None, k, ptr(idx), ptr(sc),
+                                        ptr(ws), ws_bytes, algo, current_stream()))
+    return idx, sc
+
+
+def predict_dense(U, V, d, users, mask: DeviceCSR | None):
+    """models/MF.py:109-130 for a chunk of users: fp32 [n, I] with -inf at mask nonzeros."""
+    users = _i32(users, "users")
+    out = torch.empty((users.numel(), V.shape[0]), dtype=torch.float32, device=U.device)
+    check(_lib.lib().b200rec_predict_dense(ptr(U), ptr(V), U.shape[1], d, ptr(users), users.numel(), V.shape[0],
+                                           ptr(mask.indptr) if mask is not None else None,
+                                           ptr(mask.indices) if mask is not None else None, ptr(out),
+                                           current_stream()))
+    return out
+
+
+def topk_rows(scores, k):
+    scores = require_cuda(scores, "scores", torch.float32)
+    out = torch.empty((scores.shape[0], k), dtype=torch.int32, device=scores.device)
+    check(_lib.lib().b200rec_topk_rows(ptr(scores), scores.shape[1], scores.shape[0], scores.shape[1], k, ptr(out),
+                                       current_stream()))
+    return out
+
+
+def _metrics(fn, width, topk, truth: DeviceCSR, ks, row_ids):
+    topk = _i32(topk, "topk")
+    ks_arr = (C.c_int * len(ks))(*[int(k) for k in ks])
+    out = torch.empty((topk.shape[0], width * len(ks)), dtype=torch.float32, device=topk.device)
+    check(fn(ptr(topk), topk.shape[0], topk.shape[1], ptr(_i32(row_ids, "row_ids")) if row_ids is not None else None,
+             ptr(truth.indptr), ptr(truth.indices), ks_arr, len(ks), ptr(out), current_stream()))
+    return out
+
+
+def holdout_metrics(topk, truth: DeviceCSR, ks, row_ids=None):
+    """holdout.h:20-103 on the device: fp32 [n, 3*len(ks)] = [Prec.., Recall.., NDCG..]."""
+    return _metrics(_lib.lib().b200rec_holdout_metrics, 3, topk, truth, ks, row_ids)
+
+
+def loo_metrics(topk, truth: DeviceCSR, ks, row_ids=None):
+    """loo.h:20-85 on the device: fp32 [n, 2*len(ks)] = [HR.., NDCG..]."""
+    return _metrics(_lib.lib().b200rec_loo_metrics, 2, topk, truth, ks, row_ids)
+
+
+def column_means(mat):
+    mat = require_cuda(mat, "mat", torch.float32)
+    out = np.zeros(mat.shape[1], np.float64)
+    check(_lib.lib().b200rec_column_means(ptr(mat), mat.shape[0], mat.shape[1], out.ctypes.data, current_stream()))
+    return out
+
+
+def spmm_csr(indptr, indices, values, X, d, Y=None, acc=None, acc_scale=1.0):
+    """models/LightGCN.py:196: Y = A X (and/or acc += acc_scale * A X)."""
+    n_rows = indptr.numel() - 1
+    check(_lib.lib().b200rec_spmm_csr(ptr(indptr), ptr(indices), ptr(values), n_rows, ptr(X), X.shape[1], d,
+                                      ptr(Y), Y.shape[1] if Y is not None else 0, ptr(acc),
+                                      acc.shape[1] if acc is not None else 0, float(acc_scale), current_stream()))
+    return Y

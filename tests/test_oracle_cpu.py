@@ -1,0 +1,188 @@
+"""`-m "not gpu"`: the oracle is pinned against the golden vectors produced by the
+reference itself (oracle/make_golden.py); host logic; the C-ABI library loads and
+exports every symbol include/b200rec.h declares."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import bpr_oracle as O
+from tests.util import truths_from_csr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- BPR arithmetic vs reference autograd / optimisers (tests/golden/tiny_bpr.npz) ----
+def test_oracle_forward_loss_grads(golden):
+    g = golden["tiny_bpr"]
+    U0, V0 = g["U0"], g["V0"]
+    u, i, j = g["users"][0], g["pos"][0], g["neg"][0]
+    np.testing.assert_allclose(O.forward_scores(U0, V0, u, i), g["pos_scores"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(O.forward_scores(U0, V0, u, j), g["neg_scores"], rtol=1e-6, atol=1e-6)
+    loss, _ = O.bpr_loss(U0, V0, u, i, j)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    dU, dV, _, _ = O.bpr_grads(U0, V0, u, i, j)
+    np.testing.assert_allclose(dU, g["dU"], rtol=1e-5, atol=1e-7)      # duplicates included
+    np.testing.assert_allclose(dV, g["dV"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["sgd", "sgdreg"])
+def test_oracle_sgd_trajectory(golden, tag):
+    g = golden["tiny_bpr"]
+    U, V = g["U0"].copy(), g["V0"].copy()
+    for b in range(3):
+        U, V, _ = O.sgd_step(U, V, g["users"][b], g["pos"][b], g["neg"][b], float(g[f"{tag}_lr"]), float(g[f"{tag}_reg"]))
+    np.testing.assert_allclose(U, g[f"{tag}_U"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(V, g[f"{tag}_V"], rtol=2e-5, atol=2e-6)
+
+
+def test_oracle_dense_adam(golden):
+    g = golden["tiny_bpr"]
+    U, V = g["U0"].copy(), g["V0"].copy()
+    opt = O.DenseAdam([U.shape, V.shape])
+    for b in range(3):
+        dU, dV, _, _ = O.bpr_grads(U, V, g["users"][b], g["pos"][b], g["neg"][b])
+        U, V = opt.step([U, V], [dU, dV])
+    np.testing.assert_allclose(U, g["adam_U"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(V, g["adam_V"], rtol=1e-4, atol=2e-6)
+
+
+def test_oracle_ml100k_sgd_replay(golden):
+    """Replaying the recorded reference batches through the oracle reproduces the reference's tables."""
+    g = golden["ml100k"]
+    U, V = g["sgd_U0"].copy(), g["sgd_V0"].copy()
+    off = 0
+    for n in g["sgd_blen"]:
+        sl = slice(off, off + n); off += n
+        U, V, _ = O.sgd_step(U, V, g["sgd_bu"][sl], g["sgd_bi"][sl], g["sgd_bj"][sl], float(g["sgd_lr"]), float(g["sgd_reg"]))
+    np.testing.assert_allclose(U, g["sgd_U"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(V, g["sgd_V"], rtol=1e-4, atol=1e-5)
+
+
+# ---- evaluation layer vs the reference's own C++ (oracle/_ref) and numpy twins ----
+def test_oracle_topk_vs_reference(golden, oracle_c):
+    g = golden["eval_blocks"]
+    S = g["scores"]
+    mine = oracle_c.topk(S, 100)
+    np.testing.assert_array_equal(mine, O.topk_desc(S, 100))            # C and numpy restatements agree
+    for name in ("top100_cpp", "top100_py"):
+        ref = g[name].astype(np.int64)
+        # same score at every rank (tie order is unspecified upstream)
+        np.testing.assert_array_equal(np.take_along_axis(S, mine.astype(np.int64), 1), np.take_along_axis(S, ref, 1))
+    tie_free = [r for r in range(S.shape[0]) if r not in (5, 6)]
+    np.testing.assert_array_equal(mine[tie_free], g["top100_cpp"][tie_free])
+
+
+def test_oracle_metrics_vs_reference(golden, oracle_c):
+    g = golden["eval_blocks"]
+    truths = truths_from_csr(g["m_truth_indptr"], g["m_truth_indices"])
+    ks = g["m_ks"]
+    np.testing.assert_array_equal(oracle_c.holdout(g["m_topk"], truths, ks), g["holdout_cpp"])   # bit-exact vs holdout.h
+    np.testing.assert_array_equal(O.holdout_metrics(g["m_topk"], truths, ks), g["holdout_cpp"])
+    np.testing.assert_allclose(g["holdout_cpp"], g["holdout_py"], rtol=1e-6, atol=1e-7)           # python twin
+    np.testing.assert_array_equal(oracle_c.loo(g["m_topk"], truths, ks), g["loo_cpp"])
+    np.testing.assert_array_equal(O.loo_metrics(g["m_topk"], truths, ks), g["loo_cpp"])
+    np.testing.assert_allclose(g["loo_cpp"], g["loo_py"], rtol=1e-6, atol=1e-7)
+
+
+def test_oracle_ml100k_eval(golden, oracle_c):
+    g = golden["ml100k"]
+    nu, ni = int(g["num_users"]), int(g["num_items"])
+    for tag in ("adam", "sgd"):
+        idx, sc = oracle_c.score_topk(g[f"{tag}_U"], g[f"{tag}_V"], 32, np.arange(nu), ni, g["train_indptr"],
+                                      g["train_indices"], 10)
+        np.testing.assert_allclose(sc, g[f"{tag}_top10_scores"], rtol=1e-5, atol=1e-5)
+        assert (idx == g[f"{tag}_top10"]).mean() > 0.999
+        truths = truths_from_csr(g["valid_indptr"], g["valid_indices"])
+        rows = oracle_c.holdout(idx, truths, [5, 10])
+        ndcg10 = O.mean_f32(rows[:, 5])
+        assert abs(float(ndcg10) - float(g[f"{tag}_NDCG@10"][-1])) < 1e-6
+
+
+def test_oracle_lightgcn(golden):
+    g = golden["lightgcn_ml100k"]
+    ml = golden["ml100k"]
+    import scipy.sparse as sp
+    nu, ni = int(ml["num_users"]), int(ml["num_items"])
+    R = sp.csr_matrix((np.ones(len(ml["train_indices"]), np.float32), ml["train_indices"], ml["train_indptr"]), shape=(nu, ni))
+    A = O.lightgcn_adj(R)
+    ref = sp.csr_matrix((g["adj_vals"], (g["adj_rows"], g["adj_cols"])), shape=A.shape)
+    assert A.nnz == int(g["adj_nnz"])
+    assert abs(A - ref).max() < 1e-7
+    out = O.lightgcn_propagate(A, np.concatenate([g["U0"], g["V0"]]), 3)
+    np.testing.assert_allclose(out[:nu], g["prop_U"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(out[nu:], g["prop_V"], rtol=1e-4, atol=1e-7)
+
+
+# ---- host logic ---------------------------------------------------------------
+def test_reference_sampler_restatement(golden):
+    """sampler='reference' replays data/generators.py:168-224 draw for draw (same numpy seed -> same batches)."""
+    import random
+    import scipy.sparse as sp
+    import torch
+    from recsys_pytorch_b200.generators import PairwiseGenerator
+    g = golden["ml100k"]
+    nu, ni = int(g["num_users"]), int(g["num_items"])
+    R = sp.csr_matrix((np.ones(len(g["train_indices"])), g["train_indices"], g["train_indptr"]), shape=(nu, ni))
+    random.seed(2020); np.random.seed(2020); torch.manual_seed(2020)        # utils/general.py:31-38
+    gen = PairwiseGenerator(R, num_negatives=1, num_positives_per_user=1, batch_size=256, shuffle=True,
+                            device="cpu", sampler="reference")
+    assert len(gen) == 4
+    bu, bi, bj = [], [], []
+    for _ in range(3):
+        for (u, i, j) in gen:
+            bu.append(u.numpy()); bi.append(i.numpy()); bj.append(j.numpy())
+    np.testing.assert_array_equal(np.concatenate(bu), g["adam_bu"])
+    np.testing.assert_array_equal(np.concatenate(bi), g["adam_bi"])
+    np.testing.assert_array_equal(np.concatenate(bj), g["adam_bj"])
+
+
+def test_sampler_mirror_properties():
+    rng = np.random.default_rng(5)
+    ni = 200
+    rows = [np.sort(rng.choice(ni, rng.integers(1, 150), replace=False)).astype(np.int32) for _ in range(50)]
+    indptr = np.zeros(51, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.concatenate(rows)
+    for t in range(400):
+        u = t % 50
+        p, n = O.sample_triple(9, 3, t, u, indptr, indices, ni)
+        assert p in rows[u] and n not in rows[u] and 0 <= n < ni
+
+
+def test_statistics_and_cpu_refusal():
+    from recsys_pytorch_b200.evaluation import Statistics
+    st = Statistics("x"); st.update(1.0); st.update([2.0, 3.0]); st.update(np.float32(4.0))
+    assert st.cnt == 4 and abs(float(st.mean) - 2.5) < 1e-7
+    import types
+    import torch
+    from recsys_pytorch_b200 import B200RecError
+    from recsys_pytorch_b200.mf import MF
+    with pytest.raises(B200RecError):        # no CPU fallback: a CPU device is refused loudly
+        MF(types.SimpleNamespace(num_users=4, num_items=4), {"hidden_dim": 8}, torch.device("cpu"))
+
+
+# ---- C ABI ---------------------------------------------------------------------
+def test_cabi_exports_every_declared_symbol(built_lib):
+    from recsys_pytorch_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "b200rec.h")).read()
+    declared = set(re.findall(r"\b(b200rec_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(built_lib, name), f"{name} declared in include/b200rec.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert built_lib.b200rec_version() >= 100
+
+
+def test_cabi_argument_errors_without_gpu(built_lib):
+    """Argument validation and the no-device refusal run on a CPU-only box (no compute)."""
+    from recsys_pytorch_b200 import _lib
+    import ctypes as C
+    assert built_lib.b200rec_bpr_step(None, None) == _lib.EINVAL
+    assert b"NULL" in built_lib.b200rec_last_error()
+    sc = np.zeros((2, 8), np.float32); out = np.zeros((2, 4), np.int32)
+    assert built_lib.b200rec_top_k_array_index(sc.ctypes.data, 8, 2, 9, out.ctypes.data) == _lib.EINVAL   # k > cols
+    import torch
+    if not torch.cuda.is_available():
+        rc = built_lib.b200rec_top_k_array_index(sc.ctypes.data, 8, 2, 4, out.ctypes.data)
+        assert rc == _lib.ECUDA and b"no CPU fallback" in built_lib.b200rec_last_error()
