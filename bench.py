@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py - BPR-MF hot path on B200 (BASELINE.json metric: BPR triples/s for
+training, scored pairs/s + NDCG@10 for evaluation).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3          # this repo's CUDA path
+    python bench.py --impl reference --steps 5 --warmup 1   # the reference's CPU path (torch restatement)
+    torchrun --nproc-per-node N bench.py --gpus N ...       # one rank per GPU
+
+A *step* is one pass of the hot path over one batch of synthetic triples at the
+configuration BASELINE.json's metric is quoted on (configs[1]: BPRMF synthetic
+1M users x 100k items, d=128): ONE fused kernel launch that samples (pos, neg) on
+the device for a batch of B users, gathers the three rows, and scatters the SGD
+update.  Inputs are larger than L2 (the step walks B user rows of 512 B = 512 MB at
+B=1M, L2 is 126 MB), so no L2 flush is needed between timed iterations.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` is the
+same metric through the public plugin API (`MF.train_batch`) with the batch's user
+ids coming from pinned HOST memory and the loss read back to the host every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG = dict(num_users=1_000_000, num_items=100_000, d=128, batch=1_000_000, seed=2020, lr=0.05, reg=1e-4,
+           init_std=0.01, eval_users=32_768, eval_k=10)
+FALLBACK_HBM_GBS = 6650.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), float(j.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def timed_region(fn, steps, world):
+    """barrier + sync | K steps between CUDA events on the launching stream | sync + barrier; max over ranks."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        fn(s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import types
+    from recsys_pytorch_b200 import _lib, engine, synthetic
+    from recsys_pytorch_b200.evaluation import Evaluator
+    from recsys_pytorch_b200.mf import MF
+
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the engine has no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    c = dict(CFG)
+    if args.small:
+        c.update(num_users=50_000, num_items=20_000, batch=50_000, eval_users=4096)
+    hbm_gbs, _, peak_src = measured_peaks()
+
+    if world > 1:
+        from recsys_pytorch_b200 import dist as bdist
+        return bdist.bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_gbs, peak_src)
+
+    train, target = synthetic.make_interactions(c["num_users"], c["num_items"], seed=c["seed"], device=dev)
+    ds = types.SimpleNamespace(num_users=c["num_users"], num_items=c["num_items"], train_data=train,
+                               valid_input=train, valid_target=target, protocol="holdout", dataname="synthetic")
+    hp = {"hidden_dim": c["d"], "pointwise": False, "loss_func": "ce", "optimizer": "sgd", "lr": c["lr"],
+          "reg": c["reg"], "init_std": c["init_std"], "gather": args.gather, "seed": c["seed"],
+          "score_algo": args.score_algo}
+    model = MF(ds, hp, dev)
+    B, d, ld = c["batch"], c["d"], model.U.shape[1]
+    g = torch.Generator(device=dev); g.manual_seed(c["seed"])
+    n_perm = 4
+    perms = [torch.randperm(c["num_users"], device=dev, generator=g)[:B].to(torch.int32).contiguous() for _ in range(n_perm)]
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    flags = (_lib.F_TMA_GATHER if args.gather == "tma" else 0) | _lib.F_USERS_UNIQUE
+
+    def step_dev(s):
+        engine.bpr_step(model.U, model.V, d, perms[s % n_perm], csr=train, lr=c["lr"], reg=c["reg"],
+                        sink=_lib.SINK_UPDATE, flags=flags, seed=c["seed"], step=s + 1, loss_sum=loss)
+
+    for s in range(args.warmup):
+        step_dev(s)
+    clocks = ClockSampler(local); clocks.start()
+    l0 = _lib.launch_count()
+    ms = timed_region(step_dev, args.steps, world)
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop()
+    triples_per_s = B * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+
+    # ---- e2e: plugin API, user ids from pinned host memory, loss read back every step ----
+    host_perms = [p.cpu().pin_memory() for p in perms]
+    slot = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step_e2e(s):
+        u = host_perms[s % n_perm].to(dev, non_blocking=True)                      # H2D of the step's input
+        slot.zero_()
+        model.train_batch(u, csr=train, step_key=1000 + s, users_unique=True, loss_slot=slot)
+        return float(slot.item()) / B                                              # D2H of the step's result
+
+    for s in range(min(args.warmup, 3)):
+        step_e2e(s)
+    ms_e2e = timed_region(step_e2e, args.steps, world)
+    e2e = {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": B * 4,
+           "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
+           "api": "recsys_pytorch_b200.mf.MF.train_batch (users from pinned host memory, loss.item())"}
+
+    # ---- evaluation leg: fused score + mask + top-k + holdout metrics on a user sample ----
+    ev_users = torch.arange(c["eval_users"], dtype=torch.int32, device=dev)
+    ev = Evaluator(train, _SubsetTarget(target, c["eval_users"]), protocol="holdout", ks=[c["eval_k"]])
+    ev.evaluate(model)                                                              # warm-up
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    scores = ev.evaluate(model)
+    torch.cuda.synchronize(); t_eval = time.perf_counter() - t0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); idx, _ = model.predict_topk_device(ev_users, train, c["eval_k"]); e1.record(); torch.cuda.synchronize()
+    pairs = c["eval_users"] * c["num_items"]
+    eval_leg = {"scored_pairs_per_sec": pairs / (e0.elapsed_time(e1) * 1e-3), "e2e_pairs_per_sec": pairs / t_eval,
+                "ndcg@%d" % c["eval_k"]: float(scores["NDCG@%d" % c["eval_k"]]), "users": c["eval_users"],
+                "k": c["eval_k"], "algo": args.score_algo,
+                "flops_per_pair": 2 * d}
+
+    # ---- roofline of the dominant kernel (fused BPR step): algorithmic bytes = 24d+8 per triple ----
+    bytes_per_triple = 24 * d + 8
+    achieved = bytes_per_triple * B / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "bpr_step_dram_bytes.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_triple": bytes_per_triple,
+                "kernel": "bpr_step_%s_kernel<32,1,UPDATE>" % args.gather}
+
+    cpu_base = cpu_baseline_leg(c, args) if not args.no_cpu else None
+    out = {"metric": "BPR triples/sec (train)", "value": triples_per_s, "unit": "triples/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BPRMF synthetic %dx%d d=%d, 1xB200 fused kernel (BASELINE configs[1])" %
+                      (c["num_users"], c["num_items"], d), "batch_triples": B, "optimizer": "sgd+l2", "lr": c["lr"],
+                      "reg": c["reg"], "sampler": "on-device uniform negative vs CSR", "gather": args.gather,
+                      "l2_policy": "inputs larger than L2 (512 MB of user rows per step)", "nnz_train": train.nnz},
+           "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base,
+           "eval": eval_leg, "final_loss": float(loss.item()) / (B * (args.steps + args.warmup))}
+    print(json.dumps(out))
+
+
+class _SubsetTarget:
+    """First n rows of a DeviceCSR presented as the dict-free target the Evaluator accepts."""
+
+    def __new__(cls, csr, n):
+        import scipy.sparse as sp
+        indptr = csr.indptr[: n + 1].cpu().numpy()
+        indices = csr.indices[: int(indptr[-1])].cpu().numpy()
+        return sp.csr_matrix((np.ones(len(indices), np.float32), indices, indptr), shape=(n, csr.shape[1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's torch CPU path restated (oracle/torch_port.py)
+# ------------------------------------------------------------------------------------------------
+def _cpu_workload(c, batch, n_batches, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_batches):
+        u = torch.from_numpy(rng.permutation(c["num_users"])[:batch].astype(np.int64))
+        i = torch.from_numpy(rng.integers(0, c["num_items"], batch).astype(np.int64))
+        j = torch.from_numpy(rng.integers(0, c["num_items"], batch).astype(np.int64))
+        out.append((u, i, j))
+    return out
+
+
+def cpu_baseline_leg(c, args, steps=3, warmup=1, batch=65_536):
+    """Bounded sample on the host cores: a few 65,536-triple steps of the reference's own step
+    (dense autograd grads + dense Adam over all U+I rows, models/MF.py:64-68) at the same table sizes."""
+    from oracle import torch_port as TP
+    t_all = time.perf_counter()
+    model = TP.RefMF(c["num_users"], c["num_items"], c["d"], init_std=c["init_std"])
+    sec = TP.time_train(model, _cpu_workload(c, batch, steps + warmup, 1), warmup)
+    return {"value": batch / sec, "unit": "triples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps of %d triples (reference MF.py:64-68 restated on torch CPU: dense grads + dense Adam "
+                      "over %d rows); %.1f s total" % (steps, batch, c["num_users"] + c["num_items"],
+                                                       time.perf_counter() - t_all)}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import torch_port as TP
+    c = dict(CFG)
+    if args.small:
+        c.update(num_users=50_000, num_items=20_000, batch=50_000, eval_users=4096)
+    batch = 65_536 if not args.small else 8192
+    model = TP.RefMF(c["num_users"], c["num_items"], c["d"], init_std=c["init_std"])
+    wl = _cpu_workload(c, batch, args.steps + args.warmup, 1)
+    sec = TP.time_train(model, wl, args.warmup)
+    val = batch / sec
+    # evaluation leg: chunked restatement on 2 chunks of 1024 users
+    fns, kind = TP.native_eval_lib()
+    rng = np.random.default_rng(3)
+    deg = 40
+    mp = np.arange(c["num_users"] + 1, dtype=np.int64)[:2049] * deg
+    mi = np.sort(rng.integers(0, c["num_items"], (2048, deg)), 1).astype(np.int32).ravel()
+    tp = np.arange(2049, dtype=np.int64) * 8
+    ti = rng.integers(0, c["num_items"], 2048 * 8).astype(np.int32)
+    t0 = time.perf_counter(); pairs = 0
+    for ch in range(2):
+        users = np.arange(ch * 1024, (ch + 1) * 1024)
+        n, _ = TP.eval_chunk(model, users, mp, mi, tp, ti, c["eval_k"], fns)
+        pairs += n
+    t_eval = time.perf_counter() - t0
+    cores = torch.get_num_threads()
+    sample = "%d steps x %d triples at %dx%d d=%d (dense autograd + dense Adam, MF.py:64-68)" % (
+        args.steps, batch, c["num_users"], c["num_items"], c["d"])
+    out = {"impl": "reference", "metric": "BPR triples/sec (train)", "value": val, "unit": "triples/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BPRMF synthetic %dx%d d=%d (BASELINE configs[1]), reference CPU path" %
+                      (c["num_users"], c["num_items"], c["d"]), "batch_triples": batch, "optimizer": "adam (MF.py:30)"},
+           "cpu_baseline": {"value": val, "unit": "triples/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "eval": {"scored_pairs_per_sec": pairs / t_eval, "native": kind, "users": 2048, "k": c["eval_k"]},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gather", default="tma", choices=["tma", "ldg"])
+    ap.add_argument("--score-algo", dest="score_algo", default="exact", choices=["exact", "tc"])
+    ap.add_argument("--layout", default="item_sharded", choices=["item_sharded", "user_sharded"])
+    ap.add_argument("--small", action="store_true", help="tiny shapes for a quick functional run (NOT a bench value)")
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,7 @@ int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int3
 /* flags */
 #define B200REC_F_USERS_UNIQUE 1 /* no user id repeats inside the batch: user rows use plain vector stores */
 #define B200REC_F_TMA_GATHER 2   /* rows gathered with cp.async.bulk (TMA) into shared memory */
+#define B200REC_F_ITEM_DELTA 4   /* SINK_UPDATE: item-row deltas accumulate into dense gV (user-sharded layout) */
 
 typedef struct b200rec_bpr_args {
     float *U;              /* [num_users, ld]  user_embedding.weight (models/MF.py:23)   */
@@ -106,6 +107,11 @@ typedef struct b200rec_bpr_args {
     float *gU, *gV;        /* SINK_GRAD: dense [num_users,ld], [num_items,ld] (caller zeroes) */
     double *loss_sum;      /* optional device scalar, += sum_b -log sigmoid(x_b) */
     float *x_out;          /* optional [B]: x_b = s(u,i) - s(u,j)             */
+    /* multi-GPU layouts (0 / NULL = single device) */
+    int32_t item_lo, item_hi; /* item-sharded: V holds rows [item_lo,item_hi); a rank processes only the
+                                 triples whose sampled positive is in range and samples negatives from it */
+    float *udelta;         /* item-sharded: user delta rows go to udelta[t] ([B,ld]) instead of U        */
+    float inv_batch;       /* >0: overrides 1/B in g = -sigmoid(-x)/B (global batch of a sharded step)   */
 } b200rec_bpr_args;
 
 /* models/MF.py:63-68 (zero_grad -> process_one_batch -> backward -> step) as ONE
@@ -125,6 +131,11 @@ int b200rec_sample_triples(const int32_t *users, int B, const int64_t *csr_indpt
 /* second phase of the exact step: W[row] += stage rows (vector atomics). */
 int b200rec_bpr_apply(float *U, float *V, int ld, const int32_t *users, const int32_t *pos,
                       const int32_t *neg, int B, const float *stage, void *stream);
+
+/* W[ids[t]] += scale * delta[t] for t < n (vector atomics): applies the exchanged user-gradient
+ * rows of the item-sharded layout to every replica. */
+int b200rec_rows_add(float *W, int ld, const int32_t *ids, int n, const float *delta, int ld_delta,
+                     float scale, void *stream);
 
 /* dense SGD / Adam sweeps: torch.optim.SGD(lr) and torch.optim.Adam(lr, betas,
  * eps, weight_decay=0) as constructed at models/MF.py:30 - every element moves. */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libb200rec.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SINK_UPDATE, SINK_STAGE, SINK_GRAD, SINK_NONE = 0, 1, 2, 3
-F_USERS_UNIQUE, F_TMA_GATHER = 1, 2
+F_USERS_UNIQUE, F_TMA_GATHER, F_ITEM_DELTA = 1, 2, 4
 SCORE_EXACT, SCORE_TC = 0, 1
 
 
@@ -38,6 +38,8 @@ class BprArgs(C.Structure):
         ("sink", C.c_int32), ("flags", C.c_int32),
         ("stage", C.c_void_p), ("gU", C.c_void_p), ("gV", C.c_void_p),
         ("loss_sum", C.c_void_p), ("x_out", C.c_void_p),
+        ("item_lo", C.c_int32), ("item_hi", C.c_int32),
+        ("udelta", C.c_void_p), ("inv_batch", C.c_float),
     ]
 
 
@@ -53,6 +55,7 @@ _PROTOS = {
     "b200rec_bpr_step": (_I, [C.POINTER(BprArgs), _P]),
     "b200rec_sample_triples": (_I, [_P, _I, _P, _P, _I, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "b200rec_bpr_apply": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _P]),
+    "b200rec_rows_add": (_I, [_P, _I, _P, _I, _P, _I, _F, _P]),
     "b200rec_sgd_dense": (_I, [_P, _P, _L, _F, _P]),
     "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
     "b200rec_score_topk_workspace": (_L, [_I, _I, _I, _I, _I]),

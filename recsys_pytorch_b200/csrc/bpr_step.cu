@@ -28,8 +28,18 @@ struct BprParams {
     b200rec_bpr_args a;
     float invB;
     int chunk;       // triples per warp-chunk (multiple of 32/G, <= 32)
+    int stages;      // TMA path: shared-memory stages per warp
     int64_t n_chunks;
 };
+
+// dL/dx of -log(sigmoid(x))/B the way the reference's fp32 autograd evaluates it (models/MF.py:105):
+// s = fl(1/(1+fl(exp(-x)))), grad = -(1 - s)/B.  It saturates to exactly 0 for x > ~16.6 (s rounds to 1),
+// which matters under Adam (a 1e-10 gradient would still move a weight by ~lr).  For x < -88 the
+// reference produces NaN; here s -> 0 and the gradient is the finite limit -1/B.
+__device__ __forceinline__ float bpr_grad(float x, float invB) {
+    const float s = 1.f / (1.f + expf(-x));
+    return -(1.f - s) * invB;
+}
 
 __device__ __forceinline__ float softplus_neg(float x) {  // -log(sigmoid(x)) = log(1+exp(-x)), stable
     return x > 0.f ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
@@ -53,10 +63,16 @@ __device__ __forceinline__ void fetch_triple(const b200rec_bpr_args &a, int64_t 
         } else {
             const int32_t *row = a.csr_indices + lo;
             if (sample_pos) i = row[(uint32_t)(((uint64_t)rng_u32(a.seed, a.step, (uint64_t)t, 0) * deg) >> 32)];
-            if (sample_neg) {
+            // item-sharded layout: only the rank owning the positive processes the triple,
+            // and it draws the negative from its own id range
+            const bool sharded = a.item_hi > a.item_lo;
+            const uint32_t n_lo = sharded ? (uint32_t)a.item_lo : 0u;
+            const uint32_t n_cnt = sharded ? (uint32_t)(a.item_hi - a.item_lo) : (uint32_t)a.num_items;
+            if (sharded && (i < a.item_lo || i >= a.item_hi)) valid = false;
+            if (sample_neg && valid) {
                 for (uint32_t tries = 0; tries < 64; ++tries) {
-                    j = (int)(((uint64_t)rng_u32(a.seed, a.step, (uint64_t)t, 1 + tries) *
-                               (uint64_t)(uint32_t)a.num_items) >> 32);
+                    j = (int)(n_lo + (uint32_t)(((uint64_t)rng_u32(a.seed, a.step, (uint64_t)t, 1 + tries) *
+                                                 (uint64_t)n_cnt) >> 32));
                     uint32_t l = 0, r = deg;  // lower_bound in the sorted row
                     while (l < r) {
                         uint32_t m = (l + r) >> 1;
@@ -92,11 +108,17 @@ __device__ __forceinline__ void sink_chunk(const b200rec_bpr_args &a, int64_t t,
     dj.z = sc * fmaf(-g, ru.z, regB * rj.z); dj.w = sc * fmaf(-g, ru.w, regB * rj.w);
     const int64_t ld = a.ld;
     if (SINK == B200REC_SINK_UPDATE) {
-        float *pu = a.U + (int64_t)tu * ld + q * 4;
-        if (uniq) st4(pu, make_float4(ru.x + du.x, ru.y + du.y, ru.z + du.z, ru.w + du.w));
-        else red4(pu, du);
-        red4(a.V + (int64_t)ti * ld + q * 4, di);
-        red4(a.V + (int64_t)tj * ld + q * 4, dj);
+        if (a.udelta) {                                   // item-sharded: user delta row -> exchange buffer [B, ld]
+            st4(a.udelta + t * ld + q * 4, du);
+        } else {
+            float *pu = a.U + (int64_t)tu * ld + q * 4;
+            if (uniq) st4(pu, make_float4(ru.x + du.x, ru.y + du.y, ru.z + du.z, ru.w + du.w));
+            else red4(pu, du);
+        }
+        // user-sharded: item deltas accumulate in a dense exchange buffer instead of the replica
+        float *vdst = (a.flags & B200REC_F_ITEM_DELTA) ? a.gV : a.V;
+        red4(vdst + (int64_t)(ti - a.item_lo) * ld + q * 4, di);
+        red4(vdst + (int64_t)(tj - a.item_lo) * ld + q * 4, dj);
     } else if (SINK == B200REC_SINK_STAGE) {
         float *s = a.stage + (t * 3) * ld + q * 4;
         st4(s, du); st4(s + ld, di); st4(s + 2 * ld, dj);
@@ -144,8 +166,8 @@ __global__ void __launch_bounds__(256) bpr_step_ldg_kernel(const BprParams p) {
                 const int q = sl + k * G;
                 if (tv && q < d4) {
                     nu[k] = ld4(a.U + (int64_t)tu * ld + q * 4);
-                    ni[k] = ld4(a.V + (int64_t)ti * ld + q * 4);
-                    nj[k] = ld4(a.V + (int64_t)tj * ld + q * 4);
+                    ni[k] = ld4(a.V + (int64_t)(ti - a.item_lo) * ld + q * 4);
+                    nj[k] = ld4(a.V + (int64_t)(tj - a.item_lo) * ld + q * 4);
                 } else {
                     nu[k] = ni[k] = nj[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -167,7 +189,7 @@ __global__ void __launch_bounds__(256) bpr_step_ldg_kernel(const BprParams p) {
                 part = fmaf(ru[k].w, ri[k].w - rj[k].w, part);
             }
             const float x = group_sum<G>(part);
-            const float g = -p.invB / (1.f + expf(x));  // -sigmoid(-x)/B
+            const float g = bpr_grad(x, p.invB);
             const int64_t t = c * p.chunk + it * TPW + sg;
             if (cv) {
                 if (sl == 0) {
@@ -218,7 +240,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 constexpr int kTmaWarps = 8;   // warps per CTA
-constexpr int kTmaStages = 8;  // stages per warp
+constexpr int kTmaMaxStages = 8;  // stages per warp (fewer when rows are wide)
 
 template <int G, int CPL, int SINK>
 __global__ void __launch_bounds__(kTmaWarps * 32) bpr_step_tma_kernel(const BprParams p) {
@@ -232,8 +254,9 @@ __global__ void __launch_bounds__(kTmaWarps * 32) bpr_step_tma_kernel(const BprP
     const uint32_t row_bytes = (uint32_t)a.ld * 4u;
     const uint32_t stage_bytes = row_bytes * 3u * TPW;
     // layout: [warps][stages] mbarriers (8 B each) then [warps][stages][TPW][3][ld] floats
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + wid * kTmaStages;
-    const uint32_t data_off = (uint32_t)(kTmaWarps * kTmaStages * 8);
+    const int kTmaStages = p.stages;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + wid * kTmaMaxStages;
+    const uint32_t data_off = (uint32_t)(kTmaWarps * kTmaMaxStages * 8);
     float *wdata = reinterpret_cast<float *>(smem_raw + data_off + (size_t)wid * kTmaStages * stage_bytes);
     if (lane < kTmaStages) mbar_init(smem_u32(bars + lane), TPW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -258,15 +281,17 @@ __global__ void __launch_bounds__(kTmaWarps * 32) bpr_step_tma_kernel(const BprP
             const int src = it * TPW + sg;
             const int tu = __shfl_sync(0xffffffffu, u, src);
             const int ti = __shfl_sync(0xffffffffu, i, src);
-            const int tj = __shfl_sync(0xffffffffu, j, src);
+            int tj = __shfl_sync(0xffffffffu, j, src);
+            int ti_ = ti;
+            if (!__shfl_sync(0xffffffffu, (int)valid, src)) { ti_ = a.item_lo; tj = a.item_lo; }  // keep addresses in range
             if (sl == 0) {
                 const uint32_t slot = n_slot % kTmaStages;
                 const uint32_t bar = smem_u32(bars + slot);
                 const uint32_t dst = smem_u32(wdata) + slot * stage_bytes + (uint32_t)sg * 3u * row_bytes;
                 mbar_expect_tx(bar, 3u * row_bytes);
                 bulk_g2s(dst, a.U + (int64_t)tu * ld, row_bytes, bar);
-                bulk_g2s(dst + row_bytes, a.V + (int64_t)ti * ld, row_bytes, bar);
-                bulk_g2s(dst + 2u * row_bytes, a.V + (int64_t)tj * ld, row_bytes, bar);
+                bulk_g2s(dst + row_bytes, a.V + (int64_t)(ti_ - a.item_lo) * ld, row_bytes, bar);
+                bulk_g2s(dst + 2u * row_bytes, a.V + (int64_t)(tj - a.item_lo) * ld, row_bytes, bar);
             }
         };
         const int pre = iters < kTmaStages ? iters : kTmaStages;
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32) bpr_step_tma_kernel(const BprP
             ++n_consumed;
             __syncwarp();
             if (it + kTmaStages < iters) issue(it + kTmaStages, n_consumed - 1 + kTmaStages);  // refill this slot
-            const float g = -p.invB / (1.f + expf(x));
+            const float g = bpr_grad(x, p.invB);
             const int64_t t = c * p.chunk + it * TPW + sg;
             if (cv) {
                 if (sl == 0) {
@@ -349,6 +374,20 @@ __global__ void __launch_bounds__(256) sample_triples_kernel(const b200rec_bpr_a
     }
 }
 
+// W[ids[t]] += delta[t]   (user-gradient apply after the exchange; ids unique per call or not: atomics)
+__global__ void __launch_bounds__(256) rows_add_kernel(float *W, int ld, const int32_t *ids, int n, const float *delta,
+                                                       int ldd, float scale) {
+    const int d4 = ld >> 2;
+    const int64_t total = (int64_t)n * d4;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(e % d4);
+        const int64_t t = e / d4;
+        float4 v = ld4(delta + t * ldd + q * 4);
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red4(W + (int64_t)ids[t] * ld + q * 4, v);
+    }
+}
+
 __global__ void __launch_bounds__(256) mf_forward_kernel(const float *U, const float *V, int ld, int d,
                                                          const int32_t *users, const int32_t *items, int n,
                                                          float *out) {
@@ -392,16 +431,19 @@ __global__ void __launch_bounds__(256) adam_dense_kernel(float *p, const float *
 // host side
 // ---------------------------------------------------------------------------
 template <int G, int CPL>
-static int launch_bpr(const BprParams &p, cudaStream_t s) {
+static int launch_bpr(BprParams &p, cudaStream_t s) {
     const bool tma = (p.a.flags & B200REC_F_TMA_GATHER) != 0;
+    {   // stages per warp: as many as fit in ~96 KB per CTA (2 CTAs/SM), between 2 and kTmaMaxStages
+        const size_t per_stage = (size_t)kTmaWarps * p.a.ld * 4 * 3 * (32 / G);
+        int st = (int)((96 * 1024) / per_stage);
+        p.stages = st < 2 ? 2 : (st > kTmaMaxStages ? kTmaMaxStages : st);
+    }
     const int sms = sm_count();
     constexpr int TPW = 32 / G;
 #define B200_LAUNCH_SINK(SINKV)                                                                              \
     if (tma) {                                                                                               \
         auto kern = bpr_step_tma_kernel<G, CPL, SINKV>;                                                      \
-        const size_t smem = (size_t)kTmaWarps * kTmaStages * (8 + (size_t)p.a.ld * 4 * 3 * TPW);             \
-        B200_REQUIRE(smem <= 227 * 1024, B200REC_EUNSUPPORTED, "bpr_step TMA path: row too large (ld=%d)",   \
-                     p.a.ld);                                                                                \
+        const size_t smem = (size_t)kTmaWarps * (kTmaMaxStages * 8 + (size_t)p.stages * p.a.ld * 4 * 3 * TPW);  \
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
         int occ = 0;                                                                                         \
         B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kTmaWarps * 32, smem));          \
@@ -438,6 +480,7 @@ using namespace b200;
 extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
     B200_REQUIRE(args != nullptr, B200REC_EINVAL, "bpr_step: args is NULL");
     const b200rec_bpr_args &a = *args;
+    if (a.B == 0) return B200REC_OK;
     B200_REQUIRE(a.U && a.V && a.users, B200REC_EINVAL, "bpr_step: U, V and users are required");
     B200_REQUIRE(a.B >= 0 && a.d >= 1 && a.ld >= a.d && (a.ld % 4) == 0 && a.ld <= 512, B200REC_EINVAL,
                  "bpr_step: need 1 <= d <= ld <= 512, ld %% 4 == 0 (d=%d ld=%d)", a.d, a.ld);
@@ -448,6 +491,10 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
     B200_REQUIRE(a.sink >= 0 && a.sink <= 3, B200REC_EINVAL, "bpr_step: bad sink %d", a.sink);
     B200_REQUIRE(a.sink != B200REC_SINK_STAGE || a.stage, B200REC_EINVAL, "bpr_step: SINK_STAGE needs stage");
     B200_REQUIRE(a.sink != B200REC_SINK_GRAD || (a.gU && a.gV), B200REC_EINVAL, "bpr_step: SINK_GRAD needs gU,gV");
+    B200_REQUIRE(!(a.flags & B200REC_F_ITEM_DELTA) || a.gV, B200REC_EINVAL, "bpr_step: F_ITEM_DELTA needs gV");
+    B200_REQUIRE(a.item_hi >= a.item_lo && a.item_lo >= 0, B200REC_EINVAL, "bpr_step: bad item shard range");
+    B200_REQUIRE(a.item_hi == a.item_lo || (a.pos == nullptr && a.neg == nullptr) || a.item_lo == 0, B200REC_EINVAL,
+                 "bpr_step: item-sharded mode samples its own triples (pos/neg must be NULL)");
     if (a.B == 0) return B200REC_OK;
 
     const int d4 = a.ld / 4;
@@ -457,7 +504,7 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
     const int TPW = 32 / G;
     BprParams p;
     p.a = a;
-    p.invB = 1.0f / (float)a.B;
+    p.invB = a.inv_batch > 0.f ? a.inv_batch : 1.0f / (float)a.B;
     // chunk: as large as 32 triples, shrunk (to a multiple of TPW) until every warp slot has work
     const int64_t slots = (int64_t)sm_count() * 48;
     int chunk = 32;
@@ -547,6 +594,20 @@ extern "C" int b200rec_sample_triples(const int32_t *users, int B, const int64_t
     int64_t blocks = ((int64_t)B + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
     sample_triples_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+extern "C" int b200rec_rows_add(float *W, int ld, const int32_t *ids, int n, const float *delta, int ld_delta,
+                                float scale, void *stream) {
+    B200_REQUIRE(W && ids && delta, B200REC_EINVAL, "rows_add: null argument");
+    B200_REQUIRE(ld > 0 && ld % 4 == 0 && ld_delta >= ld && ld_delta % 4 == 0, B200REC_EINVAL, "rows_add: bad ld");
+    if (n <= 0) return B200REC_OK;
+    const int64_t total = (int64_t)n * (ld / 4);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    rows_add_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(W, ld, ids, n, delta,
+                                                                                          ld_delta, scale);
     B200_LAUNCH_CHECK();
     return B200REC_OK;
 }

@@ -1,0 +1,221 @@
+"""Multi-GPU BPR-MF training: one process per GPU, torch.distributed (NCCL over
+NVLink 5 / NVSwitch) for the plumbing, the fused sm_100a step kernel for the math.
+
+The reference has no distributed code at all; the correctness oracle
+of everything here is the single-device result on the triples the ranks actually
+used (tests/test_dist_*.py).
+
+Two layouts:
+
+``item_sharded``  (BASELINE north_star)  the item table is partitioned by contiguous
+    item-id range, I/G rows per GPU; the user table is replicated.  Every rank walks
+    the same user batch [B]; the rank whose range holds the sampled positive owns the
+    triple and draws the negative from its own range.  It updates its item rows in
+    place and writes the user delta row into a batch-aligned [B, ld] buffer (zeros
+    for triples it does not own) -> ONE all-reduce(sum) of that buffer per step ->
+    every rank applies the identical update to its user replica.
+    Wire cost: 4*ld bytes per triple per GPU - this, not HBM, bounds the layout
+    (SURVEY H9): at d=128 NVLink 5 caps the whole box near 1.0-1.8 G triples/s.
+
+``user_sharded``  (the transpose; SURVEY section 8(e) "route to >= 6x")  users are partitioned
+    by id range (U/G rows per GPU, never exchanged); the item table is replicated.
+    Each rank trains on its own users; item-row deltas accumulate in a dense
+    [I, ld] buffer -> ONE all-reduce(sum) of it per step -> V += dV on every rank.
+    Wire cost: 4*ld*I bytes per step, independent of the batch size.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import engine
+from ._lib import F_ITEM_DELTA, F_TMA_GATHER, F_USERS_UNIQUE, SINK_UPDATE
+
+
+def shard_range(n: int, world: int, rank: int):
+    """Contiguous id range [lo, hi) of `rank` when n ids are split over `world` ranks."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def owner_of(ids, n: int, world: int):
+    """Rank owning each id under shard_range (vectorised; numpy or torch)."""
+    # smallest r with ids < n*(r+1)//world  ==  ((ids+1)*world - 1) // n   for 0 <= ids < n
+    return ((ids + 1) * world - 1) // n
+
+
+def allreduce_sum(t):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+class ItemShardedBPR:
+    """north_star layout.  `train` is the GLOBAL DeviceCSR of positives (replicated)."""
+
+    def __init__(self, num_users, num_items, d, train, rank, world, device, lr=0.05, reg=0.0, init_std=0.01,
+                 seed=2020, gather="tma"):
+        self.num_users, self.num_items, self.d = num_users, num_items, d
+        self.rank, self.world, self.device = rank, world, device
+        self.lr, self.reg, self.seed = lr, reg, seed
+        self.train = train
+        self.lo, self.hi = shard_range(num_items, world, rank)
+        g = torch.Generator(device=device); g.manual_seed(seed)
+        self.U = engine.alloc_table(num_users, d, device, init_std, g)            # identical replica on every rank
+        gi = torch.Generator(device=device); gi.manual_seed(seed * 7919 + 1 + rank)
+        self.V = engine.alloc_table(self.hi - self.lo, d, device, init_std, gi)   # rows [lo, hi)
+        self.flags = (F_TMA_GATHER if gather == "tma" else 0)
+        self._udelta = None
+
+    def local_compute(self, users, step_key, loss_sum=None, out_pos=None, out_neg=None):
+        """Fused step on the triples this rank owns: item rows updated in place; returns the
+        batch-aligned [B, ld] user-delta buffer (zero rows for triples owned elsewhere)."""
+        B = users.numel()
+        ld = self.U.shape[1]
+        if self._udelta is None or self._udelta.shape[0] != B:
+            self._udelta = torch.empty((B, ld), dtype=torch.float32, device=self.device)
+        self._udelta.zero_()
+        engine.bpr_step(self.U, self.V, self.d, users, csr=self.train, lr=self.lr, reg=self.reg, sink=SINK_UPDATE,
+                        flags=self.flags, seed=self.seed, step=step_key, loss_sum=loss_sum, out_pos=out_pos,
+                        out_neg=out_neg, item_range=(self.lo, self.hi), udelta=self._udelta)
+        return self._udelta
+
+    def apply_user_delta(self, users, udelta):
+        engine.rows_add(self.U, users, udelta)
+
+    def step(self, users, step_key, loss_sum=None, out_pos=None, out_neg=None):
+        """users: int32 [B] - the SAME tensor content on every rank."""
+        ud = self.local_compute(users, step_key, loss_sum, out_pos, out_neg)
+        allreduce_sum(ud)                                                          # the ONE collective of the step
+        self.apply_user_delta(users, ud)
+
+
+class UserShardedBPR:
+    """transpose layout.  `train_local` holds the CSR rows of this rank's users (local row ids)."""
+
+    def __init__(self, num_users, num_items, d, train_local, rank, world, device, lr=0.05, reg=0.0, init_std=0.01,
+                 seed=2020, gather="tma"):
+        self.num_users, self.num_items, self.d = num_users, num_items, d
+        self.rank, self.world, self.device = rank, world, device
+        self.lr, self.reg, self.seed = lr, reg, seed
+        self.train = train_local
+        self.lo, self.hi = shard_range(num_users, world, rank)
+        gu = torch.Generator(device=device); gu.manual_seed(seed * 7919 + 1 + rank)
+        self.U = engine.alloc_table(self.hi - self.lo, d, device, init_std, gu)   # rows [lo, hi)
+        g = torch.Generator(device=device); g.manual_seed(seed)
+        self.V = engine.alloc_table(num_items, d, device, init_std, g)            # identical replica on every rank
+        self.dV = torch.zeros_like(self.V)
+        self.flags = (F_TMA_GATHER if gather == "tma" else 0) | F_ITEM_DELTA
+
+    def local_compute(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True, out_pos=None,
+                      out_neg=None):
+        """Fused step on this rank's users: user rows updated in place; returns the dense [I, ld]
+        item-delta buffer."""
+        self.dV.zero_()
+        engine.bpr_step(self.U, self.V, self.d, users_local, csr=self.train, lr=self.lr, reg=self.reg,
+                        sink=SINK_UPDATE, flags=self.flags | (F_USERS_UNIQUE if users_unique else 0), seed=self.seed,
+                        step=step_key * self.world + self.rank, loss_sum=loss_sum, gV=self.dV, out_pos=out_pos,
+                        out_neg=out_neg, inv_batch=1.0 / float(global_batch))
+        return self.dV
+
+    def apply_item_delta(self, dV):
+        engine.sgd_dense(self.V, dV, -1.0)                                         # V += dV on every replica
+
+    def step(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True, out_pos=None, out_neg=None):
+        """users_local: int32 [B_local] local row ids of this rank's batch."""
+        dV = self.local_compute(users_local, step_key, global_batch, loss_sum, users_unique, out_pos, out_neg)
+        allreduce_sum(dV)                                                          # the ONE collective of the step
+        self.apply_item_delta(dV)
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1)
+# ------------------------------------------------------------------------------------------------
+def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_gbs, peak_src):
+    """Weak scaling: per-GPU work is fixed (B_local = c['batch'] triples per rank per step); the
+    user population grows with N (N x num_users) while the item catalogue follows BASELINE
+    configs[2] proportionally (N x num_items, capped at 1M)."""
+    from . import _lib, synthetic
+    d = c["d"]
+    B_local = c["batch"]
+    nu, ni = c["num_users"] * world, min(c["num_items"] * world, 1_000_000)
+    layout = args.layout
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    if layout == "item_sharded":
+        # replicated CSR + replicated user table; every rank walks the same global batch of N*B_local users
+        train, _ = synthetic.make_interactions(nu, ni, seed=c["seed"], device=dev)
+        tr = ItemShardedBPR(nu, ni, d, train, rank, world, dev, lr=c["lr"], reg=c["reg"], init_std=c["init_std"],
+                            seed=c["seed"], gather=args.gather)
+        g = torch.Generator(device=dev); g.manual_seed(c["seed"])
+        B_glob = B_local * world
+        perms = [torch.randperm(nu, device=dev, generator=g)[:B_glob].to(torch.int32).contiguous() for _ in range(2)]
+
+        def step(s):
+            tr.step(perms[s % 2], s + 1, loss_sum=loss)
+        wire = 4 * tr.U.shape[1]
+        coll = "all_reduce(sum) of the [B, ld] fp32 user-delta buffer (%d MiB) per step" % (B_glob * wire >> 20)
+    else:
+        ulo, uhi = shard_range(nu, world, rank)
+        train, _ = synthetic.make_interactions(uhi - ulo, ni, seed=c["seed"] + rank, device=dev)
+        tr = UserShardedBPR(nu, ni, d, train, rank, world, dev, lr=c["lr"], reg=c["reg"], init_std=c["init_std"],
+                            seed=c["seed"], gather=args.gather)
+        g = torch.Generator(device=dev); g.manual_seed(c["seed"] + rank)
+        perms = [torch.randperm(uhi - ulo, device=dev, generator=g)[:B_local].to(torch.int32).contiguous() for _ in range(2)]
+        B_glob = B_local * world
+
+        def step(s):
+            tr.step(perms[s % 2], s + 1, B_glob, loss_sum=loss)
+        coll = "all_reduce(sum) of the dense [I, ld] fp32 item-delta buffer (%d MiB) per step" % (ni * 4 * tr.V.shape[1] >> 20)
+
+    for s in range(args.warmup):
+        step(s)
+    clocks = ClockSampler(dev.index or 0)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    ms = timed_region(step, args.steps, world)
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    # e2e: same step with the batch's user ids arriving from pinned host memory and the loss read back
+    host = [p.cpu().pin_memory() for p in perms]
+
+    def step_e2e(s):
+        u = host[s % 2].to(dev, non_blocking=True)
+        loss.zero_()
+        if layout == "item_sharded":
+            tr.step(u, 1000 + s, loss_sum=loss)
+        else:
+            tr.step(u, 1000 + s, B_glob, loss_sum=loss)
+        return float(loss.item())
+
+    for s in range(2):
+        step_e2e(s)
+    ms_e2e = timed_region(step_e2e, args.steps, world)
+    if rank == 0:
+        val = B_glob * args.steps / (ms * 1e-3)
+        bpt = 24 * d + 8
+        per_gpu = bpt * B_local / (ms / args.steps * 1e-3) / 1e9
+        out = {"metric": "BPR triples/sec (train)", "value": val, "unit": "triples/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "BPRMF synthetic %dx%d d=%d, %s over %d GPUs" % (nu, ni, d, layout, world),
+                          "batch_triples": B_glob, "per_gpu_triples": B_local, "optimizer": "sgd+l2",
+                          "parallelism": "%s%d" % (layout, world), "collective": coll, "gather": args.gather,
+                          "l2_policy": "inputs larger than L2"},
+               "clocks": clk,
+               "e2e": {"value": B_glob * args.steps / (ms_e2e * 1e-3), "unit": "triples/s",
+                       "h2d_bytes_per_step": int(perms[0].numel() * 4), "d2h_bytes_per_step": 8,
+                       "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": hbm_gbs, "unit": "GB/s",
+                            "frac": per_gpu / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                            "note": "per-GPU algorithmic bytes of the step kernel over the WHOLE step time "
+                                    "(collective included)"},
+               "cpu_baseline": None}
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()

@@ -72,7 +72,7 @@ def mf_forward(U, V, d, users, items):
 
 def bpr_step(U, V, d, users, pos=None, neg=None, csr: DeviceCSR | None = None, lr=0.0, reg=0.0, sink=SINK_UPDATE,
              flags=0, seed=0, step=0, loss_sum=None, x_out=None, out_pos=None, out_neg=None, stage=None, gU=None,
-             gV=None):
+             gV=None, item_range=None, udelta=None, inv_batch=0.0):
     """models/MF.py:63-68 as one fused kernel (see b200rec_bpr_step)."""
     require_cuda(U, "U", torch.float32); require_cuda(V, "V", torch.float32)
     a = BprArgs()
@@ -93,12 +93,22 @@ def bpr_step(U, V, d, users, pos=None, neg=None, csr: DeviceCSR | None = None, l
     a.gV = ptr(require_cuda(gV, "gV", torch.float32)) if gV is not None else None
     a.loss_sum = ptr(require_cuda(loss_sum, "loss_sum", torch.float64)) if loss_sum is not None else None
     a.x_out = ptr(require_cuda(x_out, "x_out", torch.float32)) if x_out is not None else None
+    if item_range is not None:
+        a.item_lo, a.item_hi = int(item_range[0]), int(item_range[1])
+    a.udelta = ptr(require_cuda(udelta, "udelta", torch.float32)) if udelta is not None else None
+    a.inv_batch = float(inv_batch)
     check(_lib.lib().b200rec_bpr_step(C.byref(a), current_stream()))
 
 
 def bpr_apply(U, V, users, pos, neg, stage):
     check(_lib.lib().b200rec_bpr_apply(ptr(U), ptr(V), U.shape[1], ptr(_i32(users, "users")), ptr(_i32(pos, "pos")),
                                        ptr(_i32(neg, "neg")), users.numel(), ptr(stage), current_stream()))
+
+
+def rows_add(W, ids, delta, scale=1.0):
+    """W[ids[t]] += scale * delta[t] (vector atomics)."""
+    check(_lib.lib().b200rec_rows_add(ptr(W), W.shape[1], ptr(_i32(ids, "ids")), ids.numel(), ptr(delta),
+                                      delta.shape[-1], float(scale), current_stream()))
 
 
 def sample_triples(users, csr: DeviceCSR, seed, step):

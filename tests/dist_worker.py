@@ -1,0 +1,46 @@
+"""torchrun worker for tests/test_dist.py::test_torchrun_two_gpus_replicas_stay_identical."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from recsys_pytorch_b200 import synthetic
+    from recsys_pytorch_b200.dist import ItemShardedBPR, UserShardedBPR, shard_range
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    nu, ni, d, B = 20000, 8000, 128, 8192
+    train, _ = synthetic.make_interactions(nu, ni, seed=1, device=dev)
+    tr = ItemShardedBPR(nu, ni, d, train, rank, world, dev, lr=1.0, reg=0.001, init_std=0.1, seed=3)
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    for s in range(5):
+        users = torch.randperm(nu, device=dev, generator=g)[:B].to(torch.int32)
+        tr.step(users, s + 1)
+    chk = tr.U.double().sum().reshape(1)
+    both = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    assert all(torch.equal(b, both[0]) for b in both), "user replicas diverged"
+    ulo, uhi = shard_range(nu, world, rank)
+    trl, _ = synthetic.make_interactions(uhi - ulo, ni, seed=2 + rank, device=dev)
+    tu = UserShardedBPR(nu, ni, d, trl, rank, world, dev, lr=1.0, reg=0.001, init_std=0.1, seed=3)
+    for s in range(5):
+        users = torch.randperm(uhi - ulo, device=dev, generator=g)[:4096].to(torch.int32)
+        tu.step(users, s + 1, 4096 * world)
+    chk = tu.V.double().sum().reshape(1)
+    dist.all_gather(both, chk)
+    assert all(torch.equal(b, both[0]) for b in both), "item replicas diverged"
+    dist.barrier()
+    if rank == 0:
+        print("DIST_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+"""Multi-GPU layouts (recsys_pytorch_b200/dist.py).  The reference has no distributed code;
+the oracle is the single-device result on the triples the ranks actually used."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bpr_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_ranges_and_owner():
+    from recsys_pytorch_b200.dist import owner_of, shard_range
+    for n in (1, 7, 100, 1000, 100_000):
+        for w in (1, 2, 3, 4, 8):
+            if n < w:
+                continue
+            ranges = [shard_range(n, w, r) for r in range(w)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(ranges[r][1] == ranges[r + 1][0] for r in range(w - 1))
+            ids = np.arange(n)
+            own = owner_of(ids, n, w)
+            for r, (lo, hi) in enumerate(ranges):
+                assert (own[lo:hi] == r).all()
+
+
+def _gloo_worker(rank, world, port, q):
+    """Host-side exchange logic on CPU: ownership by positive item + one all-reduce of the
+    batch-aligned user-delta buffer == the single-process oracle gradient."""
+    import torch.distributed as dist
+    from recsys_pytorch_b200.dist import allreduce_sum, owner_of, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)                        # same stream on every rank
+    nu, ni, d, B = 40, 30, 8, 16
+    U = rng.standard_normal((nu, d)).astype(np.float32); V = rng.standard_normal((ni, d)).astype(np.float32)
+    u = rng.permutation(nu)[:B]; i = rng.integers(0, ni, B); j = rng.integers(0, ni, B)
+    lo, hi = shard_range(ni, world, rank)
+    mine = owner_of(i, ni, world) == rank
+    assert ((i >= lo) & (i < hi) == mine).all()
+    buf = torch.zeros((B, d), dtype=torch.float32)
+    _, _, g, _ = O.bpr_grads(U, V, u, i, j)
+    buf[mine] = torch.from_numpy((g[mine, None] * (V[i[mine]] - V[j[mine]])).astype(np.float32))
+    allreduce_sum(buf)
+    full = (g[:, None] * (V[i] - V[j])).astype(np.float32)
+    ok = np.allclose(buf.numpy(), full, rtol=1e-6, atol=1e-7)
+    q.put((rank, bool(ok), float(np.abs(buf.numpy()).sum())))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_user_delta_exchange():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok, _ in res)
+    assert abs(res[0][2] - res[1][2]) < 1e-6           # every replica ends with the same buffer
+
+
+# ---- GPU: both layouts emulated rank by rank on one device, checked against the oracle ----
+def _csr(rng, nu, ni, lo, hi, dev):
+    from recsys_pytorch_b200 import engine
+    rows = [np.sort(rng.choice(ni, rng.integers(lo, hi), replace=False)).astype(np.int32) for _ in range(nu)]
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+    return rows, engine.DeviceCSR(torch.from_numpy(indptr).to(dev), torch.from_numpy(np.concatenate(rows)).to(dev), (nu, ni))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_item_sharded_equals_single_device_oracle(dev, world):
+    from recsys_pytorch_b200.dist import ItemShardedBPR, shard_range
+    rng = np.random.default_rng(world)
+    nu, ni, d, B = 3000, 4000, 128, 1024
+    rows, csr = _csr(rng, nu, ni, 1, 40, dev)
+    ranks = [ItemShardedBPR(nu, ni, d, csr, r, world, dev, lr=5.0, reg=0.01, init_std=0.1, seed=5) for r in range(world)]
+    for r in ranks[1:]:
+        assert torch.equal(r.U, ranks[0].U)            # replicas start identical
+    U0 = ranks[0].U.cpu().numpy(); V0 = np.concatenate([r.V.cpu().numpy() for r in ranks])
+    users = torch.from_numpy(rng.permutation(nu)[:B].astype(np.int32)).to(dev)
+    outs, bufs = [], []
+    for r in ranks:
+        op, on = torch.full((B,), -7, dtype=torch.int32, device=dev), torch.full((B,), -7, dtype=torch.int32, device=dev)
+        bufs.append(r.local_compute(users, 3, out_pos=op, out_neg=on).clone())
+        outs.append((op.cpu().numpy(), on.cpu().numpy()))
+    total = torch.stack(bufs).sum(0)                     # what the all-reduce produces
+    for r in ranks:
+        r.apply_user_delta(users, total)
+    # every triple is owned by exactly one rank; its negative lies in the owner's range and is a non-positive
+    pos = np.full(B, -1); neg = np.full(B, -1)
+    for r, (op, on) in enumerate(outs):
+        lo, hi = shard_range(ni, world, r)
+        m = op >= 0
+        assert ((op[m] >= lo) & (op[m] < hi) & (on[m] >= lo) & (on[m] < hi)).all()
+        assert (pos[m] == -1).all()
+        pos[m], neg[m] = op[m], on[m]
+    assert (pos >= 0).all()
+    un = users.cpu().numpy()
+    for t in range(B):
+        assert pos[t] in rows[un[t]] and neg[t] not in rows[un[t]]
+    Ur, Vr, _ = O.sgd_step(U0, V0, un, pos, neg, 5.0, 0.01)
+    for r in ranks:
+        np.testing.assert_allclose(r.U.cpu().numpy(), Ur, rtol=2e-5, atol=2e-6)
+    Vg = np.concatenate([r.V.cpu().numpy() for r in ranks])
+    step = np.abs(Vr - V0).max()
+    assert np.abs(Vg - Vr).max() < 0.02 * step + 2e-6    # item rows: in-place (Hogwild) inside a rank
+
+
+@pytest.mark.gpu
+def test_user_sharded_equals_single_device_oracle(dev):
+    from recsys_pytorch_b200.dist import UserShardedBPR, shard_range
+    world = 2
+    rng = np.random.default_rng(9)
+    nu, ni, d, Bl = 2000, 1500, 64, 512
+    ranks, csrs, rowsets = [], [], []
+    for r in range(world):
+        lo, hi = shard_range(nu, world, r)
+        rows, csr = _csr(rng, hi - lo, ni, 1, 30, dev)
+        rowsets.append(rows)
+        ranks.append(UserShardedBPR(nu, ni, d, csr, r, world, dev, lr=5.0, reg=0.01, init_std=0.1, seed=5))
+    assert torch.equal(ranks[0].V, ranks[1].V)
+    V0 = ranks[0].V.cpu().numpy(); U0 = np.concatenate([r.U.cpu().numpy() for r in ranks])
+    us, ps, ns, dVs = [], [], [], []
+    for r, tr in enumerate(ranks):
+        lo, hi = shard_range(nu, world, r)
+        ul = torch.from_numpy(rng.permutation(hi - lo)[:Bl].astype(np.int32)).to(dev)
+        op, on = torch.empty_like(ul), torch.empty_like(ul)
+        dVs.append(tr.local_compute(ul, 4, Bl * world, out_pos=op, out_neg=on).clone())
+        us.append(ul.cpu().numpy() + lo); ps.append(op.cpu().numpy()); ns.append(on.cpu().numpy())
+    total = torch.stack(dVs).sum(0)
+    for tr in ranks:
+        tr.apply_item_delta(total)
+    u, i, j = np.concatenate(us), np.concatenate(ps), np.concatenate(ns)
+    Ur, Vr, _ = O.sgd_step(U0, V0, u, i, j, 5.0, 0.01)      # one global batch of world*Bl triples
+    np.testing.assert_allclose(np.concatenate([r.U.cpu().numpy() for r in ranks]), Ur, rtol=2e-5, atol=2e-6)
+    for tr in ranks:
+        np.testing.assert_allclose(tr.V.cpu().numpy(), Vr, rtol=2e-5, atol=2e-6)   # deltas from pre-step V: exact
+
+
+@pytest.mark.gpu
+def test_torchrun_two_gpus_replicas_stay_identical(dev):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    port = 29500 + os.getpid() % 500
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "DIST_OK" in out.stdout
