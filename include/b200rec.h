@@ -160,6 +160,12 @@ int b200rec_score_topk(const float *U, const float *V, int ld, int d, const int3
                        const int32_t *mask_indices, int k, int32_t *out_idx, float *out_score,
                        void *workspace, int64_t workspace_bytes, int algo, void *stream);
 
+/* Test hook (not part of the reference surface): the raw bf16 tensor-core scores of the
+ * B200REC_SCORE_TC candidate pass, dense fp32 [roundup(n_users,256), roundup(num_items,128)]. */
+int b200rec_debug_tc_scores(const float *U, const float *V, int ld, int d, const int32_t *users,
+                            int n_users, int num_items, float *dump, void *workspace,
+                            int64_t workspace_bytes, void *stream);
+
 /* models/MF.py:109-130 for the dense predict() contract (small U only):
  * out fp32 [n_users, num_items] = U[users] @ V^T with -inf at mask nonzeros. */
 int b200rec_predict_dense(const float *U, const float *V, int ld, int d, const int32_t *users,

@@ -1,10 +1,628 @@
-// tcgen05 scoring path - placeholder until the tensor-core kernel lands; refuses loudly.
+// Tensor-core scoring + top-K for sm_100a:  tcgen05 (UMMA) bf16 candidate pass with
+// TMEM accumulators and TMA-fed shared-memory tiles, followed by an exact fp32 re-rank.
+//
+// Replaces models/MF.py:109-112 (`user_latent @ all_item_latent.T`, cuBLAS SGEMM
+// when run on a GPU), the dense score matrix + -inf mask of MF.py:117-130 and the
+// per-row std::partial_sort_copy of evaluation/backend/cython/include/func.h:12-31.
+//
+// Exactness argument.  Let S be the fp32 scores the exact kernel
+// (score_exact.cu) would produce and S~ the bf16 tensor-core scores.  For a user row
+// |S~ - S| <= eps = c * |u|_2 * max_v |v|_2 with c = 2^-8 (two bf16 roundings) plus
+// the fp32 accumulation slack.  If tau is ANY lower bound on the K'-th largest S~ of
+// the row (K' = K + #masked items of the user, so that at least K unmasked items
+// lie above it), every item of the exact top-K has S~ >= tau - 2 eps.  The candidate
+// pass therefore keeps, per row, every item with S~ >= tau - 2 eps, raising tau as it
+// goes (bucketed selection over the row's candidate buffer); the re-rank kernel then
+// drops masked items, recomputes the survivors with the SAME k-ordered fp32 FMA
+// chain as the exact kernel and selects the top-K by (score desc, id asc).  Rows whose
+// candidate buffer cannot hold K' + slack entries are flagged and re-done by the
+// exact kernel, so the result is always identical to B200REC_SCORE_EXACT.
+//
+// Kernel roles (one CTA = 256 user rows x all item tiles of 128):
+//   warp 0      TMA producer: A (users) once, B (items) k-blocks through a smem ring
+//   warp 1      MMA issuer: tcgen05.mma.kind::f16, M=128 x N=128 x K=16, two M halves,
+//               double-buffered 4 x 128 TMEM columns; tcgen05.commit frees smem / signals tiles
+//   warps 2-9   epilogue: tcgen05.ld 32x32b (thread == user row), 3-input FMNMX threshold
+//               filter, candidate append, warp-cooperative threshold raise
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
 #include "common.cuh"
+#include "topk_list.cuh"
+
 namespace b200 {
-int64_t score_topk_tc_workspace(int, int, int, int) { return 0; }
-int score_topk_tc(const float *, const float *, int, int, const int32_t *, int, int, const int64_t *, const int32_t *,
-                  int, int32_t *, float *, void *, int64_t, cudaStream_t) {
-    set_error("score_topk: B200REC_SCORE_TC is not built in this revision");
-    return B200REC_EUNSUPPORTED;
+
+int score_topk_exact(const float *U, const float *V, int ld, int d, const int32_t *users, int n_users, int num_items,
+                     const int64_t *mi, const int32_t *mx, int k, int32_t *oi, float *os, float *dense,
+                     cudaStream_t s);
+
+constexpr int kBM = 256;        // user rows per CTA (two M=128 halves)
+constexpr int kBN = 128;        // items per tile
+constexpr int kBK = 64;         // bf16 per k-block = one 128-byte swizzle row
+constexpr int kCand = 512;      // candidate slots per row
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kRowsPerLaunch = 148 * kBM * 2;
+
+// ---- PTX wrappers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                     "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc),
+        "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO=1 [16,30) | SBO=1024B>>4 [32,46) | version=1 [46,48) | layout=2 (SW128) [61,64)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=128, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((128u >> 4) << 24);
+
+// ---- pre-pass: fp32 rows -> bf16 [rows_pad, dpad] (+ row norms, + global max norm) ------------
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float *__restrict__ src, int ld, int d,
+                                                      const int32_t *__restrict__ ids, int rows, int rows_pad,
+                                                      int dpad, __nv_bfloat16 *__restrict__ dst,
+                                                      float *__restrict__ norms, unsigned *__restrict__ max_norm_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = w; r < rows_pad; r += nw) {
+        const float *p = (r < rows) ? src + (int64_t)(ids ? ids[r] : r) * ld : nullptr;
+        float ss = 0.f;
+        for (int c = lane; c < dpad; c += 32) {
+            const float v = (p && c < d) ? p[c] : 0.f;
+            ss = fmaf(v, v, ss);
+            dst[r * dpad + c] = __float2bfloat16_rn(v);
+        }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) {
+            const float nrm = sqrtf(ss) * 1.0000005f;  // rounded up a hair: it feeds an upper bound
+            if (norms && r < rows) norms[r] = nrm;
+            if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nrm));  // nonneg floats order as uints
+        }
+    }
+}
+
+struct TcParams {
+    int n_rows, num_items, n_tiles, k, d;
+    const int32_t *users;            // row -> user id (mask row)
+    const int64_t *mask_indptr;      // may be NULL
+    const float *row_norm;           // [n_rows]
+    const unsigned *vmax_bits;       // [1]
+    uint64_t *cand;                  // [n_rows, kCand]  (ordered approx score << 32 | item id)
+    int32_t *cand_cnt;               // [n_rows]  (-1 = overflow: re-do with the exact kernel)
+    float *dump;                     // bring-up: dense [n_rows_pad, n_tiles*kBN] approx scores, else NULL
+};
+
+// warp-cooperative threshold raise for the lanes in `need` (bit per lane); see file header
+__device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &thr, int keff,
+                                                 float eps2, int *hist, int lane) {
+    while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        uint64_t *base = reinterpret_cast<uint64_t *>(__shfl_sync(0xffffffffu, (unsigned long long)my_cand, L));
+        const int n = __shfl_sync(0xffffffffu, cnt, L);
+        const int kf = __shfl_sync(0xffffffffu, keff, L);
+        const float e2 = __shfl_sync(0xffffffffu, eps2, L);
+        uint64_t e[kCand / 32];
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kCand / 32; ++i) {
+            const int p = lane + 32 * i;
+            e[i] = (p < n) ? base[p] : 0ull;
+            if (p < n) {
+                const float s = ord2f((uint32_t)(e[i] >> 32));
+                mn = fminf(mn, s); mx = fmaxf(mx, s);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        hist[lane] = 0;
+        __syncwarp();
+        const float scale = (mx > mn) ? 32.f / (mx - mn) : 0.f;
+#pragma unroll
+        for (int i = 0; i < kCand / 32; ++i) {
+            if (lane + 32 * i < n) {
+                int b = (int)((ord2f((uint32_t)(e[i] >> 32)) - mn) * scale);
+                b = b > 31 ? 31 : (b < 0 ? 0 : b);
+                atomicAdd(&hist[b], 1);
+            }
+        }
+        __syncwarp();
+        int suf = hist[lane];  // suffix sum: entries in buckets >= lane
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_down_sync(0xffffffffu, suf, o);
+            if (lane + o < 32) suf += t;
+        }
+        const unsigned okb = __ballot_sync(0xffffffffu, suf >= kf);
+        const int bstar = okb ? 31 - __clz(okb) : 0;
+        // tau = smallest score among the entries in buckets >= bstar  (so at least kf entries are >= tau)
+        float tau = INFINITY;
+#pragma unroll
+        for (int i = 0; i < kCand / 32; ++i) {
+            if (lane + 32 * i < n) {
+                const float s = ord2f((uint32_t)(e[i] >> 32));
+                int b = (int)((s - mn) * scale);
+                b = b > 31 ? 31 : (b < 0 ? 0 : b);
+                if (b >= bstar) tau = fminf(tau, s);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
+        const float old_thr = __shfl_sync(0xffffffffu, thr, L);
+        float new_thr = fmaxf(old_thr, tau - e2);
+        // compact: keep entries with score >= new_thr
+        int keep = 0;
+#pragma unroll
+        for (int i = 0; i < kCand / 32; ++i)
+            if (lane + 32 * i < n && ord2f((uint32_t)(e[i] >> 32)) >= new_thr) ++keep;
+        int pre = keep;  // inclusive scan
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        int w = pre - keep;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kCand / 32; ++i)
+            if (lane + 32 * i < n && ord2f((uint32_t)(e[i] >> 32)) >= new_thr) base[w++] = e[i];
+        __syncwarp();
+        if (lane == L) {
+            if (total > kCand - 64) { cnt = -1; thr = INFINITY; }  // cannot make room: exact kernel re-does the row
+            else { cnt = total; thr = new_thr; }
+        }
+    }
+}
+
+template <int KB>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const TcParams p, const int n_stages) {
+    extern __shared__ unsigned char smem_dyn[];
+    // SWIZZLE_128B operands need 1024-byte alignment: round the dynamic base up (1 KB of slack is allocated)
+    unsigned char *smem_raw = smem_dyn + ((1024u - (s32(smem_dyn) & 1023u)) & 1023u);
+    // layout: A[KB][256 rows][128 B] | B ring [n_stages][128 rows][128 B] | barriers | hist
+    unsigned char *smA = smem_raw;
+    unsigned char *smB = smA + (size_t)KB * kBM * 128;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smB + (size_t)n_stages * kBN * 128);
+    uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *afull = bars + 20;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
+    int *hist_all = reinterpret_cast<int *>(bars + 22);  // [kEpiWarps][32]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kBM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; ++s) { mbar_init(s32(full + s), 1); mbar_init(s32(empty + s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(s32(tfull + a), 1); mbar_init(s32(tempty + a), kEpiWarps); }
+        mbar_init(s32(afull), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (4 accumulators of 128 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(s32(afull), (uint32_t)KB * kBM * 128);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(s32(smA + (size_t)kb * kBM * 128), &tmA, kb * kBK, row0, s32(afull));
+            uint32_t it = 0;
+            for (int t = 0; t < p.n_tiles; ++t) {
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+                    mbar_wait(s32(empty + s), ph ^ 1u);
+                    mbar_expect_tx(s32(full + s), kBN * 128);
+                    tma_load_2d(s32(smB + (size_t)s * kBN * 128), &tmB, kb * kBK, t * kBN, s32(full + s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            mbar_wait(s32(afull), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t it = 0;
+            for (int t = 0; t < p.n_tiles; ++t) {
+                const uint32_t as = t & 1, aph = (t >> 1) & 1u;
+                mbar_wait(s32(tempty + as), aph ^ 1u);  // epilogue has drained this accumulator pair
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+                    mbar_wait(s32(full + s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t bdesc = smem_desc_sw128(s32(smB + (size_t)s * kBN * 128));
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t adesc = smem_desc_sw128(s32(smA + (size_t)kb * kBM * 128 + (size_t)h * 128 * 128));
+                        const uint32_t dcol = tmem_base + (as * 2 + h) * kBN;
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)  // +32 B along K inside the swizzle atom = +2 in the address field
+                            umma_bf16(dcol, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(s32(empty + s));  // smem slot reusable once these MMAs have read it
+                }
+                umma_commit(s32(tfull + as));     // accumulators of tile t complete
+            }
+        }
+    } else {
+        // ================= epilogue: thread == user row =================
+        const int ew = warp - 2;
+        const int q = warp & 3;            // TMEM lane quadrant this warp may touch
+        const int h = ew >> 2;             // M half
+        const int r_local = h * 128 + q * 32 + lane;
+        const int row = row0 + r_local;
+        const bool row_ok = row < p.n_rows;
+        int *hist = hist_all + ew * 32;
+        uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
+        int cnt = 0, keff = p.k;
+        float thr = -INFINITY, eps2 = 0.f;
+        if (row_ok) {
+            if (p.mask_indptr) {
+                const int u = p.users[row];
+                keff += (int)(p.mask_indptr[u + 1] - p.mask_indptr[u]);
+            }
+            const float vmax = __uint_as_float(*p.vmax_bits);
+            const float c = 0.00390625f * 1.05f + (float)p.d * 2.4e-7f;  // 2^-8 (+5%) + fp32 accumulation slack
+            eps2 = 2.f * c * p.row_norm[row] * vmax;
+            if (keff > kCand / 2 - 32) { cnt = -1; thr = INFINITY; }      // too many masked items for the buffer
+        } else {
+            thr = INFINITY;
+        }
+        for (int t = 0; t < p.n_tiles; ++t) {
+            const uint32_t as = t & 1, aph = (t >> 1) & 1u;
+            mbar_wait(s32(tfull + as), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int n0 = t * kBN;
+            const bool ragged = n0 + kBN > p.num_items;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kBN; c0 += 32) {
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + h) * kBN + c0, rr);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+                if (p.dump) {
+                    float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)p.n_tiles * kBN) + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                }
+                if (ragged) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c0 + j >= p.num_items) v[j] = -INFINITY;
+                }
+                float gm[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float a = max3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
+                    const float b = max3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
+                    gm[g] = max3(a, b, fmaxf(v[8 * g + 6], v[8 * g + 7]));
+                }
+                const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+                if (m >= thr) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (gm[g] >= thr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float s = v[8 * g + j];
+                                if (s >= thr && cnt >= 0) {
+                                    my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (uint32_t)(n0 + c0 + 8 * g + j);
+                                    ++cnt;
+                                }
+                            }
+                        }
+                    }
+                }
+                const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - 33);
+                if (need) raise_thresholds(need, my_cand, cnt, thr, keff, eps2, hist, lane);
+            }
+            // this warp is done reading the accumulator pair of tile t
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s32(tempty + as));
+        }
+        if (row_ok) p.cand_cnt[row] = cnt;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// ---- exact fp32 re-rank of the candidates (same k-ordered FMA chain as score_exact.cu) ---------
+__global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U, const float *__restrict__ V, int ld,
+                                                     int d, const int32_t *__restrict__ users, int n_rows, int k,
+                                                     const int64_t *__restrict__ mask_indptr,
+                                                     const int32_t *__restrict__ mask_indices,
+                                                     const uint64_t *__restrict__ cand,
+                                                     const int32_t *__restrict__ cand_cnt, int32_t *__restrict__ out_idx,
+                                                     float *__restrict__ out_score, int32_t *__restrict__ redo_rows,
+                                                     int32_t *__restrict__ redo_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t *rk = reinterpret_cast<uint64_t *>(smem_raw) + (size_t)wid * k;
+    float *us = reinterpret_cast<float *>(smem_raw + (size_t)8 * k * 8) + (size_t)wid * d;
+    for (int row = blockIdx.x * 8 + wid; row < n_rows; row += gridDim.x * 8) {
+        const int n = cand_cnt[row];
+        if (n < 0) {  // overflow / too many masked items: the exact kernel re-does this row
+            if (lane == 0) redo_rows[atomicAdd(redo_count, 1)] = row;
+            continue;
+        }
+        const int u = users[row];
+        for (int c = lane; c < d; c += 32) us[c] = U[(int64_t)u * ld + c];
+        for (int pp = lane; pp < k; pp += 32) rk[pp] = make_key(-INFINITY, 0x7FFFFFFF);
+        __syncwarp();
+        const int32_t *mrow = nullptr;
+        int mdeg = 0;
+        if (mask_indptr) { mrow = mask_indices + mask_indptr[u]; mdeg = (int)(mask_indptr[u + 1] - mask_indptr[u]); }
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int c = c0 + lane;
+            bool ok = c < n;
+            uint64_t key = 0;
+            if (ok) {
+                const int item = (int)(uint32_t)(cand[(size_t)row * kCand + c] & 0xFFFFFFFFu);
+                int l = 0, r = mdeg;  // masked? (models/MF.py:130)
+                while (l < r) { const int m = (l + r) >> 1; if (mrow[m] < item) l = m + 1; else r = m; }
+                if (l < mdeg && mrow[l] == item) ok = false;
+                if (ok) {
+                    const float *pv = V + (int64_t)item * ld;
+                    float acc = 0.f;
+                    for (int kk = 0; kk < d; ++kk) acc = fmaf(us[kk], pv[kk], acc);  // ascending k: the oracle's chain
+                    key = make_key(acc, item);
+                }
+            }
+            topk_list_offer(rk, k, key, ok, lane);
+        }
+        __syncwarp();
+        for (int pp = lane; pp < k; pp += 32) {
+            out_idx[(int64_t)row * k + pp] = key_id(rk[pp]);
+            if (out_score) out_score[(int64_t)row * k + pp] = key_score(rk[pp]);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void gather_ids_kernel(const int32_t *users, const int32_t *rows, int n, int32_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = users[rows[i]];
+}
+__global__ void scatter_rows_kernel(const int32_t *rows, int n, int k, const int32_t *src_idx, const float *src_sc,
+                                    int32_t *dst_idx, float *dst_sc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * k) {
+        const int r = rows[i / k], c = i % k;
+        dst_idx[(int64_t)r * k + c] = src_idx[i];
+        if (dst_sc) dst_sc[(int64_t)r * k + c] = src_sc[i];
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 [rows, dpad] row-major; box = 64 elements (128 B, SWIZZLE_128B) x box_rows
+static int make_map(CUtensorMap *m, void *base, uint64_t rows, uint64_t dpad, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    B200_REQUIRE(fn != nullptr, B200REC_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[2] = {dpad, rows};
+    cuuint64_t strides[1] = {dpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, B200REC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return B200REC_OK;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct TcLayout {
+    int dpad, KB, rows_cap, items_pad;
+    size_t off_vb, off_ub, off_norm, off_vmax, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, total;
+};
+static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
+    TcLayout L;
+    L.dpad = (int)align_up(d, kBK);
+    L.KB = L.dpad / kBK;
+    L.rows_cap = n_users < kRowsPerLaunch ? (int)align_up(n_users > 0 ? n_users : 1, kBM) : kRowsPerLaunch;
+    L.items_pad = (int)align_up(num_items, kBN);
+    size_t o = 0;
+    L.off_vb = o; o = align_up(o + (size_t)L.items_pad * L.dpad * 2, 1024);
+    L.off_ub = o; o = align_up(o + (size_t)L.rows_cap * L.dpad * 2, 1024);
+    L.off_norm = o; o = align_up(o + (size_t)L.rows_cap * 4, 256);
+    L.off_vmax = o; o = align_up(o + 4, 256);
+    L.off_cand = o; o = align_up(o + (size_t)L.rows_cap * kCand * 8, 256);
+    L.off_cnt = o; o = align_up(o + (size_t)L.rows_cap * 4, 256);
+    L.off_redo = o; o = align_up(o + (size_t)L.rows_cap * 4, 256);
+    L.off_redo_n = o; o = align_up(o + 4, 256);
+    L.off_ruser = o; o = align_up(o + (size_t)L.rows_cap * 4, 256);
+    L.off_ridx = o; o = align_up(o + (size_t)L.rows_cap * k * 4, 256);
+    L.off_rsc = o; o = align_up(o + (size_t)L.rows_cap * k * 4, 256);
+    L.total = o;
+    return L;
+}
+
+int64_t score_topk_tc_workspace(int n_users, int num_items, int d, int k) {
+    return (int64_t)tc_layout(n_users, num_items, d, k).total + 1024;
+}
+
+template <int KB>
+static int launch_candidates(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int n_blocks,
+                             cudaStream_t s) {
+    auto kern = tc_candidate_kernel<KB>;
+    const size_t a_bytes = (size_t)KB * kBM * 128;
+    int stages = (int)((224 * 1024 - a_bytes - 4096) / (kBN * 128));
+    if (stages > 8) stages = 8;
+    B200_REQUIRE(stages >= 2, B200REC_EUNSUPPORTED, "score_topk TC: d too large for shared memory");
+    const size_t smem = 1024 + a_bytes + (size_t)stages * kBN * 128 + 22 * 8 + kEpiWarps * 32 * 4 + 64;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int32_t *users, int n_users,
+                       int num_items, const int64_t *mi, const int32_t *mx, int k, int32_t *oi, float *os, void *ws,
+                       int64_t ws_bytes, float *dump, cudaStream_t s) {
+    if (n_users <= 0) return B200REC_OK;
+    B200_REQUIRE(d <= 256, B200REC_EUNSUPPORTED, "score_topk TC: d <= 256 (got %d)", d);
+    B200_REQUIRE(k <= kCand / 4, B200REC_EUNSUPPORTED, "score_topk TC: k <= %d (got %d)", kCand / 4, k);
+    const TcLayout L = tc_layout(n_users, num_items, d, k);
+    unsigned char *base = reinterpret_cast<unsigned char *>(align_up((size_t)ws, 1024));
+    B200_REQUIRE(ws && (int64_t)((base - (unsigned char *)ws) + L.total) <= ws_bytes, B200REC_ENOMEM,
+                 "score_topk TC: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)L.total + 1024);
+    __nv_bfloat16 *vb = reinterpret_cast<__nv_bfloat16 *>(base + L.off_vb);
+    __nv_bfloat16 *ub = reinterpret_cast<__nv_bfloat16 *>(base + L.off_ub);
+    float *norms = reinterpret_cast<float *>(base + L.off_norm);
+    unsigned *vmax = reinterpret_cast<unsigned *>(base + L.off_vmax);
+    uint64_t *cand = reinterpret_cast<uint64_t *>(base + L.off_cand);
+    int32_t *cnt = reinterpret_cast<int32_t *>(base + L.off_cnt);
+    int32_t *redo = reinterpret_cast<int32_t *>(base + L.off_redo);
+    int32_t *redo_n = reinterpret_cast<int32_t *>(base + L.off_redo_n);
+    int32_t *ruser = reinterpret_cast<int32_t *>(base + L.off_ruser);
+    int32_t *ridx = reinterpret_cast<int32_t *>(base + L.off_ridx);
+    float *rsc = reinterpret_cast<float *>(base + L.off_rsc);
+    const int sms = sm_count();
+
+    // item table -> bf16 once per call
+    B200_CUDA(cudaMemsetAsync(vmax, 0, 4, s));
+    to_bf16_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, num_items, L.items_pad, L.dpad, vb, nullptr, vmax);
+    B200_LAUNCH_CHECK();
+    CUtensorMap mb;
+    int rc = make_map(&mb, vb, (uint64_t)L.items_pad, (uint64_t)L.dpad, kBN);
+    if (rc) return rc;
+
+    for (int r0 = 0; r0 < n_users; r0 += L.rows_cap) {
+        const int nr = (n_users - r0) < L.rows_cap ? (n_users - r0) : L.rows_cap;
+        const int nr_pad = (int)align_up(nr, kBM);
+        to_bf16_kernel<<<sms * 4, 256, 0, s>>>(U, ld, d, users + r0, nr, nr_pad, L.dpad, ub, norms, nullptr);
+        B200_LAUNCH_CHECK();
+        CUtensorMap ma;
+        if ((rc = make_map(&ma, ub, (uint64_t)nr_pad, (uint64_t)L.dpad, kBM))) return rc;
+        TcParams p;
+        p.n_rows = nr; p.num_items = num_items; p.n_tiles = L.items_pad / kBN; p.k = k; p.d = d;
+        p.users = users + r0; p.mask_indptr = mi; p.row_norm = norms; p.vmax_bits = vmax;
+        p.cand = cand; p.cand_cnt = cnt; p.dump = dump ? dump + (size_t)r0 * L.items_pad : nullptr;
+        switch (L.KB) {
+            case 1: rc = launch_candidates<1>(ma, mb, p, nr_pad / kBM, s); break;
+            case 2: rc = launch_candidates<2>(ma, mb, p, nr_pad / kBM, s); break;
+            case 3: rc = launch_candidates<3>(ma, mb, p, nr_pad / kBM, s); break;
+            default: rc = launch_candidates<4>(ma, mb, p, nr_pad / kBM, s); break;
+        }
+        if (rc) return rc;
+        if (!oi) continue;  // dump-only bring-up call
+        B200_CUDA(cudaMemsetAsync(redo_n, 0, 4, s));
+        const size_t rsmem = (size_t)8 * k * 8 + (size_t)8 * d * 4;
+        B200_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        int rgrid = (nr + 7) / 8;
+        if (rgrid > sms * 8) rgrid = sms * 8;
+        rerank_kernel<<<rgrid, 256, rsmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, cand, cnt, oi + (size_t)r0 * k,
+                                                os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
+        B200_LAUNCH_CHECK();
+        int n_redo = 0;
+        B200_CUDA(cudaMemcpyAsync(&n_redo, redo_n, 4, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaStreamSynchronize(s));
+        if (n_redo > 0) {  // rows the candidate buffer could not hold: exact kernel, then scatter back
+            gather_ids_kernel<<<(n_redo + 255) / 256, 256, 0, s>>>(users + r0, redo, n_redo, ruser);
+            B200_LAUNCH_CHECK();
+            if ((rc = score_topk_exact(U, V, ld, d, ruser, n_redo, num_items, mi, mx, k, ridx, os ? rsc : nullptr,
+                                       nullptr, s)))
+                return rc;
+            scatter_rows_kernel<<<(n_redo * k + 255) / 256, 256, 0, s>>>(redo, n_redo, k, ridx, os ? rsc : nullptr,
+                                                                         oi + (size_t)r0 * k,
+                                                                         os ? os + (size_t)r0 * k : nullptr);
+            B200_LAUNCH_CHECK();
+        }
+    }
+    return B200REC_OK;
+}
+
+int score_topk_tc(const float *U, const float *V, int ld, int d, const int32_t *users, int n_users, int num_items,
+                  const int64_t *mi, const int32_t *mx, int k, int32_t *oi, float *os, void *ws, int64_t ws_bytes,
+                  cudaStream_t s) {
+    return score_topk_tc_impl(U, V, ld, d, users, n_users, num_items, mi, mx, k, oi, os, ws, ws_bytes, nullptr, s);
+}
+
 }  // namespace b200
+
+// bring-up / test hook: raw bf16 tensor-core scores of the candidate pass, dense fp32
+// [rows_pad(256), items_pad(128)] row-major (no top-k).  Not part of the reference surface.
+extern "C" int b200rec_debug_tc_scores(const float *U, const float *V, int ld, int d, const int32_t *users, int n_users,
+                                       int num_items, float *dump, void *workspace, int64_t workspace_bytes,
+                                       void *stream) {
+    using namespace b200;
+    B200_REQUIRE(U && V && users && dump && workspace, B200REC_EINVAL, "debug_tc_scores: null argument");
+    B200_REQUIRE(n_users <= kRowsPerLaunch, B200REC_EINVAL, "debug_tc_scores: at most %d rows", kRowsPerLaunch);
+    return score_topk_tc_impl(U, V, ld, d, users, n_users, num_items, nullptr, nullptr, 1, nullptr, nullptr, workspace,
+                              workspace_bytes, dump, (cudaStream_t)stream);
+}

@@ -147,6 +147,19 @@ def score_topk(U, V, d, users, mask: DeviceCSR | None, k, algo=SCORE_EXACT, want
     return idx, sc
 
 
+def debug_tc_scores(U, V, d, users):
+    """Test hook: raw bf16 tensor-core scores of the candidate pass, fp32 [n, I]."""
+    users = _i32(users, "users")
+    n, ni = users.numel(), V.shape[0]
+    rp, ip = (n + 255) // 256 * 256, (ni + 127) // 128 * 128
+    out = torch.zeros((rp, ip), dtype=torch.float32, device=U.device)
+    ws_bytes = int(_lib.lib().b200rec_score_topk_workspace(n, ni, d, 1, SCORE_TC))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=U.device)
+    check(_lib.lib().b200rec_debug_tc_scores(ptr(U), ptr(V), U.shape[1], d, ptr(users), n, ni, ptr(out), ptr(ws),
+                                             ws_bytes, current_stream()))
+    return out[:n, :ni]
+
+
 def predict_dense(U, V, d, users, mask: DeviceCSR | None):
     """models/MF.py:109-130 for a chunk of users: fp32 [n, I] with -inf at mask nonzeros."""
     users = _i32(users, "users")

@@ -1,0 +1,95 @@
+"""`-m gpu`: the tcgen05 scoring path (B200REC_SCORE_TC).  The bar: the fused
+tensor-core candidate pass + fp32 re-rank returns EXACTLY what the exact CUDA-core
+kernel returns (which tests/test_gpu_parity.py pins bit-exactly to the C oracle)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from recsys_pytorch_b200 import engine  # noqa: E402
+from recsys_pytorch_b200._lib import SCORE_EXACT, SCORE_TC  # noqa: E402
+
+
+def _tables(rng, nu, ni, d, dev, std=1.0):
+    U = engine.alloc_table(nu, d, dev, std=0.0); V = engine.alloc_table(ni, d, dev, std=0.0)
+    U[:, :d] = torch.from_numpy((rng.standard_normal((nu, d)) * std).astype(np.float32)).to(dev)
+    V[:, :d] = torch.from_numpy((rng.standard_normal((ni, d)) * std).astype(np.float32)).to(dev)
+    return U, V
+
+
+def _mask(rng, nu, ni, lo, hi, dev, heavy=()):
+    rows = []
+    for u in range(nu):
+        n = hi * 6 if u in heavy else int(rng.integers(lo, hi))
+        rows.append(np.sort(rng.choice(ni, min(n, ni - 200), replace=False)).astype(np.int32))
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+    return engine.DeviceCSR(torch.from_numpy(indptr).to(dev), torch.from_numpy(np.concatenate(rows)).to(dev), (nu, ni))
+
+
+@pytest.mark.parametrize("d", [128, 64, 50, 256, 200, 150, 8])
+def test_tc_raw_scores_are_the_bf16_gemm(dev, d):
+    """TMA tiles + UMMA descriptors + TMEM read-back: the candidate pass computes bf16(U) . bf16(V)^T."""
+    rng = np.random.default_rng(d)
+    nu, ni = 300, 1000                      # ragged in both tile dimensions
+    U, V = _tables(rng, nu, ni, d, dev)
+    users = torch.from_numpy(rng.permutation(nu).astype(np.int32)).to(dev)
+    got = engine.debug_tc_scores(U, V, d, users)
+    Ub = U[users.long(), :d].to(torch.bfloat16).to(torch.float64)
+    Vb = V[:, :d].to(torch.bfloat16).to(torch.float64)
+    ref = (Ub @ Vb.T).to(torch.float32)
+    scale = float(torch.linalg.norm(Ub, dim=1).max() * torch.linalg.norm(Vb, dim=1).max())
+    err = float((got - ref).abs().max())
+    assert err < 2e-6 * scale, f"max |tc - bf16 gemm| = {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("d,k,nu,ni,std", [(128, 10, 300, 3000, 1.0), (128, 100, 513, 20000, 1.0), (64, 100, 256, 9000, 0.1),
+                                            (50, 10, 100, 1682, 1.0), (256, 100, 260, 5000, 0.05), (32, 5, 943, 1682, 1.0)])
+def test_tc_equals_exact(dev, d, k, nu, ni, std):
+    rng = np.random.default_rng(d + k)
+    U, V = _tables(rng, nu, ni, d, dev, std)
+    mask = _mask(rng, nu, ni, 0, 60, dev)
+    users = torch.from_numpy(rng.permutation(nu).astype(np.int32)).to(dev)
+    ie, se = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_EXACT)
+    it, st = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_TC)
+    assert torch.equal(it, ie), f"{(it != ie).sum().item()} of {it.numel()} ids differ"
+    assert torch.equal(st, se)                      # same k-ordered fp32 FMA chain in the re-rank: bit-exact
+    it2, _ = engine.score_topk(U, V, d, users, None, k, algo=SCORE_TC)
+    ie2, _ = engine.score_topk(U, V, d, users, None, k, algo=SCORE_EXACT)
+    assert torch.equal(it2, ie2)
+
+
+def test_tc_heavy_mask_rows_and_ties_fall_back_to_exact(dev):
+    """Rows whose K + #masked exceeds the candidate buffer, and rows drowning in exact ties
+    (integer tables: bf16 is exact, thousands of equal scores), are re-done by the exact kernel."""
+    rng = np.random.default_rng(3)
+    nu, ni, d, k = 300, 6000, 64, 100
+    U = engine.alloc_table(nu, d, dev, std=0.0); V = engine.alloc_table(ni, d, dev, std=0.0)
+    U[:, :d] = torch.from_numpy(rng.integers(-1, 2, (nu, d)).astype(np.float32)).to(dev)
+    V[:, :d] = torch.from_numpy(rng.integers(-1, 2, (ni, d)).astype(np.float32)).to(dev)
+    mask = _mask(rng, nu, ni, 0, 60, dev, heavy=set(range(0, nu, 7)))
+    users = torch.arange(nu, dtype=torch.int32, device=dev)
+    ie, se = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_EXACT)
+    it, st = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_TC)
+    assert torch.equal(it, ie) and torch.equal(st, se)
+
+
+def test_tc_large_catalogue_properties(dev):
+    """BASELINE configs[1] item count (100k), top-100: sorted by (score desc, id asc), no masked item,
+    identical to the exact kernel on a sample of rows."""
+    rng = np.random.default_rng(5)
+    nu, ni, d, k = 2048, 100_000, 128, 100
+    U, V = _tables(rng, nu, ni, d, dev, 0.1)
+    mask = _mask(rng, nu, ni, 10, 120, dev)
+    users = torch.arange(nu, dtype=torch.int32, device=dev)
+    it, st = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_TC)
+    s = st.cpu().numpy(); i = it.cpu().numpy()
+    assert (np.diff(s, axis=1) <= 0).all()
+    ties = np.diff(s, axis=1) == 0
+    assert (np.diff(i, axis=1)[ties] > 0).all()
+    ip, ix = mask.indptr.cpu().numpy(), mask.indices.cpu().numpy()
+    for u in range(0, nu, 97):
+        assert not set(i[u]) & set(ix[ip[u]:ip[u + 1]])
+    sample = users[::16].contiguous()
+    ie, se = engine.score_topk(U, V, d, sample, mask, k, algo=SCORE_EXACT)
+    assert torch.equal(it[::16], ie) and torch.equal(st[::16], se)
