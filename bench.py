@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-CFG = dict(num_users=1_000_000, num_items=100_000, d=128, batch=1_000_000, seed=2020, lr=0.05, reg=1e-4,
+CFG = dict(num_users=1_000_000, num_items=100_000, d=128, batch=1_000_000, seed=2020, lr=0.05 * 1_000_000, reg=1e-4,
            init_std=0.01, eval_users=32_768, eval_k=10)
 FALLBACK_HBM_GBS = 6650.0
 
@@ -313,7 +313,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gather", default="tma", choices=["tma", "ldg"])
+    ap.add_argument("--gather", default="ldg", choices=["tma", "ldg"])
     ap.add_argument("--score-algo", dest="score_algo", default="exact", choices=["exact", "tc"])
     ap.add_argument("--layout", default="item_sharded", choices=["item_sharded", "user_sharded"])
     ap.add_argument("--small", action="store_true", help="tiny shapes for a quick functional run (NOT a bench value)")

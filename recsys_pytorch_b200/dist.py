@@ -58,7 +58,7 @@ class ItemShardedBPR:
     """north_star layout.  `train` is the GLOBAL DeviceCSR of positives (replicated)."""
 
     def __init__(self, num_users, num_items, d, train, rank, world, device, lr=0.05, reg=0.0, init_std=0.01,
-                 seed=2020, gather="tma"):
+                 seed=2020, gather="ldg"):
         self.num_users, self.num_items, self.d = num_users, num_items, d
         self.rank, self.world, self.device = rank, world, device
         self.lr, self.reg, self.seed = lr, reg, seed
@@ -98,7 +98,7 @@ class UserShardedBPR:
     """transpose layout.  `train_local` holds the CSR rows of this rank's users (local row ids)."""
 
     def __init__(self, num_users, num_items, d, train_local, rank, world, device, lr=0.05, reg=0.0, init_std=0.01,
-                 seed=2020, gather="tma"):
+                 seed=2020, gather="ldg"):
         self.num_users, self.num_items, self.d = num_users, num_items, d
         self.rank, self.world, self.device = rank, world, device
         self.lr, self.reg, self.seed = lr, reg, seed

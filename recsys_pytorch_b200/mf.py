@@ -14,7 +14,8 @@ Extra hparams (all optional; defaults keep `conf/MF.yaml` working):
     step        'fused' (ONE kernel per batch, Hogwild inside a step) |
                 'exact' (stage + apply: autograd's pre-step-weights semantics)
     sampler     'device' (default) | 'reference' (generators.py:168-224 call for call)
-    gather      'tma' (cp.async.bulk ring, default) | 'ldg'
+    gather      'ldg' (default: per-lane float4 loads, 2.2 G triples/s) | 'tma' (cp.async.bulk ring; the
+                TMA engine issues ~1 bulk copy per 50 cycles, so 512-byte row gathers cap at 1.75 G triples/s)
     init_std    embedding init std (nn.Embedding default N(0,1), MF.py:23-24)
     score_algo  'exact' | 'tc'   scoring kernel used by predict_topk
     seed        sampler / permutation seed
@@ -97,7 +98,7 @@ class MF(BaseModel):
         self.reg = float(_hp(hparams, "reg", 0.0))
         self.step_mode = str(_hp(hparams, "step", "fused")).lower()
         self.sampler = str(_hp(hparams, "sampler", "device")).lower()
-        self.gather = str(_hp(hparams, "gather", "tma")).lower()
+        self.gather = str(_hp(hparams, "gather", "ldg")).lower()
         self.score_algo = SCORE_TC if str(_hp(hparams, "score_algo", "exact")).lower() == "tc" else SCORE_EXACT
         self.seed = int(_hp(hparams, "seed", 2020))
         std = float(_hp(hparams, "init_std", 1.0))

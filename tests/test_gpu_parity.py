@@ -153,7 +153,8 @@ def test_empty_batch_and_errors(dev):
     with pytest.raises(_lib.B200RecError):
         engine.bpr_step(U, V, 8, torch.zeros(4, dtype=torch.int32, device=dev))        # sampling without a CSR
     with pytest.raises(_lib.B200RecError):
-        engine.bpr_step(U[:, :6].contiguous(), V, 6, e, e, e)  # ld % 4 != 0
+        one = torch.zeros(1, dtype=torch.int32, device=dev)
+        engine.bpr_step(U[:, :6].contiguous(), V[:, :6].contiguous(), 6, one, one, one)  # ld % 4 != 0
 
 
 # --------------------------------------------------------------------------- #
