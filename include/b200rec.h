@@ -84,6 +84,7 @@ int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int3
 #define B200REC_F_USERS_UNIQUE 1 /* no user id repeats inside the batch: user rows use plain vector stores */
 #define B200REC_F_TMA_GATHER 2   /* rows gathered with cp.async.bulk (TMA) into shared memory */
 #define B200REC_F_ITEM_DELTA 4   /* SINK_UPDATE: item-row deltas accumulate into dense gV (user-sharded layout) */
+#define B200REC_F_GENERIC 8      /* force the general kernel where the lean d=128/256 fast path would be taken */
 
 typedef struct b200rec_bpr_args {
     float *U;              /* [num_users, ld]  user_embedding.weight (models/MF.py:23)   */
@@ -189,10 +190,11 @@ int b200rec_loo_metrics(const int32_t *topk, int n, int max_k, const int32_t *ro
 int b200rec_column_means(const float *mat, int64_t n, int cols, double *out_host, void *stream);
 
 /* models/LightGCN.py:196 one propagation layer Y = A X for CSR A (fp32 values),
- * optionally accumulating acc += scale * Y (the running layer mean of :198-200). */
+ * optionally accumulating acc += scale * Y (the running layer mean of :198-200);
+ * acc_init != 0 starts the mean instead: acc = scale * X + scale * Y (first layer). */
 int b200rec_spmm_csr(const int64_t *indptr, const int32_t *indices, const float *values,
                      int n_rows, const float *X, int ldx, int d, float *Y, int ldy, float *acc,
-                     int ldacc, float acc_scale, void *stream);
+                     int ldacc, float acc_scale, int acc_init, void *stream);
 
 #ifdef __cplusplus
 }

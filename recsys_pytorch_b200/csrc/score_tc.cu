@@ -27,6 +27,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 #include "topk_list.cuh"
 
@@ -592,6 +594,14 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         int n_redo = 0;
         B200_CUDA(cudaMemcpyAsync(&n_redo, redo_n, 4, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaStreamSynchronize(s));
+        if (getenv("B200REC_TC_STATS")) {  // diagnostics only
+            std::vector<int32_t> hc((size_t)nr);
+            cudaMemcpy(hc.data(), cnt, (size_t)nr * 4, cudaMemcpyDeviceToHost);
+            long long tot = 0, mx = 0, over = 0;
+            for (int v : hc) { if (v < 0) ++over; else { tot += v; if (v > mx) mx = v; } }
+            fprintf(stderr, "[b200rec tc] rows=%d redo=%d (cnt<0: %lld) mean_cand=%.1f max_cand=%lld k=%d tiles=%d\n", nr,
+                    n_redo, over, nr > over ? (double)tot / (double)(nr - over) : 0.0, mx, k, p.n_tiles);
+        }
         if (n_redo > 0) {  // rows the candidate buffer could not hold: exact kernel, then scatter back
             gather_ids_kernel<<<(n_redo + 255) / 256, 256, 0, s>>>(users + r0, redo, n_redo, ruser);
             B200_LAUNCH_CHECK();

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const int64_t *__restrict
                                                        const float *__restrict__ values, int n_rows,
                                                        const float *__restrict__ X, int ldx, int d4,
                                                        float *__restrict__ Y, int ldy, float *__restrict__ acc,
-                                                       int ldacc, float acc_scale) {
+                                                       int ldacc, float acc_scale, int acc_init) {
     constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31;
     const int sl = lane % G, sg = lane / G;
@@ -57,6 +57,10 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const int64_t *__restrict
                 if (acc) {
                     float *pa = acc + row * ldacc + q * 4;
                     float4 o = ld4(pa);
+                    if (acc_init) {  // first layer: running mean starts as scale * E_0 (models/LightGCN.py:198-200)
+                        const float4 x0 = ld4(X + row * ldx + q * 4);
+                        o = make_float4(acc_scale * x0.x, acc_scale * x0.y, acc_scale * x0.z, acc_scale * x0.w);
+                    }
                     o.x = fmaf(acc_scale, a[k].x, o.x); o.y = fmaf(acc_scale, a[k].y, o.y);
                     o.z = fmaf(acc_scale, a[k].z, o.z); o.w = fmaf(acc_scale, a[k].w, o.w);
                     st4(pa, o);
@@ -68,12 +72,12 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const int64_t *__restrict
 
 template <int G, int CPL>
 static int launch_spmm(const int64_t *indptr, const int32_t *indices, const float *values, int n_rows, const float *X,
-                       int ldx, int d4, float *Y, int ldy, float *acc, int ldacc, float sc, cudaStream_t s) {
+                       int ldx, int d4, float *Y, int ldy, float *acc, int ldacc, float sc, int acc_init, cudaStream_t s) {
     constexpr int RPW = 32 / G;
     int64_t blocks = ((int64_t)n_rows + 8 * RPW - 1) / (8 * RPW);
     const int64_t cap = (int64_t)sm_count() * 8;
     spmm_csr_kernel<G, CPL><<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(indptr, indices, values, n_rows, X, ldx,
-                                                                               d4, Y, ldy, acc, ldacc, sc);
+                                                                               d4, Y, ldy, acc, ldacc, sc, acc_init);
     B200_LAUNCH_CHECK();
     return B200REC_OK;
 }
@@ -84,7 +88,7 @@ using namespace b200;
 
 extern "C" int b200rec_spmm_csr(const int64_t *indptr, const int32_t *indices, const float *values, int n_rows,
                                 const float *X, int ldx, int d, float *Y, int ldy, float *acc, int ldacc,
-                                float acc_scale, void *stream) {
+                                float acc_scale, int acc_init, void *stream) {
     B200_REQUIRE(indptr && indices && values && X && (Y || acc), B200REC_EINVAL, "spmm_csr: null argument");
     B200_REQUIRE(d >= 1 && ldx >= d && ldx % 4 == 0 && ldx <= 512, B200REC_EINVAL, "spmm_csr: bad d/ldx");
     B200_REQUIRE((!Y || (ldy >= d && ldy % 4 == 0)) && (!acc || (ldacc >= d && ldacc % 4 == 0)), B200REC_EINVAL,
@@ -96,7 +100,7 @@ extern "C" int b200rec_spmm_csr(const int64_t *indptr, const int32_t *indices, c
     while (G < d4 && G < 32) G <<= 1;
     const int CPL = (d4 + G - 1) / G;
     cudaStream_t s = (cudaStream_t)stream;
-#define B200_SPMM(GG, CC) return launch_spmm<GG, CC>(indptr, indices, values, n_rows, X, ldx, d4, Y, ldy, acc, ldacc, acc_scale, s)
+#define B200_SPMM(GG, CC) return launch_spmm<GG, CC>(indptr, indices, values, n_rows, X, ldx, d4, Y, ldy, acc, ldacc, acc_scale, acc_init, s)
     switch (G) {
         case 1: B200_SPMM(1, 1);
         case 2: B200_SPMM(2, 1);

@@ -205,10 +205,12 @@ def column_means(mat):
     return out
 
 
-def spmm_csr(indptr, indices, values, X, d, Y=None, acc=None, acc_scale=1.0):
-    """models/LightGCN.py:196: Y = A X (and/or acc += acc_scale * A X)."""
+def spmm_csr(indptr, indices, values, X, d, Y=None, acc=None, acc_scale=1.0, acc_init=False):
+    """models/LightGCN.py:196: Y = A X; optionally acc += acc_scale * A X, or with
+    acc_init acc = acc_scale * (X + A X) (start of the running layer mean, :198-200)."""
     n_rows = indptr.numel() - 1
     check(_lib.lib().b200rec_spmm_csr(ptr(indptr), ptr(indices), ptr(values), n_rows, ptr(X), X.shape[1], d,
                                       ptr(Y), Y.shape[1] if Y is not None else 0, ptr(acc),
-                                      acc.shape[1] if acc is not None else 0, float(acc_scale), current_stream()))
+                                      acc.shape[1] if acc is not None else 0, float(acc_scale), int(bool(acc_init)),
+                                      current_stream()))
     return Y

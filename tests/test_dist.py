@@ -108,7 +108,7 @@ def test_item_sharded_equals_single_device_oracle(dev, world):
         assert pos[t] in rows[un[t]] and neg[t] not in rows[un[t]]
     Ur, Vr, _ = O.sgd_step(U0, V0, un, pos, neg, 5.0, 0.01)
     for r in ranks:
-        np.testing.assert_allclose(r.U.cpu().numpy(), Ur, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(r.U.cpu().numpy(), Ur, rtol=2e-5, atol=5e-6)
     Vg = np.concatenate([r.V.cpu().numpy() for r in ranks])
     step = np.abs(Vr - V0).max()
     assert np.abs(Vg - Vr).max() < 0.02 * step + 2e-6    # item rows: in-place (Hogwild) inside a rank
