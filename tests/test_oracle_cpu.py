@@ -186,3 +186,21 @@ def test_cabi_argument_errors_without_gpu(built_lib):
     if not torch.cuda.is_available():
         rc = built_lib.b200rec_top_k_array_index(sc.ctypes.data, 8, 2, 4, out.ctypes.data)
         assert rc == _lib.ECUDA and b"no CPU fallback" in built_lib.b200rec_last_error()
+
+
+def test_torch_port_reproduces_reference_adam(golden):
+    """oracle/torch_port.py (the timed CPU baseline) IS the reference's step: same tables after 3 Adam steps."""
+    import torch
+    from oracle.torch_port import RefMF
+    g = golden["tiny_bpr"]
+    torch.set_num_threads(1)
+    m = RefMF(50, 40, 8)
+    with torch.no_grad():
+        m.user_embedding.weight.copy_(torch.from_numpy(g["U0"])); m.item_embedding.weight.copy_(torch.from_numpy(g["V0"]))
+    losses = []
+    for b in range(3):
+        u, i, j = (torch.from_numpy(g[k][b]) for k in ("users", "pos", "neg"))
+        losses.append(float(m.train_step(u, i, j)))
+    np.testing.assert_allclose(m.user_embedding.weight.detach().numpy(), g["adam_U"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(m.item_embedding.weight.detach().numpy(), g["adam_V"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(losses, g["adam_loss"], rtol=1e-6)
