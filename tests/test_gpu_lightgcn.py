@@ -33,7 +33,7 @@ def test_norm_adj_matches_reference_graph(golden, dev):
     assert cols.numel() == int(g["adj_nnz"])
     order = np.lexsort((g["adj_cols"], g["adj_rows"]))           # reference COO (coalesced) -> row-major order
     np.testing.assert_array_equal(cols.cpu().numpy(), g["adj_cols"][order])
-    np.testing.assert_allclose(vals.cpu().numpy(), g["adj_vals"][order], rtol=2e-7, atol=0)
+    np.testing.assert_allclose(vals.cpu().numpy(), g["adj_vals"][order], rtol=5e-7, atol=0)   # <= 2 ulp: pow(-0.5) rounding
     counts = np.bincount(g["adj_rows"], minlength=nu + ni)
     np.testing.assert_array_equal(np.diff(indptr.cpu().numpy()), counts)
 
