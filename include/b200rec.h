@@ -161,8 +161,11 @@ int b200rec_score_topk(const float *U, const float *V, int ld, int d, const int3
                        const int32_t *mask_indices, int k, int32_t *out_idx, float *out_score,
                        void *workspace, int64_t workspace_bytes, int algo, void *stream);
 
-/* Test hook (not part of the reference surface): the raw bf16 tensor-core scores of the
- * B200REC_SCORE_TC candidate pass, dense fp32 [roundup(n_users,256), roundup(num_items,128)]. */
+/* Test hooks (not part of the reference surface): the raw fp16 tensor-core scores of the
+ * B200REC_SCORE_TC candidate pass, dense fp32 [roundup(n_users,256), roundup(num_items,128)], items in
+ * the kernel's descending-norm order and rescaled domain; debug_tc_layout gives the workspace offsets
+ * (relative to the 1024-aligned workspace base) of that permutation and of {scale_v, scale_u}. */
+int b200rec_debug_tc_layout(int n_users, int num_items, int d, int64_t *off_perm, int64_t *off_scales);
 int b200rec_debug_tc_scores(const float *U, const float *V, int ld, int d, const int32_t *users,
                             int n_users, int num_items, float *dump, void *workspace,
                             int64_t workspace_bytes, void *stream);

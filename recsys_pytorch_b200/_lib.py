@@ -60,6 +60,7 @@ _PROTOS = {
     "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
     "b200rec_score_topk_workspace": (_L, [_I, _I, _I, _I, _I]),
     "b200rec_score_topk": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _P, _P, _L, _I, _P]),
+    "b200rec_debug_tc_layout": (_I, [_I, _I, _I, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200rec_debug_tc_scores": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P, _L, _P]),
     "b200rec_predict_dense": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P, _P, _P]),
     "b200rec_topk_rows": (_I, [_P, _L, _I, _I, _I, _P, _P]),

@@ -449,6 +449,116 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) bpr_step_fast_kernel(co
 }
 
 // ---------------------------------------------------------------------------
+// Fast path with a deep asynchronous gather: rows travel global -> shared with cp.async
+// (LDGSTS.128, 16 B per lane per row piece) into a per-warp ring of S stages, one commit
+// group per triple, cp.async.wait_group S-1 before the oldest is consumed.  Every lane
+// reads back exactly the 16-byte pieces it copied itself, so the ring is a per-lane
+// FIFO: no warp- or CTA-level synchronisation.  S triples (S * 1.5 KB at d=128) are in
+// flight per warp at no register cost - the LDG fast path above is latency-bound
+// (long-scoreboard 16.7 stalls/issue, DRAM 58 %, ncu run 4) with 3 in flight.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int CPL, bool UNIQ, bool LOSS, int S>
+__global__ void __launch_bounds__(256) bpr_step_async_kernel(const BprParams p) {
+    extern __shared__ __align__(16) float4 ring_all[];   // [8 warps][S][3][CPL][32] float4
+    float *__restrict__ const U = p.a.U;
+    float *__restrict__ const V = p.a.V;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4 *const ring = ring_all + (size_t)wid * S * 3 * CPL * 32 + lane;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int64_t LD = 128 * CPL;
+    const float c_g = p.a.lr * p.invB;
+    const float c_r = -p.a.lr * p.a.reg * p.invB;
+    const int chunk = p.chunk, B = p.a.B;
+    const int64_t n_chunks = p.n_chunks;
+    b200rec_bpr_args a = p.a;
+    float loss_local = 0.f;
+
+    for (int64_t c = warp_global; c < n_chunks; c += n_warps) {
+        const int64_t t_lane = c * chunk + lane;
+        bool valid = (lane < chunk) && (t_lane < B);
+        int u, i, j;
+        fetch_triple(a, t_lane, valid, u, i, j);
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+
+        auto issue = [&](int it) {
+            if (it < chunk && ((vmask >> it) & 1u)) {
+                const int tu = __shfl_sync(0xffffffffu, u, it);
+                const int ti = __shfl_sync(0xffffffffu, i, it);
+                const int tj = __shfl_sync(0xffffffffu, j, it);
+                float4 *slot = ring + (size_t)(it % S) * 3 * CPL * 32;
+                const float *pu = U + (int64_t)tu * LD + lane * 4;
+                const float *pi = V + (int64_t)ti * LD + lane * 4;
+                const float *pj = V + (int64_t)tj * LD + lane * 4;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    cp_async16(slot + (0 * CPL + k) * 32, pu + 128 * k);
+                    cp_async16(slot + (1 * CPL + k) * 32, pi + 128 * k);
+                    cp_async16(slot + (2 * CPL + k) * 32, pj + 128 * k);
+                }
+            }
+            cp_async_commit();   // one (possibly empty) group per triple slot keeps the group count uniform
+        };
+#pragma unroll
+        for (int it = 0; it < S; ++it) issue(it);
+        for (int it = 0; it < chunk; ++it) {
+            cp_async_wait<S - 1>();   // groups up to `it` have landed
+            if ((vmask >> it) & 1u) {
+                const int tu = __shfl_sync(0xffffffffu, u, it);
+                const int ti = __shfl_sync(0xffffffffu, i, it);
+                const int tj = __shfl_sync(0xffffffffu, j, it);
+                const float4 *slot = ring + (size_t)(it % S) * 3 * CPL * 32;
+                float4 ru[CPL], ri[CPL], rj[CPL], df[CPL];
+                float part = 0.f;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    ru[k] = slot[(0 * CPL + k) * 32]; ri[k] = slot[(1 * CPL + k) * 32]; rj[k] = slot[(2 * CPL + k) * 32];
+                    df[k] = make_float4(ri[k].x - rj[k].x, ri[k].y - rj[k].y, ri[k].z - rj[k].z, ri[k].w - rj[k].w);
+                    part = fmaf(ru[k].x, df[k].x, part); part = fmaf(ru[k].y, df[k].y, part);
+                    part = fmaf(ru[k].z, df[k].z, part); part = fmaf(ru[k].w, df[k].w, part);
+                }
+                const float x = group_sum<32>(part);   // consumes every lane's shared-memory reads of this slot
+                issue(it + S);                          // refill the slot just freed
+                const float s = __frcp_rn(1.f + __expf(-x));
+                const float a1 = c_g * (1.f - s);
+                if (LOSS) loss_local += (x < -15.f) ? -x : -__logf(s);
+                float *pu = U + (int64_t)tu * LD + lane * 4;
+                float *pi = V + (int64_t)ti * LD + lane * 4;
+                float *pj = V + (int64_t)tj * LD + lane * 4;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    float4 du, di, dj;
+                    du.x = fmaf(a1, df[k].x, c_r * ru[k].x); du.y = fmaf(a1, df[k].y, c_r * ru[k].y);
+                    du.z = fmaf(a1, df[k].z, c_r * ru[k].z); du.w = fmaf(a1, df[k].w, c_r * ru[k].w);
+                    di.x = fmaf(a1, ru[k].x, c_r * ri[k].x); di.y = fmaf(a1, ru[k].y, c_r * ri[k].y);
+                    di.z = fmaf(a1, ru[k].z, c_r * ri[k].z); di.w = fmaf(a1, ru[k].w, c_r * ri[k].w);
+                    dj.x = fmaf(-a1, ru[k].x, c_r * rj[k].x); dj.y = fmaf(-a1, ru[k].y, c_r * rj[k].y);
+                    dj.z = fmaf(-a1, ru[k].z, c_r * rj[k].z); dj.w = fmaf(-a1, ru[k].w, c_r * rj[k].w);
+                    if (UNIQ) st4(pu + 128 * k, make_float4(ru[k].x + du.x, ru[k].y + du.y, ru[k].z + du.z, ru[k].w + du.w));
+                    else red4(pu + 128 * k, du);
+                    red4(pi + 128 * k, di);
+                    red4(pj + 128 * k, dj);
+                }
+            } else {
+                issue(it + S);
+            }
+        }
+        cp_async_wait<0>();
+    }
+    if (LOSS) {
+        if (lane == 0 && loss_local != 0.f) atomicAdd(p.a.loss_sum, (double)loss_local);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // second phase of the exact step, forward, dense optimisers
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bpr_apply_kernel(float *U, float *V, int ld, const int32_t *users,

@@ -32,7 +32,12 @@ template <int TM>
 __global__ void __launch_bounds__(256) score_topk_exact_kernel(
     const float *__restrict__ U, const float *__restrict__ V, int ld, int d, const int32_t *__restrict__ users,
     int n_users, int num_items, const int64_t *__restrict__ mask_indptr, const int32_t *__restrict__ mask_indices,
-    int k, int32_t *__restrict__ out_idx, float *__restrict__ out_score, float *__restrict__ dense_out) {
+    int k, int32_t *__restrict__ out_idx, float *__restrict__ out_score, float *__restrict__ dense_out,
+    int items_per_split, uint64_t *__restrict__ part_keys) {
+    // blockIdx.y = item split: with few user rows the catalogue is divided over gridDim.y CTAs per row
+    // block (each writes its local top-k keys to part_keys[row][split][k]; merge_topk_kernel finishes)
+    const int item_begin = blockIdx.y * items_per_split;
+    const int item_end = (item_begin + items_per_split < num_items) ? item_begin + items_per_split : num_items;
     using C = ExactCfg<TM>;
     constexpr int TN = C::TN;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -57,7 +62,7 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(
     __syncthreads();
 
     const bool vec_ok = (ld % 4) == 0;
-    for (int n0 = 0; n0 < num_items; n0 += TN) {
+    for (int n0 = item_begin; n0 < item_end; n0 += TN) {
         float acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(
                 const int c = e / (kKSlab / 4), kq = e % (kKSlab / 4);
                 const int kk = k0 + 4 * kq;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n0 + c < num_items && kk < d) {
+                if (n0 + c < item_end && kk < d) {
                     const float *src = V + (int64_t)(n0 + c) * ld + kk;
                     if (vec_ok && kk + 3 < ld) v = *reinterpret_cast<const float4 *>(src);
                     else { v.x = src[0]; if (kk + 1 < ld) v.y = src[1]; if (kk + 2 < ld) v.z = src[2]; if (kk + 3 < ld) v.w = src[3]; }
@@ -137,14 +142,14 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(
                 if (lane == 0) mcur[r] = cur;
             }
             if (dense_out) {
-                for (int c = lane; c < TN && n0 + c < num_items; c += 32)
+                for (int c = lane; c < TN && n0 + c < item_end; c += 32)
                     dense_out[(int64_t)gr * num_items + n0 + c] = Srow[c];
             }
             if (k > 0) {
                 uint64_t *rk = keys + (size_t)r * k;
                 for (int c0 = 0; c0 < TN; c0 += 32) {
                     const int c = c0 + lane;
-                    const bool ok = (c < TN) && (n0 + c < num_items);
+                    const bool ok = (c < TN) && (n0 + c < item_end);
                     const uint64_t key = ok ? make_key(Srow[c], n0 + c) : 0ull;
                     topk_list_offer(rk, k, key, ok, lane);
                 }
@@ -158,10 +163,40 @@ __global__ void __launch_bounds__(256) score_topk_exact_kernel(
             const int gr = row0 + r;
             if (gr < n_users) {
                 const uint64_t key = keys[e];
-                out_idx[(int64_t)gr * k + p] = key_id(key);
-                if (out_score) out_score[(int64_t)gr * k + p] = key_score(key);
+                if (part_keys) {
+                    part_keys[((int64_t)gr * gridDim.y + blockIdx.y) * k + p] = key;
+                } else {
+                    out_idx[(int64_t)gr * k + p] = key_id(key);
+                    if (out_score) out_score[(int64_t)gr * k + p] = key_score(key);
+                }
             }
         }
+    }
+}
+
+// merges the per-split local top-k lists of a row (keys are globally comparable): one warp per row
+__global__ void __launch_bounds__(256) merge_topk_kernel(const uint64_t *__restrict__ part_keys, int n_rows, int splits,
+                                                         int k, int32_t *__restrict__ out_idx,
+                                                         float *__restrict__ out_score) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t *rk = reinterpret_cast<uint64_t *>(smem_raw) + (size_t)wid * k;
+    for (int row = blockIdx.x * 8 + wid; row < n_rows; row += gridDim.x * 8) {
+        for (int p = lane; p < k; p += 32) rk[p] = make_key(-INFINITY, 0x7FFFFFFF);
+        __syncwarp();
+        const uint64_t *src = part_keys + (int64_t)row * splits * k;
+        const int total = splits * k;
+        for (int c0 = 0; c0 < total; c0 += 32) {
+            const int c = c0 + lane;
+            const bool ok = c < total;
+            topk_list_offer(rk, k, ok ? src[c] : 0ull, ok, lane);
+        }
+        __syncwarp();
+        for (int p = lane; p < k; p += 32) {
+            out_idx[(int64_t)row * k + p] = key_id(rk[p]);
+            if (out_score) out_score[(int64_t)row * k + p] = key_score(rk[p]);
+        }
+        __syncwarp();
     }
 }
 
@@ -182,8 +217,37 @@ static int launch_exact(const float *U, const float *V, int ld, int d, const int
     B200_REQUIRE(smem <= 227 * 1024, B200REC_EUNSUPPORTED, "score_topk: k=%d too large", k);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (n_users + TM - 1) / TM;
-    kern<<<grid, 256, smem, s>>>(U, V, ld, d, users, n_users, num_items, mi, mx, k, oi, os, dense);
+    using C = ExactCfg<TM>;
+    const int n_tiles = (num_items + C::TN - 1) / C::TN;
+    const int sms = sm_count();
+    // few row blocks (e.g. the TC path's overflow rows, small evaluations): split the catalogue so the
+    // whole chip works on them, then merge the per-split top-k lists
+    int splits = 1;
+    if (k > 0 && !dense && grid < 2 * sms) {
+        splits = (2 * sms + grid - 1) / grid;
+        if (splits > n_tiles) splits = n_tiles;
+        if (splits > 512) splits = 512;
+    }
+    if (splits <= 1) {
+        kern<<<grid, 256, smem, s>>>(U, V, ld, d, users, n_users, num_items, mi, mx, k, oi, os, dense, num_items,
+                                     nullptr);
+        B200_LAUNCH_CHECK();
+        return B200REC_OK;
+    }
+    const int tiles_per_split = (n_tiles + splits - 1) / splits;
+    splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    uint64_t *part = nullptr;
+    B200_CUDA(cudaMallocAsync(&part, (size_t)n_users * splits * k * sizeof(uint64_t), s));
+    kern<<<dim3(grid, splits), 256, smem, s>>>(U, V, ld, d, users, n_users, num_items, mi, mx, k, nullptr, nullptr,
+                                               nullptr, tiles_per_split * C::TN, part);
     B200_LAUNCH_CHECK();
+    const size_t msmem = (size_t)8 * k * 8;
+    B200_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    int mgrid = (n_users + 7) / 8;
+    if (mgrid > sms * 8) mgrid = sms * 8;
+    merge_topk_kernel<<<mgrid, 256, msmem, s>>>(part, n_users, splits, k, oi, os);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaFreeAsync(part, s));
     return B200REC_OK;
 }
 

@@ -1,34 +1,36 @@
-// Tensor-core scoring + top-K for sm_100a:  tcgen05 (UMMA) bf16 candidate pass with
+// Tensor-core scoring + top-K for sm_100a:  tcgen05 (UMMA) fp16 candidate pass with
 // TMEM accumulators and TMA-fed shared-memory tiles, followed by an exact fp32 re-rank.
 //
 // Replaces models/MF.py:109-112 (`user_latent @ all_item_latent.T`, cuBLAS SGEMM
 // when run on a GPU), the dense score matrix + -inf mask of MF.py:117-130 and the
 // per-row std::partial_sort_copy of evaluation/backend/cython/include/func.h:12-31.
 //
-// Exactness argument.  Let S be the fp32 scores the exact kernel
-// (score_exact.cu) would produce and S~ the bf16 tensor-core scores.  For a user row
-// |S~ - S| <= eps = c * |u|_2 * max_v |v|_2 with c = 2^-8 (two bf16 roundings) plus
-// the fp32 accumulation slack.  If tau is ANY lower bound on the K'-th largest S~ of
-// the row (K' = K + #masked items of the user, so that at least K unmasked items
-// lie above it), every item of the exact top-K has S~ >= tau - 2 eps.  The candidate
-// pass therefore keeps, per row, every item with S~ >= tau - 2 eps, raising tau as it
-// goes (bucketed selection over the row's candidate buffer); the re-rank kernel then
-// drops masked items, recomputes the survivors with the SAME k-ordered fp32 FMA
-// chain as the exact kernel and selects the top-K by (score desc, id asc).  Rows whose
-// candidate buffer cannot hold K' + slack entries are flagged and re-done by the
-// exact kernel, so the result is always identical to B200REC_SCORE_EXACT.
+// Exactness argument.  Tables are rescaled by powers of two and rounded to
+// fp16 (unit roundoff 2^-11); the tensor cores accumulate exact products in fp32.  For a
+// user u and item i,  |S~ - S| <= e(u,i) = c |u|_2 |v_i|_2,  c = 2^-10 (+5%) + d*2.4e-7.
+// With L = S~ - e <= S <= S~ + e = H:  if tau is any lower bound of the K'-th largest L of
+// the row (K' = K + #masked items of the user, so at least K unmasked items have
+// S >= tau), every item of the exact top-K has H >= tau.  Items are visited in
+// DESCENDING NORM order (one radix sort per call), so a whole 128-item tile shares the
+// bound e_t = c |u| * (largest norm in the tile), which shrinks along the sweep while tau
+// grows.  The candidate pass keeps every item with S~ + e_t >= tau, raising tau by a
+// bucketed selection over the row's candidate buffer when it fills; the re-rank kernel
+// drops masked items, recomputes survivors with the SAME k-ordered fp32 FMA chain as the
+// exact kernel and selects by (score desc, id asc).  Rows whose buffer cannot hold
+// K' + slack are re-done by the exact kernel: the result always equals B200REC_SCORE_EXACT.
 //
 // Kernel roles (one CTA = 256 user rows x all item tiles of 128):
 //   warp 0      TMA producer: A (users) once, B (items) k-blocks through a smem ring
 //   warp 1      MMA issuer: tcgen05.mma.kind::f16, M=128 x N=128 x K=16, two M halves,
 //               double-buffered 4 x 128 TMEM columns; tcgen05.commit frees smem / signals tiles
-//   warps 2-9   epilogue: tcgen05.ld 32x32b (thread == user row), 3-input FMNMX threshold
-//               filter, candidate append, warp-cooperative threshold raise
+//   warps 2-9   epilogue: tcgen05.ld 32x32b.x64 (thread == user row), FMNMX3 max tree against
+//               the row threshold, candidate append, warp-cooperative threshold raise
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
+#include <cub/cub.cuh>
 #include "common.cuh"
 #include "topk_list.cuh"
 
@@ -40,7 +42,7 @@ int score_topk_exact(const float *U, const float *V, int ld, int d, const int32_
 
 constexpr int kBM = 256;        // user rows per CTA (two M=128 halves)
 constexpr int kBN = 128;        // items per tile
-constexpr int kBK = 64;         // bf16 per k-block = one 128-byte swizzle row
+constexpr int kBK = 64;         // fp16 per k-block = one 128-byte swizzle row
 constexpr int kCand = 512;      // candidate slots per row
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (2 + kEpiWarps) * 32;
@@ -72,7 +74,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                      "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc),
@@ -82,17 +84,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// 64 consecutive fp32 accumulator columns of this thread's TMEM lane (row)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-        "%29,%30,%31}, [%32];"
+        "%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,"
+        "%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
@@ -104,32 +115,69 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N=128, M=128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=B=f16 (format 0),
+// K-major both, N=128 -> n_dim=16 [17,23), M=128 -> m_dim=8 [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((128u >> 4) << 24);
 
-// ---- pre-pass: fp32 rows -> bf16 [rows_pad, dpad] (+ row norms, + global max norm) ------------
-__global__ void __launch_bounds__(256) to_bf16_kernel(const float *__restrict__ src, int ld, int d,
-                                                      const int32_t *__restrict__ ids, int rows, int rows_pad,
-                                                      int dpad, __nv_bfloat16 *__restrict__ dst,
-                                                      float *__restrict__ norms, unsigned *__restrict__ max_norm_bits) {
+// ---- pre-pass kernels ----------------------------------------------------------------------------
+// row norms (rounded up a hair: they feed upper bounds) + global max |x| and max norm
+__global__ void __launch_bounds__(256) row_stats_kernel(const float *__restrict__ src, int ld, int d,
+                                                        const int32_t *__restrict__ ids, int rows,
+                                                        float *__restrict__ norms, unsigned *__restrict__ max_abs_bits) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = w; r < rows_pad; r += nw) {
-        const float *p = (r < rows) ? src + (int64_t)(ids ? ids[r] : r) * ld : nullptr;
+    float mabs = 0.f;
+    for (int64_t r = w; r < rows; r += nw) {
+        const float *p = src + (int64_t)(ids ? ids[r] : r) * ld;
         float ss = 0.f;
-        for (int c = lane; c < dpad; c += 32) {
-            const float v = (p && c < d) ? p[c] : 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = p[c];
             ss = fmaf(v, v, ss);
-            dst[r * dpad + c] = __float2bfloat16_rn(v);
+            mabs = fmaxf(mabs, fabsf(v));
         }
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) {
-            const float nrm = sqrtf(ss) * 1.0000005f;  // rounded up a hair: it feeds an upper bound
-            if (norms && r < rows) norms[r] = nrm;
-            if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nrm));  // nonneg floats order as uints
-        }
+        if (lane == 0) norms[r] = sqrtf(ss) * 1.000001f;
     }
+    for (int o = 16; o > 0; o >>= 1) mabs = fmaxf(mabs, __shfl_xor_sync(0xffffffffu, mabs, o));
+    if (lane == 0 && mabs > 0.f) atomicMax(max_abs_bits, __float_as_uint(mabs));  // nonneg floats order as uints
+}
+
+// power-of-two scale that maps max|x| into [2^13, 2^14): exact in fp32, keeps fp16 out of overflow
+__device__ __forceinline__ float pow2_scale(unsigned max_abs_bits) {
+    const float m = __uint_as_float(max_abs_bits);
+    if (!(m > 0.f) || !isfinite(m)) return 1.f;
+    int e;
+    frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+    const int sh = 14 - e;
+    return ldexpf(1.f, sh > 100 ? 100 : (sh < -100 ? -100 : sh));
+}
+
+// dst[p] = fp16(scale * src[order ? order[p] : (ids ? ids[p] : p)]), rows >= `rows` and columns >= d zero
+__global__ void __launch_bounds__(256) to_f16_kernel(const float *__restrict__ src, int ld, int d,
+                                                     const int32_t *__restrict__ ids, const int32_t *__restrict__ order,
+                                                     int rows, int rows_pad, int dpad, const unsigned *__restrict__ max_abs_bits,
+                                                     __half *__restrict__ dst, float *__restrict__ scale_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float sc = pow2_scale(*max_abs_bits);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && scale_out) *scale_out = sc;
+    for (int64_t r = w; r < rows_pad; r += nw) {
+        const float *p = nullptr;
+        if (r < rows) p = src + (int64_t)(order ? order[r] : (ids ? ids[r] : (int)r)) * ld;
+        for (int c = lane; c < dpad; c += 32) dst[r * dpad + c] = __float2half_rn((p && c < d) ? p[c] * sc : 0.f);
+    }
+}
+
+__global__ void iota_kernel(int32_t *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+// tile_norm[t] = largest item norm in tile t (= first entry, norms sorted descending)
+__global__ void tile_norm_kernel(const uint32_t *sorted_norm_bits, int num_items, int n_tiles, float *tile_norm) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_tiles) tile_norm[t] = (t * kBN < num_items) ? __uint_as_float(sorted_norm_bits[t * kBN]) : 0.f;
 }
 
 struct TcParams {
@@ -137,31 +185,38 @@ struct TcParams {
     const int32_t *users;            // row -> user id (mask row)
     const int64_t *mask_indptr;      // may be NULL
     const float *row_norm;           // [n_rows]
-    const unsigned *vmax_bits;       // [1]
-    uint64_t *cand;                  // [n_rows, kCand]  (ordered approx score << 32 | item id)
+    const float *tile_norm;          // [n_tiles]
+    const float *scale_u, *scale_v;  // device scalars (powers of two)
+    uint64_t *cand;                  // [n_rows, kCand]  (ordered approx score << 32 | sorted item position)
     int32_t *cand_cnt;               // [n_rows]  (-1 = overflow: re-do with the exact kernel)
-    float *dump;                     // bring-up: dense [n_rows_pad, n_tiles*kBN] approx scores, else NULL
+    float *dump;                     // bring-up: dense [n_rows_pad, n_tiles*kBN] approx scores (sorted order), else NULL
 };
 
-// warp-cooperative threshold raise for the lanes in `need` (bit per lane); see file header
-__device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &thr, int keff,
-                                                 float eps2, int *hist, int lane) {
+// warp-cooperative threshold raise for the lanes in `need` (bit per lane); see file header.
+// Entries hold S~ (scaled); e = cu * tile_norm[pos/128]; L = S~ - e, H = S~ + e.
+__device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int keff, float cu,
+                                                 const float *__restrict__ tile_norm, int *hist, int lane) {
     while (need) {
-        const int L = __ffs(need) - 1;
+        const int Lsrc = __ffs(need) - 1;
         need &= need - 1;
-        uint64_t *base = reinterpret_cast<uint64_t *>(__shfl_sync(0xffffffffu, (unsigned long long)my_cand, L));
-        const int n = __shfl_sync(0xffffffffu, cnt, L);
-        const int kf = __shfl_sync(0xffffffffu, keff, L);
-        const float e2 = __shfl_sync(0xffffffffu, eps2, L);
+        uint64_t *base = reinterpret_cast<uint64_t *>(__shfl_sync(0xffffffffu, (unsigned long long)my_cand, Lsrc));
+        const int n = __shfl_sync(0xffffffffu, cnt, Lsrc);
+        const int kf = __shfl_sync(0xffffffffu, keff, Lsrc);
+        const float c_u = __shfl_sync(0xffffffffu, cu, Lsrc);
+        const float old_tau = __shfl_sync(0xffffffffu, tau, Lsrc);
         uint64_t e[kCand / 32];
+        float lo[kCand / 32], hi[kCand / 32];
         float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
         for (int i = 0; i < kCand / 32; ++i) {
             const int p = lane + 32 * i;
             e[i] = (p < n) ? base[p] : 0ull;
+            lo[i] = INFINITY; hi[i] = -INFINITY;
             if (p < n) {
                 const float s = ord2f((uint32_t)(e[i] >> 32));
-                mn = fminf(mn, s); mx = fmaxf(mx, s);
+                const float err = c_u * tile_norm[(uint32_t)(e[i] & 0xFFFFFFFFu) / kBN];
+                lo[i] = s - err; hi[i] = s + err;
+                mn = fminf(mn, lo[i]); mx = fmaxf(mx, lo[i]);
             }
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -174,7 +229,7 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
 #pragma unroll
         for (int i = 0; i < kCand / 32; ++i) {
             if (lane + 32 * i < n) {
-                int b = (int)((ord2f((uint32_t)(e[i] >> 32)) - mn) * scale);
+                int b = (int)((lo[i] - mn) * scale);
                 b = b > 31 ? 31 : (b < 0 ? 0 : b);
                 atomicAdd(&hist[b], 1);
             }
@@ -187,25 +242,23 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         }
         const unsigned okb = __ballot_sync(0xffffffffu, suf >= kf);
         const int bstar = okb ? 31 - __clz(okb) : 0;
-        // tau = smallest score among the entries in buckets >= bstar  (so at least kf entries are >= tau)
-        float tau = INFINITY;
+        // new tau = smallest L among the entries in buckets >= bstar  (so at least kf entries have L >= tau)
+        float t_new = INFINITY;
 #pragma unroll
         for (int i = 0; i < kCand / 32; ++i) {
             if (lane + 32 * i < n) {
-                const float s = ord2f((uint32_t)(e[i] >> 32));
-                int b = (int)((s - mn) * scale);
+                int b = (int)((lo[i] - mn) * scale);
                 b = b > 31 ? 31 : (b < 0 ? 0 : b);
-                if (b >= bstar) tau = fminf(tau, s);
+                if (b >= bstar) t_new = fminf(t_new, lo[i]);
             }
         }
-        for (int o = 16; o > 0; o >>= 1) tau = fminf(tau, __shfl_xor_sync(0xffffffffu, tau, o));
-        const float old_thr = __shfl_sync(0xffffffffu, thr, L);
-        float new_thr = fmaxf(old_thr, tau - e2);
-        // compact: keep entries with score >= new_thr
+        for (int o = 16; o > 0; o >>= 1) t_new = fminf(t_new, __shfl_xor_sync(0xffffffffu, t_new, o));
+        t_new = fmaxf(old_tau, t_new);
+        // compact: keep entries whose upper bound still reaches tau
         int keep = 0;
 #pragma unroll
         for (int i = 0; i < kCand / 32; ++i)
-            if (lane + 32 * i < n && ord2f((uint32_t)(e[i] >> 32)) >= new_thr) ++keep;
+            if (lane + 32 * i < n && hi[i] >= t_new) ++keep;
         int pre = keep;  // inclusive scan
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, pre, o);
@@ -216,16 +269,16 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < kCand / 32; ++i)
-            if (lane + 32 * i < n && ord2f((uint32_t)(e[i] >> 32)) >= new_thr) base[w++] = e[i];
+            if (lane + 32 * i < n && hi[i] >= t_new) base[w++] = e[i];
         __syncwarp();
-        if (lane == L) {
-            if (total > kCand - 64) { cnt = -1; thr = INFINITY; }  // cannot make room: exact kernel re-does the row
-            else { cnt = total; thr = new_thr; }
+        if (lane == Lsrc) {
+            if (total > kCand - kBN - 32) { cnt = -1; tau = INFINITY; }  // cannot make room: exact kernel re-does the row
+            else { cnt = total; tau = t_new; }
         }
     }
 }
 
-template <int KB>
+template <int KB, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const TcParams p, const int n_stages) {
@@ -242,6 +295,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kBM;
+    const int n_tiles = p.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) { mbar_init(s32(full + s), 1); mbar_init(s32(empty + s), 1); }
@@ -266,7 +320,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_expect_tx(s32(afull), (uint32_t)KB * kBM * 128);
             for (int kb = 0; kb < KB; ++kb) tma_load_2d(s32(smA + (size_t)kb * kBM * 128), &tmA, kb * kBK, row0, s32(afull));
             uint32_t it = 0;
-            for (int t = 0; t < p.n_tiles; ++t) {
+            for (int t = 0; t < n_tiles; ++t) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
                     mbar_wait(s32(empty + s), ph ^ 1u);
@@ -281,7 +335,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(s32(afull), 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t it = 0;
-            for (int t = 0; t < p.n_tiles; ++t) {
+            for (int t = 0; t < n_tiles; ++t) {
                 const uint32_t as = t & 1, aph = (t >> 1) & 1u;
                 mbar_wait(s32(tempty + as), aph ^ 1u);  // epilogue has drained this accumulator pair
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -296,7 +350,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint32_t dcol = tmem_base + (as * 2 + h) * kBN;
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k)  // +32 B along K inside the swizzle atom = +2 in the address field
-                            umma_bf16(dcol, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
+                            umma_f16(dcol, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) ? 1u : 0u);
                     }
                     umma_commit(s32(empty + s));  // smem slot reusable once these MMAs have read it
                 }
@@ -313,73 +367,68 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool row_ok = row < p.n_rows;
         int *hist = hist_all + ew * 32;
         uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
+        const float *__restrict__ tile_norm = p.tile_norm;
+        const int num_items = p.num_items;
         int cnt = 0, keff = p.k;
-        float thr = -INFINITY, eps2 = 0.f;
+        float tau = -INFINITY, cu = 0.f;
         if (row_ok) {
             if (p.mask_indptr) {
                 const int u = p.users[row];
                 keff += (int)(p.mask_indptr[u + 1] - p.mask_indptr[u]);
             }
-            const float vmax = __uint_as_float(*p.vmax_bits);
-            const float c = 0.00390625f * 1.05f + (float)p.d * 2.4e-7f;  // 2^-8 (+5%) + fp32 accumulation slack
-            eps2 = 2.f * c * p.row_norm[row] * vmax;
-            if (keff > kCand / 2 - 32) { cnt = -1; thr = INFINITY; }      // too many masked items for the buffer
+            const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;   // 2^-10 (+5%) + fp32 accumulation slack
+            cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);         // error bound per unit item norm, scaled domain
+            if (keff > kCand / 2 - 32) { cnt = -1; tau = INFINITY; }         // too many masked items for the buffer
         } else {
-            thr = INFINITY;
+            tau = INFINITY;
         }
-        for (int t = 0; t < p.n_tiles; ++t) {
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kBN;
+        for (int t = 0; t < n_tiles; ++t) {
             const uint32_t as = t & 1, aph = (t >> 1) & 1u;
+            const float thr = tau - cu * tile_norm[t];   // keep S~ with S~ + e_t >= tau
             mbar_wait(s32(tfull + as), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int n0 = t * kBN;
-            const bool ragged = n0 + kBN > p.num_items;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kBN; c0 += 32) {
-                uint32_t rr[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (as * 2 + h) * kBN + c0, rr);
-                float v[32];
+            for (int c0 = 0; c0 < kBN; c0 += 64) {
+                float v[64];
+                tmem_ld64(lane_addr + as * 2 * kBN + c0, v);
+                if (DUMP) {
+                    float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * kBN) + n0 + c0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-                if (p.dump) {
-                    float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)p.n_tiles * kBN) + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                    for (int j = 0; j < 64; ++j) dst[j] = v[j];
                 }
-                if (ragged) {
+                float gm[8];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + c0 + j >= p.num_items) v[j] = -INFINITY;
-                }
-                float gm[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 8; ++g) {
                     const float a = max3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
                     const float b = max3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
                     gm[g] = max3(a, b, fmaxf(v[8 * g + 6], v[8 * g + 7]));
                 }
-                const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-                if (m >= thr) {
+                const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
+                if (m >= thr && cnt >= 0) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
+                    for (int g = 0; g < 8; ++g) {
                         if (gm[g] >= thr) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float s = v[8 * g + j];
-                                if (s >= thr && cnt >= 0) {
-                                    my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (uint32_t)(n0 + c0 + 8 * g + j);
+                                const int pos = n0 + c0 + 8 * g + j;
+                                if (s >= thr && pos < num_items) {
+                                    my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (uint32_t)pos;
                                     ++cnt;
                                 }
                             }
                         }
                     }
                 }
-                const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - 33);
-                if (need) raise_thresholds(need, my_cand, cnt, thr, keff, eps2, hist, lane);
             }
             // this warp is done reading the accumulator pair of tile t
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(s32(tempty + as));
+            const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kBN - 1);
+            if (need) raise_thresholds(need, my_cand, cnt, tau, keff, cu, tile_norm, hist, lane);
         }
         if (row_ok) p.cand_cnt[row] = cnt;
     }
@@ -393,6 +442,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
                                                      int d, const int32_t *__restrict__ users, int n_rows, int k,
                                                      const int64_t *__restrict__ mask_indptr,
                                                      const int32_t *__restrict__ mask_indices,
+                                                     const int32_t *__restrict__ item_of_pos,
                                                      const uint64_t *__restrict__ cand,
                                                      const int32_t *__restrict__ cand_cnt, int32_t *__restrict__ out_idx,
                                                      float *__restrict__ out_score, int32_t *__restrict__ redo_rows,
@@ -419,7 +469,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
             bool ok = c < n;
             uint64_t key = 0;
             if (ok) {
-                const int item = (int)(uint32_t)(cand[(size_t)row * kCand + c] & 0xFFFFFFFFu);
+                const int item = item_of_pos[(uint32_t)(cand[(size_t)row * kCand + c] & 0xFFFFFFFFu)];
                 int l = 0, r = mdeg;  // masked? (models/MF.py:130)
                 while (l < r) { const int m = (l + r) >> 1; if (mrow[m] < item) l = m + 1; else r = m; }
                 if (l < mdeg && mrow[l] == item) ok = false;
@@ -472,7 +522,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// bf16 [rows, dpad] row-major; box = 64 elements (128 B, SWIZZLE_128B) x box_rows
+// fp16 [rows, dpad] row-major; box = 64 elements (128 B, SWIZZLE_128B) x box_rows
 static int make_map(CUtensorMap *m, void *base, uint64_t rows, uint64_t dpad, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     B200_REQUIRE(fn != nullptr, B200REC_ECUDA, "cuTensorMapEncodeTiled entry point not found");
@@ -480,7 +530,7 @@ static int make_map(CUtensorMap *m, void *base, uint64_t rows, uint64_t dpad, ui
     cuuint64_t strides[1] = {dpad * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, B200REC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return B200REC_OK;
@@ -488,9 +538,17 @@ static int make_map(CUtensorMap *m, void *base, uint64_t rows, uint64_t dpad, ui
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static size_t sort_temp_bytes(int num_items) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                              (const int32_t *)nullptr, (int32_t *)nullptr, num_items);
+    return bytes;
+}
+
 struct TcLayout {
-    int dpad, KB, rows_cap, items_pad;
-    size_t off_vb, off_ub, off_norm, off_vmax, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, total;
+    int dpad, KB, rows_cap, items_pad, n_tiles;
+    size_t off_vh, off_uh, off_unorm, off_vnorm, off_vnorm_sorted, off_iota, off_perm, off_tnorm, off_scalars, off_sort,
+        sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, total;
 };
 static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     TcLayout L;
@@ -498,19 +556,28 @@ static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     L.KB = L.dpad / kBK;
     L.rows_cap = n_users < kRowsPerLaunch ? (int)align_up(n_users > 0 ? n_users : 1, kBM) : kRowsPerLaunch;
     L.items_pad = (int)align_up(num_items, kBN);
+    L.n_tiles = L.items_pad / kBN;
+    L.sort_bytes = sort_temp_bytes(num_items);
     size_t o = 0;
-    L.off_vb = o; o = align_up(o + (size_t)L.items_pad * L.dpad * 2, 1024);
-    L.off_ub = o; o = align_up(o + (size_t)L.rows_cap * L.dpad * 2, 1024);
-    L.off_norm = o; o = align_up(o + (size_t)L.rows_cap * 4, 256);
-    L.off_vmax = o; o = align_up(o + 4, 256);
-    L.off_cand = o; o = align_up(o + (size_t)L.rows_cap * kCand * 8, 256);
-    L.off_cnt = o; o = align_up(o + (size_t)L.rows_cap * 4, 256);
-    L.off_redo = o; o = align_up(o + (size_t)L.rows_cap * 4, 256);
-    L.off_redo_n = o; o = align_up(o + 4, 256);
-    L.off_ruser = o; o = align_up(o + (size_t)L.rows_cap * 4, 256);
-    L.off_ridx = o; o = align_up(o + (size_t)L.rows_cap * k * 4, 256);
-    L.off_rsc = o; o = align_up(o + (size_t)L.rows_cap * k * 4, 256);
-    L.total = o;
+    auto take = [&](size_t bytes, size_t al) { size_t at = align_up(o, al); o = at + bytes; return at; };
+    L.off_vh = take((size_t)L.items_pad * L.dpad * 2, 1024);
+    L.off_uh = take((size_t)L.rows_cap * L.dpad * 2, 1024);
+    L.off_unorm = take((size_t)L.rows_cap * 4, 256);
+    L.off_vnorm = take((size_t)L.items_pad * 4, 256);
+    L.off_vnorm_sorted = take((size_t)L.items_pad * 4, 256);
+    L.off_iota = take((size_t)L.items_pad * 4, 256);
+    L.off_perm = take((size_t)L.items_pad * 4, 256);
+    L.off_tnorm = take((size_t)L.n_tiles * 4, 256);
+    L.off_scalars = take(64, 256);   // [0] max|v| bits, [1] max|u| bits, [2] scale_v, [3] scale_u
+    L.off_sort = take(L.sort_bytes, 256);
+    L.off_cand = take((size_t)L.rows_cap * kCand * 8, 256);
+    L.off_cnt = take((size_t)L.rows_cap * 4, 256);
+    L.off_redo = take((size_t)L.rows_cap * 4, 256);
+    L.off_redo_n = take(4, 256);
+    L.off_ruser = take((size_t)L.rows_cap * 4, 256);
+    L.off_ridx = take((size_t)L.rows_cap * k * 4, 256);
+    L.off_rsc = take((size_t)L.rows_cap * k * 4, 256);
+    L.total = align_up(o, 256);
     return L;
 }
 
@@ -521,14 +588,20 @@ int64_t score_topk_tc_workspace(int n_users, int num_items, int d, int k) {
 template <int KB>
 static int launch_candidates(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int n_blocks,
                              cudaStream_t s) {
-    auto kern = tc_candidate_kernel<KB>;
     const size_t a_bytes = (size_t)KB * kBM * 128;
     int stages = (int)((224 * 1024 - a_bytes - 4096) / (kBN * 128));
     if (stages > 8) stages = 8;
     B200_REQUIRE(stages >= 2, B200REC_EUNSUPPORTED, "score_topk TC: d too large for shared memory");
     const size_t smem = 1024 + a_bytes + (size_t)stages * kBN * 128 + 22 * 8 + kEpiWarps * 32 * 4 + 64;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
+    if (p.dump) {
+        auto kern = tc_candidate_kernel<KB, true>;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
+    } else {
+        auto kern = tc_candidate_kernel<KB, false>;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
+    }
     B200_LAUNCH_CHECK();
     return B200REC_OK;
 }
@@ -543,10 +616,15 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
     unsigned char *base = reinterpret_cast<unsigned char *>(align_up((size_t)ws, 1024));
     B200_REQUIRE(ws && (int64_t)((base - (unsigned char *)ws) + L.total) <= ws_bytes, B200REC_ENOMEM,
                  "score_topk TC: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)L.total + 1024);
-    __nv_bfloat16 *vb = reinterpret_cast<__nv_bfloat16 *>(base + L.off_vb);
-    __nv_bfloat16 *ub = reinterpret_cast<__nv_bfloat16 *>(base + L.off_ub);
-    float *norms = reinterpret_cast<float *>(base + L.off_norm);
-    unsigned *vmax = reinterpret_cast<unsigned *>(base + L.off_vmax);
+    __half *vh = reinterpret_cast<__half *>(base + L.off_vh);
+    __half *uh = reinterpret_cast<__half *>(base + L.off_uh);
+    float *unorm = reinterpret_cast<float *>(base + L.off_unorm);
+    float *vnorm = reinterpret_cast<float *>(base + L.off_vnorm);
+    uint32_t *vnorm_sorted = reinterpret_cast<uint32_t *>(base + L.off_vnorm_sorted);
+    int32_t *iota = reinterpret_cast<int32_t *>(base + L.off_iota);
+    int32_t *perm = reinterpret_cast<int32_t *>(base + L.off_perm);
+    float *tnorm = reinterpret_cast<float *>(base + L.off_tnorm);
+    unsigned *scal = reinterpret_cast<unsigned *>(base + L.off_scalars);
     uint64_t *cand = reinterpret_cast<uint64_t *>(base + L.off_cand);
     int32_t *cnt = reinterpret_cast<int32_t *>(base + L.off_cnt);
     int32_t *redo = reinterpret_cast<int32_t *>(base + L.off_redo);
@@ -556,24 +634,41 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
     float *rsc = reinterpret_cast<float *>(base + L.off_rsc);
     const int sms = sm_count();
 
-    // item table -> bf16 once per call
-    B200_CUDA(cudaMemsetAsync(vmax, 0, 4, s));
-    to_bf16_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, num_items, L.items_pad, L.dpad, vb, nullptr, vmax);
+    // ---- item side, once per call: norms, descending-norm order, fp16 copy in that order, per-tile bound ----
+    B200_CUDA(cudaMemsetAsync(scal, 0, 64, s));
+    row_stats_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, num_items, vnorm, scal + 0);
+    B200_LAUNCH_CHECK();
+    iota_kernel<<<(num_items + 255) / 256, 256, 0, s>>>(iota, num_items);
+    B200_LAUNCH_CHECK();
+    size_t sort_bytes = L.sort_bytes;
+    B200_CUDA(cub::DeviceRadixSort::SortPairsDescending(base + L.off_sort, sort_bytes,
+                                                         reinterpret_cast<const uint32_t *>(vnorm), vnorm_sorted,
+                                                         (const int32_t *)iota, perm, num_items, 0, 32, s));
+    count_launch(3);
+    to_f16_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, perm, num_items, L.items_pad, L.dpad, scal + 0, vh,
+                                           reinterpret_cast<float *>(scal + 2));
+    B200_LAUNCH_CHECK();
+    tile_norm_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(vnorm_sorted, num_items, L.n_tiles, tnorm);
     B200_LAUNCH_CHECK();
     CUtensorMap mb;
-    int rc = make_map(&mb, vb, (uint64_t)L.items_pad, (uint64_t)L.dpad, kBN);
+    int rc = make_map(&mb, vh, (uint64_t)L.items_pad, (uint64_t)L.dpad, kBN);
     if (rc) return rc;
 
     for (int r0 = 0; r0 < n_users; r0 += L.rows_cap) {
         const int nr = (n_users - r0) < L.rows_cap ? (n_users - r0) : L.rows_cap;
         const int nr_pad = (int)align_up(nr, kBM);
-        to_bf16_kernel<<<sms * 4, 256, 0, s>>>(U, ld, d, users + r0, nr, nr_pad, L.dpad, ub, norms, nullptr);
+        B200_CUDA(cudaMemsetAsync(scal + 1, 0, 4, s));
+        row_stats_kernel<<<sms * 4, 256, 0, s>>>(U, ld, d, users + r0, nr, unorm, scal + 1);
+        B200_LAUNCH_CHECK();
+        to_f16_kernel<<<sms * 4, 256, 0, s>>>(U, ld, d, users + r0, nullptr, nr, nr_pad, L.dpad, scal + 1, uh,
+                                               reinterpret_cast<float *>(scal + 3));
         B200_LAUNCH_CHECK();
         CUtensorMap ma;
-        if ((rc = make_map(&ma, ub, (uint64_t)nr_pad, (uint64_t)L.dpad, kBM))) return rc;
+        if ((rc = make_map(&ma, uh, (uint64_t)nr_pad, (uint64_t)L.dpad, kBM))) return rc;
         TcParams p;
-        p.n_rows = nr; p.num_items = num_items; p.n_tiles = L.items_pad / kBN; p.k = k; p.d = d;
-        p.users = users + r0; p.mask_indptr = mi; p.row_norm = norms; p.vmax_bits = vmax;
+        p.n_rows = nr; p.num_items = num_items; p.n_tiles = L.n_tiles; p.k = k; p.d = d;
+        p.users = users + r0; p.mask_indptr = mi; p.row_norm = unorm; p.tile_norm = tnorm;
+        p.scale_v = reinterpret_cast<float *>(scal + 2); p.scale_u = reinterpret_cast<float *>(scal + 3);
         p.cand = cand; p.cand_cnt = cnt; p.dump = dump ? dump + (size_t)r0 * L.items_pad : nullptr;
         switch (L.KB) {
             case 1: rc = launch_candidates<1>(ma, mb, p, nr_pad / kBM, s); break;
@@ -588,8 +683,8 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         B200_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         int rgrid = (nr + 7) / 8;
         if (rgrid > sms * 8) rgrid = sms * 8;
-        rerank_kernel<<<rgrid, 256, rsmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, cand, cnt, oi + (size_t)r0 * k,
-                                                os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
+        rerank_kernel<<<rgrid, 256, rsmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, perm, cand, cnt,
+                                                oi + (size_t)r0 * k, os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
         B200_LAUNCH_CHECK();
         int n_redo = 0;
         B200_CUDA(cudaMemcpyAsync(&n_redo, redo_n, 4, cudaMemcpyDeviceToHost, s));
@@ -597,10 +692,10 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         if (getenv("B200REC_TC_STATS")) {  // diagnostics only
             std::vector<int32_t> hc((size_t)nr);
             cudaMemcpy(hc.data(), cnt, (size_t)nr * 4, cudaMemcpyDeviceToHost);
-            long long tot = 0, mx = 0, over = 0;
-            for (int v : hc) { if (v < 0) ++over; else { tot += v; if (v > mx) mx = v; } }
+            long long tot = 0, mxc = 0, over = 0;
+            for (int v : hc) { if (v < 0) ++over; else { tot += v; if (v > mxc) mxc = v; } }
             fprintf(stderr, "[b200rec tc] rows=%d redo=%d (cnt<0: %lld) mean_cand=%.1f max_cand=%lld k=%d tiles=%d\n", nr,
-                    n_redo, over, nr > over ? (double)tot / (double)(nr - over) : 0.0, mx, k, p.n_tiles);
+                    n_redo, over, nr > over ? (double)tot / (double)(nr - over) : 0.0, mxc, k, p.n_tiles);
         }
         if (n_redo > 0) {  // rows the candidate buffer could not hold: exact kernel, then scatter back
             gather_ids_kernel<<<(n_redo + 255) / 256, 256, 0, s>>>(users + r0, redo, n_redo, ruser);
@@ -625,8 +720,10 @@ int score_topk_tc(const float *U, const float *V, int ld, int d, const int32_t *
 
 }  // namespace b200
 
-// bring-up / test hook: raw bf16 tensor-core scores of the candidate pass, dense fp32
-// [rows_pad(256), items_pad(128)] row-major (no top-k).  Not part of the reference surface.
+// bring-up / test hook: raw fp16 tensor-core scores of the candidate pass, dense fp32
+// [rows_pad(256), items_pad(128)] row-major, items in the kernel's descending-norm order and
+// in the rescaled domain; `perm_out` (int32 [num_items]) and `scales_out` (2 floats: scale_v,
+// scale_u) describe both.  Not part of the reference surface.
 extern "C" int b200rec_debug_tc_scores(const float *U, const float *V, int ld, int d, const int32_t *users, int n_users,
                                        int num_items, float *dump, void *workspace, int64_t workspace_bytes,
                                        void *stream) {
@@ -635,4 +732,13 @@ extern "C" int b200rec_debug_tc_scores(const float *U, const float *V, int ld, i
     B200_REQUIRE(n_users <= kRowsPerLaunch, B200REC_EINVAL, "debug_tc_scores: at most %d rows", kRowsPerLaunch);
     return score_topk_tc_impl(U, V, ld, d, users, n_users, num_items, nullptr, nullptr, 1, nullptr, nullptr, workspace,
                               workspace_bytes, dump, (cudaStream_t)stream);
+}
+
+// workspace offsets of the permutation and the two scales written by the call above (test hook)
+extern "C" int b200rec_debug_tc_layout(int n_users, int num_items, int d, int64_t *off_perm, int64_t *off_scales) {
+    using namespace b200;
+    const TcLayout L = tc_layout(n_users, num_items, d, 1);
+    *off_perm = (int64_t)L.off_perm;
+    *off_scales = (int64_t)L.off_scalars + 8;
+    return B200REC_OK;
 }

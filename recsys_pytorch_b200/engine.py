@@ -148,7 +148,9 @@ def score_topk(U, V, d, users, mask: DeviceCSR | None, k, algo=SCORE_EXACT, want
 
 
 def debug_tc_scores(U, V, d, users):
-    """Test hook: raw bf16 tensor-core scores of the candidate pass, fp32 [n, I]."""
+    """Test hook: raw fp16 tensor-core scores of the candidate pass.  Returns (scores fp32 [n, I] in
+    ORIGINAL item order and unscaled, scale_u, scale_v, perm) - the kernel itself works on items sorted by
+    descending norm and on power-of-two rescaled tables."""
     users = _i32(users, "users")
     n, ni = users.numel(), V.shape[0]
     rp, ip = (n + 255) // 256 * 256, (ni + 127) // 128 * 128
@@ -157,7 +159,15 @@ def debug_tc_scores(U, V, d, users):
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=U.device)
     check(_lib.lib().b200rec_debug_tc_scores(ptr(U), ptr(V), U.shape[1], d, ptr(users), n, ni, ptr(out), ptr(ws),
                                              ws_bytes, current_stream()))
-    return out[:n, :ni]
+    off_perm, off_scales = C.c_int64(0), C.c_int64(0)
+    check(_lib.lib().b200rec_debug_tc_layout(n, ni, d, C.byref(off_perm), C.byref(off_scales)))
+    base = (-ws.data_ptr()) % 1024
+    perm = ws[base + off_perm.value: base + off_perm.value + 4 * ni].view(torch.int32).long()
+    scales = ws[base + off_scales.value: base + off_scales.value + 8].view(torch.float32)
+    sv, su = float(scales[0]), float(scales[1])
+    res = torch.empty((n, ni), dtype=torch.float32, device=U.device)
+    res[:, perm] = out[:n, :ni] / (su * sv)
+    return res, su, sv, perm
 
 
 def predict_dense(U, V, d, users, mask: DeviceCSR | None):

@@ -34,13 +34,21 @@ def test_tc_raw_scores_are_the_bf16_gemm(dev, d):
     nu, ni = 300, 1000                      # ragged in both tile dimensions
     U, V = _tables(rng, nu, ni, d, dev)
     users = torch.from_numpy(rng.permutation(nu).astype(np.int32)).to(dev)
-    got = engine.debug_tc_scores(U, V, d, users)
-    Ub = U[users.long(), :d].to(torch.bfloat16).to(torch.float64)
-    Vb = V[:, :d].to(torch.bfloat16).to(torch.float64)
-    ref = (Ub @ Vb.T).to(torch.float32)
-    scale = float(torch.linalg.norm(Ub, dim=1).max() * torch.linalg.norm(Vb, dim=1).max())
+    got, su, sv, perm = engine.debug_tc_scores(U, V, d, users)
+    assert sorted(perm.tolist()) == list(range(ni))                       # a permutation of the items ...
+    norms = torch.linalg.norm(V[:, :d], dim=1)[perm]
+    assert bool((norms[:-1] >= norms[1:] * (1 - 1e-6)).all())             # ... by descending norm
+    Uh = (U[users.long(), :d] * su).to(torch.float16).to(torch.float64) / su   # power-of-two rescale + fp16 rounding
+    Vh = (V[:, :d] * sv).to(torch.float16).to(torch.float64) / sv
+    ref = (Uh @ Vh.T).to(torch.float32)
+    scale = float(torch.linalg.norm(Uh, dim=1).max() * torch.linalg.norm(Vh, dim=1).max())
     err = float((got - ref).abs().max())
-    assert err < 2e-6 * scale, f"max |tc - bf16 gemm| = {err} (scale {scale})"
+    assert err < 2e-6 * scale, f"max |tc - fp16 gemm| = {err} (scale {scale})"
+    # and the rigorous bound the candidate filter relies on: |S~ - S| <= c |u| |v|
+    exact = (U[users.long(), :d].double() @ V[:, :d].double().T)
+    bound = (2.0 ** -10 * 1.05 + d * 2.4e-7) * torch.linalg.norm(U[users.long(), :d].double(), dim=1)[:, None] \
+        * torch.linalg.norm(V[:, :d].double(), dim=1)[None, :]
+    assert bool(((got.double() - exact).abs() <= bound).all())
 
 
 @pytest.mark.parametrize("d,k,nu,ni,std", [(128, 10, 300, 3000, 1.0), (128, 100, 513, 20000, 1.0), (64, 100, 256, 9000, 0.1),
@@ -57,6 +65,23 @@ def test_tc_equals_exact(dev, d, k, nu, ni, std):
     it2, _ = engine.score_topk(U, V, d, users, None, k, algo=SCORE_TC)
     ie2, _ = engine.score_topk(U, V, d, users, None, k, algo=SCORE_EXACT)
     assert torch.equal(it2, ie2)
+
+
+def test_tc_equals_exact_heavy_tailed_norms_and_few_rows(dev):
+    """Popular items with 10x norms (what a trained model looks like), K=100, and a user count small enough
+    that the exact kernel itself runs in its item-split + merge form."""
+    rng = np.random.default_rng(11)
+    nu, ni, d, k = 700, 30000, 128, 100
+    U, V = _tables(rng, nu, ni, d, dev, 0.1)
+    V *= torch.exp(torch.randn(ni, 1, device=dev) * 0.8)
+    mask = _mask(rng, nu, ni, 0, 100, dev)
+    users = torch.from_numpy(rng.permutation(nu).astype(np.int32)).to(dev)
+    ie, se = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_EXACT)
+    it, st = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_TC)
+    assert torch.equal(it, ie) and torch.equal(st, se)
+    few = users[:5].contiguous()                                   # 5 rows -> hundreds of item splits
+    i5, s5 = engine.score_topk(U, V, d, few, mask, k, algo=SCORE_EXACT)
+    assert torch.equal(i5, ie[:5]) and torch.equal(s5, se[:5])
 
 
 def test_tc_heavy_mask_rows_and_ties_fall_back_to_exact(dev):
