@@ -153,7 +153,7 @@ def run_b200(args):
     n_perm = 4
     perms = [torch.randperm(c["num_users"], device=dev, generator=g)[:B].to(torch.int32).contiguous() for _ in range(n_perm)]
     loss = torch.zeros(1, dtype=torch.float64, device=dev)
-    flags = (_lib.F_TMA_GATHER if args.gather == "tma" else 0) | _lib.F_USERS_UNIQUE
+    flags = _lib.GATHER_FLAGS[args.gather] | _lib.F_USERS_UNIQUE
 
     def step_dev(s):
         engine.bpr_step(model.U, model.V, d, perms[s % n_perm], csr=train, lr=c["lr"], reg=c["reg"],
@@ -313,7 +313,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gather", default="ldg", choices=["tma", "ldg"])
+    ap.add_argument("--gather", default="ldg", choices=["ldg", "async", "tma", "generic"])
     ap.add_argument("--score-algo", dest="score_algo", default="exact", choices=["exact", "tc"])
     ap.add_argument("--layout", default="item_sharded", choices=["item_sharded", "user_sharded"])
     ap.add_argument("--small", action="store_true", help="tiny shapes for a quick functional run (NOT a bench value)")

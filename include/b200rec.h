@@ -85,6 +85,7 @@ int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int3
 #define B200REC_F_TMA_GATHER 2   /* rows gathered with cp.async.bulk (TMA) into shared memory */
 #define B200REC_F_ITEM_DELTA 4   /* SINK_UPDATE: item-row deltas accumulate into dense gV (user-sharded layout) */
 #define B200REC_F_GENERIC 8      /* force the general kernel where the lean d=128/256 fast path would be taken */
+#define B200REC_F_ASYNC_GATHER 16 /* fast path with the deep cp.async (LDGSTS) per-warp row ring */
 
 typedef struct b200rec_bpr_args {
     float *U;              /* [num_users, ld]  user_embedding.weight (models/MF.py:23)   */

@@ -729,6 +729,29 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
         !(a.flags & (B200REC_F_TMA_GATHER | B200REC_F_ITEM_DELTA | B200REC_F_GENERIC)) && !a.udelta &&
         a.item_hi == a.item_lo && !a.x_out) {
         const bool uniq = (a.flags & B200REC_F_USERS_UNIQUE) != 0, loss = a.loss_sum != nullptr;
+        if (a.flags & B200REC_F_ASYNC_GATHER) {   // deep cp.async ring (bpr_step_async_kernel)
+            const size_t smem = (size_t)8 * 8 * 3 * 512;   // 8 warps x (S*CPL = 8) x 3 rows x 512 B = 96 KB
+#define B200_ASYNC(C, Q, L, SS)                                                                                \
+    {                                                                                                          \
+        auto kern = bpr_step_async_kernel<C, Q, L, SS>;                                                        \
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        int occ = 0;                                                                                           \
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));                       \
+        if (occ < 1) occ = 1;                                                                                  \
+        const int64_t need_a = (p.n_chunks + 7) / 8, cap_a = (int64_t)sm_count() * occ;                        \
+        kern<<<(int)(need_a < cap_a ? need_a : cap_a), 256, smem, s>>>(p);                                     \
+    }
+            if (CPL == 1) {
+                if (uniq) { if (loss) B200_ASYNC(1, true, true, 8) else B200_ASYNC(1, true, false, 8) }
+                else { if (loss) B200_ASYNC(1, false, true, 8) else B200_ASYNC(1, false, false, 8) }
+            } else {
+                if (uniq) { if (loss) B200_ASYNC(2, true, true, 4) else B200_ASYNC(2, true, false, 4) }
+                else { if (loss) B200_ASYNC(2, false, true, 4) else B200_ASYNC(2, false, false, 4) }
+            }
+#undef B200_ASYNC
+            B200_LAUNCH_CHECK();
+            return B200REC_OK;
+        }
         const int64_t need = (p.n_chunks + 7) / 8;
         const int64_t cap = (int64_t)sm_count() * (CPL == 1 ? 3 : 2);
         const int grid = (int)(need < cap ? need : cap);

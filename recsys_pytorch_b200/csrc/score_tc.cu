@@ -105,6 +105,28 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 #pragma unroll
     for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
 }
+// asynchronous 32-column load (no wait) + the wait that also pins the destination registers
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -170,6 +192,10 @@ __global__ void __launch_bounds__(256) to_f16_kernel(const float *__restrict__ s
     }
 }
 
+__global__ void inverse_perm_kernel(const int32_t *perm, int n, int32_t *inv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[perm[i]] = i;
+}
 __global__ void iota_kernel(int32_t *out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = i;
@@ -184,6 +210,8 @@ struct TcParams {
     int n_rows, num_items, n_tiles, k, d;
     const int32_t *users;            // row -> user id (mask row)
     const int64_t *mask_indptr;      // may be NULL
+    const int32_t *mask_indices;
+    const int32_t *inv_perm;         // item id -> sorted position
     const float *row_norm;           // [n_rows]
     const float *tile_norm;          // [n_tiles]
     const float *scale_u, *scale_v;  // device scalars (powers of two)
@@ -204,6 +232,8 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         const int kf = __shfl_sync(0xffffffffu, keff, Lsrc);
         const float c_u = __shfl_sync(0xffffffffu, cu, Lsrc);
         const float old_tau = __shfl_sync(0xffffffffu, tau, Lsrc);
+        // lo[] = lower bound of the CLEAN entries only (bit 31 of the position = "maybe masked": such an
+        // entry never counts towards the K items that justify tau); hi[] = upper bound of every entry
         uint64_t e[kCand / 32];
         float lo[kCand / 32], hi[kCand / 32];
         float mn = INFINITY, mx = -INFINITY;
@@ -211,12 +241,15 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         for (int i = 0; i < kCand / 32; ++i) {
             const int p = lane + 32 * i;
             e[i] = (p < n) ? base[p] : 0ull;
-            lo[i] = INFINITY; hi[i] = -INFINITY;
+            lo[i] = -INFINITY; hi[i] = -INFINITY;
             if (p < n) {
                 const float s = ord2f((uint32_t)(e[i] >> 32));
-                const float err = c_u * tile_norm[(uint32_t)(e[i] & 0xFFFFFFFFu) / kBN];
-                lo[i] = s - err; hi[i] = s + err;
-                mn = fminf(mn, lo[i]); mx = fmaxf(mx, lo[i]);
+                const float err = c_u * tile_norm[(uint32_t)(e[i] & 0x7FFFFFFFu) / kBN];
+                hi[i] = s + err;
+                if (!((uint32_t)e[i] >> 31)) {
+                    lo[i] = s - err;
+                    mn = fminf(mn, lo[i]); mx = fmaxf(mx, lo[i]);
+                }
             }
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -228,7 +261,7 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         const float scale = (mx > mn) ? 32.f / (mx - mn) : 0.f;
 #pragma unroll
         for (int i = 0; i < kCand / 32; ++i) {
-            if (lane + 32 * i < n) {
+            if (lo[i] > -INFINITY) {
                 int b = (int)((lo[i] - mn) * scale);
                 b = b > 31 ? 31 : (b < 0 ? 0 : b);
                 atomicAdd(&hist[b], 1);
@@ -242,18 +275,19 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         }
         const unsigned okb = __ballot_sync(0xffffffffu, suf >= kf);
         const int bstar = okb ? 31 - __clz(okb) : 0;
-        // new tau = smallest L among the entries in buckets >= bstar  (so at least kf entries have L >= tau)
+        // new tau = smallest L among the clean entries in buckets >= bstar (at least kf clean entries have
+        // L >= tau); with fewer than kf clean entries tau cannot move
         float t_new = INFINITY;
 #pragma unroll
         for (int i = 0; i < kCand / 32; ++i) {
-            if (lane + 32 * i < n) {
+            if (lo[i] > -INFINITY) {
                 int b = (int)((lo[i] - mn) * scale);
                 b = b > 31 ? 31 : (b < 0 ? 0 : b);
                 if (b >= bstar) t_new = fminf(t_new, lo[i]);
             }
         }
         for (int o = 16; o > 0; o >>= 1) t_new = fminf(t_new, __shfl_xor_sync(0xffffffffu, t_new, o));
-        t_new = fmaxf(old_tau, t_new);
+        t_new = okb ? fmaxf(old_tau, t_new) : old_tau;
         // compact: keep entries whose upper bound still reaches tau
         int keep = 0;
 #pragma unroll
@@ -369,64 +403,89 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
         const float *__restrict__ tile_norm = p.tile_norm;
         const int num_items = p.num_items;
-        int cnt = 0, keff = p.k;
+        int cnt = 0;
+        const int keff = p.k;
         float tau = -INFINITY, cu = 0.f;
+        // 128-bit "maybe masked" filter of this row: one bit per hashed sorted-position of a train positive
+        // (no false negatives).  Flagged candidates are kept but never counted towards the K items behind tau.
+        uint64_t f_lo = 0, f_hi = 0;
         if (row_ok) {
             if (p.mask_indptr) {
                 const int u = p.users[row];
-                keff += (int)(p.mask_indptr[u + 1] - p.mask_indptr[u]);
+                const int64_t mb = p.mask_indptr[u], me = p.mask_indptr[u + 1];
+                for (int64_t m = mb; m < me; ++m) {
+                    const uint32_t hsh = ((uint32_t)p.inv_perm[p.mask_indices[m]] * 2654435761u) >> 25;
+                    if (hsh & 64u) f_hi |= 1ull << (hsh & 63u); else f_lo |= 1ull << (hsh & 63u);
+                }
             }
             const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;   // 2^-10 (+5%) + fp32 accumulation slack
             cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);         // error bound per unit item norm, scaled domain
-            if (keff > kCand / 2 - 32) { cnt = -1; tau = INFINITY; }         // too many masked items for the buffer
         } else {
             tau = INFINITY;
         }
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kBN;
+        uint32_t ra[32], rb[32];
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t as = t & 1, aph = (t >> 1) & 1u;
             const float thr = tau - cu * tile_norm[t];   // keep S~ with S~ + e_t >= tau
             mbar_wait(s32(tfull + as), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int n0 = t * kBN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < kBN; c0 += 64) {
-                float v[64];
-                tmem_ld64(lane_addr + as * 2 * kBN + c0, v);
+            const uint32_t taddr = lane_addr + as * 2 * kBN;
+            // 4 chunks of 32 columns, the next chunk's tcgen05.ld in flight while the current one is filtered
+            auto process = [&](uint32_t (&rr)[32], int c0) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
                 if (DUMP) {
                     float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * kBN) + n0 + c0;
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) dst[j] = v[j];
+                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
                 }
-                float gm[8];
+                float gm[4];
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
+                for (int g = 0; g < 4; ++g) {
                     const float a = max3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
                     const float b = max3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
                     gm[g] = max3(a, b, fmaxf(v[8 * g + 6], v[8 * g + 7]));
                 }
-                const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
+                const float m = fmaxf(max3(gm[0], gm[1], gm[2]), gm[3]);
                 if (m >= thr && cnt >= 0) {
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
+                    for (int g = 0; g < 4; ++g) {
                         if (gm[g] >= thr) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float s = v[8 * g + j];
-                                const int pos = n0 + c0 + 8 * g + j;
-                                if (s >= thr && pos < num_items) {
-                                    my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (uint32_t)pos;
+                                const uint32_t pos = (uint32_t)(n0 + c0 + 8 * g + j);
+                                if (s >= thr && pos < (uint32_t)num_items) {
+                                    const uint32_t hsh = (pos * 2654435761u) >> 25;
+                                    const uint32_t flag = (uint32_t)(((hsh & 64u) ? f_hi : f_lo) >> (hsh & 63u)) & 1u;
+                                    my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (flag << 31) | pos;
                                     ++cnt;
                                 }
                             }
                         }
                     }
                 }
-            }
-            // this warp is done reading the accumulator pair of tile t
+            };
+            tmem_ld32_async(taddr, ra);
+            tmem_ld_wait32(ra);
+            tmem_ld32_async(taddr + 32, rb);
+            process(ra, 0);
+            tmem_ld_wait32(rb);
+            tmem_ld32_async(taddr + 64, ra);
+            process(rb, 32);
+            tmem_ld_wait32(ra);
+            tmem_ld32_async(taddr + 96, rb);
+            process(ra, 64);
+            tmem_ld_wait32(rb);
+            // every TMEM read of this warp for tile t has landed: hand the accumulator pair back before
+            // filtering the last chunk
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(s32(tempty + as));
+            process(rb, 96);
             const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kBN - 1);
             if (need) raise_thresholds(need, my_cand, cnt, tau, keff, cu, tile_norm, hist, lane);
         }
@@ -469,7 +528,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
             bool ok = c < n;
             uint64_t key = 0;
             if (ok) {
-                const int item = item_of_pos[(uint32_t)(cand[(size_t)row * kCand + c] & 0xFFFFFFFFu)];
+                const int item = item_of_pos[(uint32_t)(cand[(size_t)row * kCand + c] & 0x7FFFFFFFu)];
                 int l = 0, r = mdeg;  // masked? (models/MF.py:130)
                 while (l < r) { const int m = (l + r) >> 1; if (mrow[m] < item) l = m + 1; else r = m; }
                 if (l < mdeg && mrow[l] == item) ok = false;
@@ -547,7 +606,7 @@ static size_t sort_temp_bytes(int num_items) {
 
 struct TcLayout {
     int dpad, KB, rows_cap, items_pad, n_tiles;
-    size_t off_vh, off_uh, off_unorm, off_vnorm, off_vnorm_sorted, off_iota, off_perm, off_tnorm, off_scalars, off_sort,
+    size_t off_vh, off_uh, off_unorm, off_vnorm, off_vnorm_sorted, off_iota, off_perm, off_inv, off_tnorm, off_scalars, off_sort,
         sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, total;
 };
 static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
@@ -567,6 +626,7 @@ static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     L.off_vnorm_sorted = take((size_t)L.items_pad * 4, 256);
     L.off_iota = take((size_t)L.items_pad * 4, 256);
     L.off_perm = take((size_t)L.items_pad * 4, 256);
+    L.off_inv = take((size_t)L.items_pad * 4, 256);
     L.off_tnorm = take((size_t)L.n_tiles * 4, 256);
     L.off_scalars = take(64, 256);   // [0] max|v| bits, [1] max|u| bits, [2] scale_v, [3] scale_u
     L.off_sort = take(L.sort_bytes, 256);
@@ -623,6 +683,7 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
     uint32_t *vnorm_sorted = reinterpret_cast<uint32_t *>(base + L.off_vnorm_sorted);
     int32_t *iota = reinterpret_cast<int32_t *>(base + L.off_iota);
     int32_t *perm = reinterpret_cast<int32_t *>(base + L.off_perm);
+    int32_t *inv_perm = reinterpret_cast<int32_t *>(base + L.off_inv);
     float *tnorm = reinterpret_cast<float *>(base + L.off_tnorm);
     unsigned *scal = reinterpret_cast<unsigned *>(base + L.off_scalars);
     uint64_t *cand = reinterpret_cast<uint64_t *>(base + L.off_cand);
@@ -645,6 +706,8 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
                                                          reinterpret_cast<const uint32_t *>(vnorm), vnorm_sorted,
                                                          (const int32_t *)iota, perm, num_items, 0, 32, s));
     count_launch(3);
+    inverse_perm_kernel<<<(num_items + 255) / 256, 256, 0, s>>>(perm, num_items, inv_perm);
+    B200_LAUNCH_CHECK();
     to_f16_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, perm, num_items, L.items_pad, L.dpad, scal + 0, vh,
                                            reinterpret_cast<float *>(scal + 2));
     B200_LAUNCH_CHECK();
@@ -667,7 +730,8 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         if ((rc = make_map(&ma, uh, (uint64_t)nr_pad, (uint64_t)L.dpad, kBM))) return rc;
         TcParams p;
         p.n_rows = nr; p.num_items = num_items; p.n_tiles = L.n_tiles; p.k = k; p.d = d;
-        p.users = users + r0; p.mask_indptr = mi; p.row_norm = unorm; p.tile_norm = tnorm;
+        p.users = users + r0; p.mask_indptr = mi; p.mask_indices = mx; p.inv_perm = inv_perm;
+        p.row_norm = unorm; p.tile_norm = tnorm;
         p.scale_v = reinterpret_cast<float *>(scal + 2); p.scale_u = reinterpret_cast<float *>(scal + 3);
         p.cand = cand; p.cand_cnt = cnt; p.dump = dump ? dump + (size_t)r0 * L.items_pad : nullptr;
         switch (L.KB) {

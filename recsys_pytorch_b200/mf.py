@@ -122,7 +122,8 @@ class MF(BaseModel):
         return self.item_embedding.store
 
     def _flags(self, users_unique):
-        f = F_TMA_GATHER if self.gather == "tma" else 0
+        from ._lib import GATHER_FLAGS
+        f = GATHER_FLAGS.get(self.gather, 0)
         return f | (F_USERS_UNIQUE if users_unique else 0)
 
     @staticmethod
