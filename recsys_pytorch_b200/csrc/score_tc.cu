@@ -424,35 +424,39 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tau = INFINITY;
         }
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kBN;
-        uint32_t ra[32], rb[32];
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t as = t & 1, aph = (t >> 1) & 1u;
             const float thr = tau - cu * tile_norm[t];   // keep S~ with S~ + e_t >= tau
             mbar_wait(s32(tfull + as), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int n0 = t * kBN;
-            const uint32_t taddr = lane_addr + as * 2 * kBN;
-            // 4 chunks of 32 columns, the next chunk's tcgen05.ld in flight while the current one is filtered
-            auto process = [&](uint32_t (&rr)[32], int c0) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kBN; c0 += 64) {
+                float v[64];
+                tmem_ld64(lane_addr + as * 2 * kBN + c0, v);
+                if (c0 == kBN - 64) {
+                    // every TMEM read of this warp for tile t has landed: hand the accumulator pair back
+                    // before filtering the last half
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s32(tempty + as));
+                }
                 if (DUMP) {
                     float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * kBN) + n0 + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                    for (int j = 0; j < 64; ++j) dst[j] = v[j];
                 }
-                float gm[4];
+                float gm[8];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 8; ++g) {
                     const float a = max3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
                     const float b = max3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
                     gm[g] = max3(a, b, fmaxf(v[8 * g + 6], v[8 * g + 7]));
                 }
-                const float m = fmaxf(max3(gm[0], gm[1], gm[2]), gm[3]);
+                const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
                 if (m >= thr && cnt >= 0) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
+                    for (int g = 0; g < 8; ++g) {
                         if (gm[g] >= thr) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -468,24 +472,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                 }
-            };
-            tmem_ld32_async(taddr, ra);
-            tmem_ld_wait32(ra);
-            tmem_ld32_async(taddr + 32, rb);
-            process(ra, 0);
-            tmem_ld_wait32(rb);
-            tmem_ld32_async(taddr + 64, ra);
-            process(rb, 32);
-            tmem_ld_wait32(ra);
-            tmem_ld32_async(taddr + 96, rb);
-            process(ra, 64);
-            tmem_ld_wait32(rb);
-            // every TMEM read of this warp for tile t has landed: hand the accumulator pair back before
-            // filtering the last chunk
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s32(tempty + as));
-            process(rb, 96);
+            }
             const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kBN - 1);
             if (need) raise_thresholds(need, my_cand, cnt, tau, keff, cu, tile_norm, hist, lane);
         }

@@ -131,6 +131,42 @@ class UserShardedBPR:
         allreduce_sum(dV)                                                          # the ONE collective of the step
         self.apply_item_delta(dV)
 
+    # ---- same step with the collective hidden behind the next step's kernel --------------------------
+    def step_overlapped(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True):
+        """The all-reduce of step s runs on a side stream while the fused kernel of step s+1 executes; the
+        reduced item delta is applied one step late (item rows are one step stale - bounded-staleness SGD;
+        `flush()` applies the last delta).  User rows are never stale."""
+        if not hasattr(self, "_ov"):
+            self._ov = dict(bufs=[self.dV, torch.zeros_like(self.dV)], comm=torch.cuda.Stream(device=self.device),
+                            ev_done=[torch.cuda.Event(), torch.cuda.Event()], ev_k=torch.cuda.Event(), n=0,
+                            pending=None)
+        ov = self._ov
+        cur = ov["n"] & 1
+        buf = ov["bufs"][cur]
+        main = torch.cuda.current_stream(self.device)
+        buf.zero_()
+        engine.bpr_step(self.U, self.V, self.d, users_local, csr=self.train, lr=self.lr, reg=self.reg,
+                        sink=SINK_UPDATE, flags=self.flags | (F_USERS_UNIQUE if users_unique else 0), seed=self.seed,
+                        step=step_key * self.world + self.rank, loss_sum=loss_sum, gV=buf,
+                        inv_batch=1.0 / float(global_batch))
+        ov["ev_k"].record(main)
+        with torch.cuda.stream(ov["comm"]):
+            ov["comm"].wait_event(ov["ev_k"])
+            allreduce_sum(buf)
+            ov["ev_done"][cur].record(ov["comm"])
+        if ov["pending"] is not None:                                              # delta of the previous step
+            main.wait_event(ov["ev_done"][ov["pending"]])
+            self.apply_item_delta(ov["bufs"][ov["pending"]])
+        ov["pending"] = cur
+        ov["n"] += 1
+
+    def flush(self):
+        ov = getattr(self, "_ov", None)
+        if ov and ov["pending"] is not None:
+            torch.cuda.current_stream(self.device).wait_event(ov["ev_done"][ov["pending"]])
+            self.apply_item_delta(ov["bufs"][ov["pending"]])
+            ov["pending"] = None
+
 
 # ------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
@@ -142,9 +178,14 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_g
     from . import _lib, synthetic
     d = c["d"]
     B_local = c["batch"]
-    nu, ni = c["num_users"] * world, min(c["num_items"] * world, 1_000_000)
+    # weak scaling: every GPU brings its own 1M users; the catalogue (100k items) does not grow
+    nu, ni = c["num_users"] * world, c["num_items"]
     layout = args.layout
     loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    secondary = None
+    if layout == "user_sharded" and not getattr(args, "no_secondary", False):
+        # the north_star layout measured in the same run (fewer steps: it is all-reduce bound)
+        secondary = _bench_item_sharded(args, c, rank, world, dev, timed_region, nu, ni, max(3, args.steps // 10))
     if layout == "item_sharded":
         # replicated CSR + replicated user table; every rank walks the same global batch of N*B_local users
         train, _ = synthetic.make_interactions(nu, ni, seed=c["seed"], device=dev)
@@ -168,8 +209,9 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_g
         B_glob = B_local * world
 
         def step(s):
-            tr.step(perms[s % 2], s + 1, B_glob, loss_sum=loss)
-        coll = "all_reduce(sum) of the dense [I, ld] fp32 item-delta buffer (%d MiB) per step" % (ni * 4 * tr.V.shape[1] >> 20)
+            tr.step_overlapped(perms[s % 2], s + 1, B_glob, loss_sum=loss)
+        coll = ("all_reduce(sum) of the dense [I, ld] fp32 item-delta buffer (%d MiB) per step, on a side stream, "
+                "overlapped with the next step's kernel (item rows one step stale)" % (ni * 4 * tr.V.shape[1] >> 20))
 
     for s in range(args.warmup):
         step(s)
@@ -189,7 +231,7 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_g
         if layout == "item_sharded":
             tr.step(u, 1000 + s, loss_sum=loss)
         else:
-            tr.step(u, 1000 + s, B_glob, loss_sum=loss)
+            tr.step_overlapped(u, 1000 + s, B_glob, loss_sum=loss)
         return float(loss.item())
 
     for s in range(2):
@@ -216,6 +258,29 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_g
                             "note": "per-GPU algorithmic bytes of the step kernel over the WHOLE step time "
                                     "(collective included)"},
                "cpu_baseline": None}
+        if secondary is not None:
+            out["north_star_item_sharded"] = secondary
         print(json.dumps(out))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _bench_item_sharded(args, c, rank, world, dev, timed_region, nu, ni, steps):
+    """BASELINE north_star layout (item table sharded by id range, user table replicated, ONE all-reduce of the
+    [B, ld] user-delta buffer per step) at the same shape, for the record."""
+    from . import synthetic
+    train, _ = synthetic.make_interactions(nu, ni, seed=c["seed"], device=dev)
+    tr = ItemShardedBPR(nu, ni, c["d"], train, rank, world, dev, lr=c["lr"], reg=c["reg"], init_std=c["init_std"],
+                        seed=c["seed"])
+    g = torch.Generator(device=dev); g.manual_seed(c["seed"])
+    B_glob = c["batch"] * world
+    perms = [torch.randperm(nu, device=dev, generator=g)[:B_glob].to(torch.int32).contiguous() for _ in range(2)]
+    for s in range(2):
+        tr.step(perms[s % 2], s + 1)
+    ms = timed_region(lambda s: tr.step(perms[s % 2], s + 3), steps, world)
+    res = {"value": B_glob * steps / (ms * 1e-3), "unit": "triples/s", "steps": steps, "ms_per_step": ms / steps,
+           "batch_triples": B_glob,
+           "collective": "all_reduce(sum) of the [B, ld] fp32 user-delta buffer (%d MiB) per step" % (B_glob * 4 * tr.U.shape[1] >> 20)}
+    del tr, train, perms
+    torch.cuda.empty_cache()
+    return res

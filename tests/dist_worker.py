@@ -36,6 +36,14 @@ def main():
     chk = tu.V.double().sum().reshape(1)
     dist.all_gather(both, chk)
     assert all(torch.equal(b, both[0]) for b in both), "item replicas diverged"
+    for s in range(6):                                   # collective overlapped with the next step's kernel
+        users = torch.randperm(uhi - ulo, device=dev, generator=g)[:4096].to(torch.int32)
+        tu.step_overlapped(users, 100 + s, 4096 * world)
+    tu.flush()
+    torch.cuda.synchronize()
+    chk = tu.V.double().sum().reshape(1)
+    dist.all_gather(both, chk)
+    assert all(torch.equal(b, both[0]) for b in both), "item replicas diverged (overlapped steps)"
     dist.barrier()
     if rank == 0:
         print("DIST_OK")
