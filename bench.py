@@ -217,7 +217,8 @@ def run_b200(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                 "traffic": traffic, "peak_source": peak_src, "bytes_per_triple": bytes_per_triple,
-                "kernel": "bpr_step_%s_kernel<32,1,UPDATE>" % args.gather}
+                "kernel": {"ldg": "bpr_step_fast_kernel<1,uniq,loss>", "async": "bpr_step_async_kernel<1,uniq,loss,8>",
+                           "tma": "bpr_step_tma_kernel<32,1,UPDATE>", "generic": "bpr_step_ldg_kernel<32,1,UPDATE>"}[args.gather]}
 
     cpu_base = cpu_baseline_leg(c, args) if not args.no_cpu else None
     out = {"metric": "BPR triples/sec (train)", "value": triples_per_s, "unit": "triples/s", "n_gpus": 1,
@@ -318,7 +319,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gather", default="ldg", choices=["ldg", "async", "tma", "generic"])
-    ap.add_argument("--score-algo", dest="score_algo", default="exact", choices=["exact", "tc"])
+    ap.add_argument("--score-algo", dest="score_algo", default="tc", choices=["exact", "tc"])
     ap.add_argument("--layout", default="user_sharded", choices=["item_sharded", "user_sharded"],
                     help="N>1: user_sharded (default; also measures the north_star item_sharded layout and reports it "
                          "under 'north_star_item_sharded') or item_sharded only")

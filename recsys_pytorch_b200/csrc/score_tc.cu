@@ -222,7 +222,7 @@ struct TcParams {
 
 // warp-cooperative threshold raise for the lanes in `need` (bit per lane); see file header.
 // Entries hold S~ (scaled); e = cu * tile_norm[pos/128]; L = S~ - e, H = S~ + e.
-__device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int keff, float cu,
+__device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff, float cu,
                                                  const float *__restrict__ tile_norm, int *hist, int lane) {
     while (need) {
         const int Lsrc = __ffs(need) - 1;
@@ -306,7 +306,9 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
             if (lane + 32 * i < n && hi[i] >= t_new) base[w++] = e[i];
         __syncwarp();
         if (lane == Lsrc) {
-            if (total > kCand - kBN - 32) { cnt = -1; tau = INFINITY; }  // cannot make room: exact kernel re-does the row
+            // a raise that frees < 48 slots three times in a row is thrashing (sticky high-uncertainty entries)
+            stalls = (n - total < 48) ? stalls + 1 : 0;
+            if (total > kCand - kBN - 32 || stalls >= 3) { cnt = -1; tau = INFINITY; }  // exact kernel re-does the row
             else { cnt = total; tau = t_new; }
         }
     }
@@ -403,7 +405,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
         const float *__restrict__ tile_norm = p.tile_norm;
         const int num_items = p.num_items;
-        int cnt = 0;
+        int cnt = 0, stalls = 0;
         const int keff = p.k;
         float tau = -INFINITY, cu = 0.f;
         // 128-bit "maybe masked" filter of this row: one bit per hashed sorted-position of a train positive
@@ -474,7 +476,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
             const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kBN - 1);
-            if (need) raise_thresholds(need, my_cand, cnt, tau, keff, cu, tile_norm, hist, lane);
+            if (need) raise_thresholds(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane);
         }
         if (row_ok) p.cand_cnt[row] = cnt;
     }

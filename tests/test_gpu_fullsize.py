@@ -1,0 +1,103 @@
+"""`-m gpu`: BASELINE.json's full sizes through size-independent properties (the oracle cannot run there)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from recsys_pytorch_b200 import _lib, engine, synthetic  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cfg2(dev):
+    train, target = synthetic.make_interactions(1_000_000, 100_000, seed=2020, device=dev)
+    return train, target
+
+
+def test_cfg2_fused_step_properties(dev, cfg2):
+    """configs[1] (1M x 100k, d=128, B=1M): sampled triples are valid BPR triples, the loss falls,
+    an epoch's permutation touches every user row exactly once, item rows move only where sampled."""
+    train, _ = cfg2
+    nu, ni, d = train.shape[0], train.shape[1], 128
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    U = engine.alloc_table(nu, d, dev, 0.01, g); V = engine.alloc_table(ni, d, dev, 0.01, g)
+    U0 = U.clone()
+    users = torch.randperm(nu, device=dev, generator=g).to(torch.int32)
+    pos, neg = torch.empty_like(users), torch.empty_like(users)
+    losses = []
+    for s in range(6):
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        engine.bpr_step(U, V, d, users, csr=train, lr=0.05 * nu, reg=1e-4, flags=_lib.F_USERS_UNIQUE, seed=7, step=s,
+                        loss_sum=loss, out_pos=pos if s == 0 else None, out_neg=neg if s == 0 else None)
+        losses.append(loss.item() / nu)
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0] - 0.01, losses
+    assert abs(losses[0] - np.log(2)) < 1e-3                     # N(0, 0.01) init: x ~ 0
+    # every sampled positive is in the user's row, every negative is not (checked on-device, all 1M triples)
+    ip, ix = train.indptr, train.indices.long()
+    lo, hi = ip[users.long()], ip[users.long() + 1]
+    def member(items):
+        key_rows = torch.repeat_interleave(torch.arange(nu, device=dev), (ip[1:] - ip[:-1]))
+        table = key_rows * ni + ix                                  # sorted keys (user, item)
+        q = users.long() * ni + items.long()
+        j = torch.searchsorted(table, q).clamp_(max=table.numel() - 1)
+        return table[j] == q
+    assert bool(member(pos).all()) and not bool(member(neg).any())
+    assert bool(((neg >= 0) & (neg < ni)).all())
+    assert bool((U != U0).any(dim=1).all())                          # every user row updated (one triple per user)
+    assert float(U[:, d:].abs().sum()) == 0.0                       # (ld == d here; pad check is in the width tests)
+
+
+def test_cfg2_tc_topk_properties_and_sample_exactness(dev, cfg2):
+    """configs[1] scoring: top-10 of 100k items for 65,536 users on the tensor-core path - sorted, unmasked,
+    idempotent, and bit-identical to the exact kernel on a sample; NDCG@10 from both paths within 1e-4 (equal)."""
+    train, target = cfg2
+    nu, ni, d, k = 65_536, train.shape[1], 128, 10
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    U = engine.alloc_table(train.shape[0], d, dev, 0.1, g); V = engine.alloc_table(ni, d, dev, 0.1, g)
+    V *= torch.exp(torch.randn(ni, 1, device=dev, generator=g) * 0.5)
+    users = torch.arange(nu, dtype=torch.int32, device=dev)
+    it, st = engine.score_topk(U, V, d, users, train, k, algo=_lib.SCORE_TC)
+    it2, st2 = engine.score_topk(U, V, d, users, train, k, algo=_lib.SCORE_TC)
+    assert torch.equal(it, it2) and torch.equal(st, st2)             # deterministic / idempotent
+    assert bool((st[:, :-1] >= st[:, 1:]).all())
+    sample = users[::64].contiguous()
+    ie, se = engine.score_topk(U, V, d, sample, train, k, algo=_lib.SCORE_EXACT)
+    assert torch.equal(it[::64], ie) and torch.equal(st[::64], se)
+    rows_tc = engine.holdout_metrics(it[::64].contiguous(), target, [k], row_ids=sample)
+    rows_ex = engine.holdout_metrics(ie, target, [k], row_ids=sample)
+    assert abs(float(engine.column_means(rows_tc)[2]) - float(engine.column_means(rows_ex)[2])) < 1e-4
+    # no train positive among the recommendations
+    ip, ix = train.indptr, train.indices.long()
+    key_rows = torch.repeat_interleave(torch.arange(train.shape[0], device=dev), (ip[1:] - ip[:-1]))
+    table = key_rows * ni + ix
+    q = (users.long()[:, None] * ni + it.long()).flatten()
+    j = torch.searchsorted(table, q).clamp_(max=table.numel() - 1)
+    assert not bool((table[j] == q).any())
+
+
+def test_cfg4_lightgcn_propagation_properties(dev, cfg2):
+    """configs[3] (LightGCN 1M x 100k, 3 layers, d=64): A_hat is symmetric-normalised, so D^(1/2) 1 is an
+    eigenvector with eigenvalue 1 (propagating it returns it), and propagation is linear."""
+    import types
+    from recsys_pytorch_b200.lightgcn import LightGCN
+    train, _ = cfg2
+    nu, ni = train.shape
+    ds = types.SimpleNamespace(num_users=nu, num_items=ni, train_data=train, dataname="synthetic")
+    m = LightGCN(ds, {"emb_dim": 64, "num_layers": 3, "node_dropout": 0.0, "split": False, "num_folds": 100,
+                      "graph_dir": "graph", "reg": 1e-4}, dev)
+    m.Graph = m.getSparseGraph(train)
+    indptr, cols, vals = m.Graph
+    assert cols.numel() == 2 * train.nnz
+    deg = (indptr[1:] - indptr[:-1]).float()
+    ev = deg.sqrt()
+    m.E0.zero_(); m.E0[:, 0] = ev; m.E0[:, 1] = -2.0 * ev
+    out = m.propagate(m.E0, m.out)
+    live = deg > 0
+    np.testing.assert_allclose(out[live, 0].cpu().numpy(), ev[live].cpu().numpy(), rtol=2e-4)
+    np.testing.assert_allclose(out[live, 1].cpu().numpy(), (-2.0 * ev[live]).cpu().numpy(), rtol=2e-4)
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    a = torch.zeros_like(m.E0); b = torch.zeros_like(m.E0)
+    a[:, :64].normal_(generator=g); b[:, :64].normal_(generator=g)
+    pa = m.propagate(a, torch.zeros_like(a)).clone(); pb = m.propagate(b, torch.zeros_like(a)).clone()
+    pab = m.propagate(a + b, torch.zeros_like(a))
+    assert float((pab - pa - pb).abs().max()) < 1e-4 * float(pab.abs().max())
