@@ -131,7 +131,19 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on STDOUT when the first communicator comes up; the contract is ONE JSON
+        # line on stdout, so that banner is sent to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     c = dict(CFG)
     if args.small:
         c.update(num_users=50_000, num_items=20_000, batch=50_000, eval_users=4096)

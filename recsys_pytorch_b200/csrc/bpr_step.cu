@@ -19,6 +19,7 @@
 //   TMA  : warp-private ring of shared-memory stages filled by cp.async.bulk
 //          (UBLKCP) row copies that complete on a warp-private mbarrier - no CTA
 //          level synchronisation at all; many rows in flight per warp.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -649,7 +650,9 @@ static int launch_bpr(BprParams &p, cudaStream_t s) {
         int st = (int)((96 * 1024) / per_stage);
         p.stages = st < 2 ? 2 : (st > kTmaMaxStages ? kTmaMaxStages : st);
     }
-    const int sms = sm_count();
+    // B200REC_SM_RESERVE=n leaves n SMs' worth of CTA slots free (room for a concurrent NCCL kernel)
+    static const int reserve = getenv("B200REC_SM_RESERVE") ? atoi(getenv("B200REC_SM_RESERVE")) : 0;
+    const int sms = sm_count() - ((reserve > 0 && reserve < sm_count()) ? reserve : 0);
     constexpr int TPW = 32 / G;
 #define B200_LAUNCH_SINK(SINKV)                                                                              \
     if (tma) {                                                                                               \

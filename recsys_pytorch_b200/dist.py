@@ -208,8 +208,13 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_g
         perms = [torch.randperm(uhi - ulo, device=dev, generator=g)[:B_local].to(torch.int32).contiguous() for _ in range(2)]
         B_glob = B_local * world
 
+        sync_mode = os.environ.get("B200REC_DIST_SYNC", "0") == "1"
+
         def step(s):
-            tr.step_overlapped(perms[s % 2], s + 1, B_glob, loss_sum=loss)
+            if sync_mode:
+                tr.step(perms[s % 2], s + 1, B_glob, loss_sum=loss)
+            else:
+                tr.step_overlapped(perms[s % 2], s + 1, B_glob, loss_sum=loss)
         coll = ("all_reduce(sum) of the dense [I, ld] fp32 item-delta buffer (%d MiB) per step, on a side stream, "
                 "overlapped with the next step's kernel (item rows one step stale)" % (ni * 4 * tr.V.shape[1] >> 20))
 
