@@ -181,22 +181,33 @@ def run_b200(args):
     triples_per_s = B * args.steps / (ms * 1e-3)
     ms_per_step = ms / args.steps
 
-    # ---- e2e: plugin API, user ids from pinned host memory, loss read back every step ----
+    # ---- e2e: plugin API, every step's user ids come from pinned host memory (H2D inside the timed region) and
+    # every step's loss is read back to the host (D2H); MF.train_batch_async double-buffers the copies so the
+    # H2D of step s+1 and the read-back of step s-1 overlap the kernel of step s ----
     host_perms = [p.cpu().pin_memory() for p in perms]
-    slot = torch.zeros(1, dtype=torch.float64, device=dev)
+    e2e_losses = []
+    pend = [None]
 
     def step_e2e(s):
-        u = host_perms[s % n_perm].to(dev, non_blocking=True)                      # H2D of the step's input
-        slot.zero_()
-        model.train_batch(u, csr=train, step_key=1000 + s, users_unique=True, loss_slot=slot)
-        return float(slot.item()) / B                                              # D2H of the step's result
+        h = model.train_batch_async(host_perms[s % n_perm], csr=train, step_key=1000 + s, users_unique=True)
+        if pend[0] is not None:
+            e2e_losses.append(pend[0].loss())                                      # host reads step s-1's result
+        pend[0] = h
+
+    def drain():
+        if pend[0] is not None:
+            e2e_losses.append(pend[0].loss()); pend[0] = None
 
     for s in range(min(args.warmup, 3)):
         step_e2e(s)
-    ms_e2e = timed_region(step_e2e, args.steps, world)
+    drain()
+    e2e_losses.clear()
+    ms_e2e = timed_region(lambda s: (step_e2e(s), drain() if s == args.steps - 1 else None), args.steps, world)
+    assert len(e2e_losses) == args.steps and all(np.isfinite(e2e_losses))
     e2e = {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": B * 4,
            "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
-           "api": "recsys_pytorch_b200.mf.MF.train_batch (users from pinned host memory, loss.item())"}
+           "api": "recsys_pytorch_b200.mf.MF.train_batch_async (users from pinned host memory; every step's loss "
+                  "read back, one step late)"}
 
     # ---- evaluation leg: fused score + mask + top-k + holdout metrics on a user sample ----
     ev_users = torch.arange(c["eval_users"], dtype=torch.int32, device=dev)

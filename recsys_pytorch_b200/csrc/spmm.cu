@@ -35,19 +35,39 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const int64_t *__restrict
             float v = 0.f;
             if (mp < end) { c = indices[mp]; v = values[mp]; }
             const int cnt = (int)((end - base) < G ? (end - base) : G);
-            for (int t = 0; t < cnt; ++t) {
-                const int cc = __shfl_sync(gmask, c, sg * G + t);
-                const float vv = __shfl_sync(gmask, v, sg * G + t);
+            // two-level summation: the <= G products of this block go into b[], then b[] into a[] - keeps the
+            // fp32 error of 100k-neighbour rows (popular items) at (deg/G) eps instead of deg eps; neighbour
+            // rows are fetched four at a time so four gathers are in flight per lane
+            float4 b[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = 0; t < cnt; t += 4) {
+                int cc[4];
+                float vv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int src = sg * G + ((t + i < G) ? (t + i) : (G - 1));
+                    cc[i] = __shfl_sync(gmask, c, src);
+                    vv[i] = __shfl_sync(gmask, v, src);
+                    if (t + i >= cnt) { vv[i] = 0.f; cc[i] = cc[0]; }
+                }
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
                     const int q = sl + k * G;
                     if (q < d4) {
-                        const float4 x = ld4(X + (int64_t)cc * ldx + q * 4);
-                        a[k].x = fmaf(vv, x.x, a[k].x); a[k].y = fmaf(vv, x.y, a[k].y);
-                        a[k].z = fmaf(vv, x.z, a[k].z); a[k].w = fmaf(vv, x.w, a[k].w);
+                        float4 x[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x[i] = ld4(X + (int64_t)cc[i] * ldx + q * 4);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            b[k].x = fmaf(vv[i], x[i].x, b[k].x); b[k].y = fmaf(vv[i], x[i].y, b[k].y);
+                            b[k].z = fmaf(vv[i], x[i].z, b[k].z); b[k].w = fmaf(vv[i], x[i].w, b[k].w);
+                        }
                     }
                 }
             }
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) { a[k].x += b[k].x; a[k].y += b[k].y; a[k].z += b[k].z; a[k].w += b[k].w; }
         }
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {

@@ -41,6 +41,17 @@ def _hp(hparams, key, default):
         return default
 
 
+class _StepHandle:
+    """Result of `MF.train_batch_async`: `.loss()` = mean -log sigmoid of that step (blocks until it is done)."""
+
+    def __init__(self, event, host_slot, batch):
+        self._event, self._host, self._batch = event, host_slot, batch
+
+    def loss(self):
+        self._event.synchronize()
+        return float(self._host[0]) / self._batch
+
+
 class BaseModel(nn.Module):
     """models/BaseModel.py:3-14 - the plugin base class (three no-op methods)."""
 
@@ -181,6 +192,36 @@ class MF(BaseModel):
         else:
             engine.bpr_step(self.U, self.V, d, users, pos, neg, csr=csr, lr=self.lr, reg=self.reg, sink=SINK_UPDATE,
                             seed=self.seed, step=step_key, loss_sum=loss_slot, flags=self._flags(users_unique))
+
+    def train_batch_async(self, users_host, csr=None, step_key=0, users_unique=False):
+        """Pipelined form of `train_batch` for host-resident batches: `users_host` (pinned int32 CPU tensor) is
+        copied on a side stream into one of two device buffers while the previous step still computes; the
+        step's loss is copied back into pinned memory.  Returns a handle whose `.loss()` blocks until THAT step
+        has finished - read it one step late to keep copy, compute and read-back overlapped."""
+        st = getattr(self, "_pipe", None)
+        if st is None or st["cap"] < users_host.numel():
+            cap = int(users_host.numel())
+            st = self._pipe = dict(
+                cap=cap, n=0, copy=torch.cuda.Stream(device=self.device),
+                users=[torch.empty(cap, dtype=torch.int32, device=self.device) for _ in range(2)],
+                loss=[torch.zeros(1, dtype=torch.float64, device=self.device) for _ in range(2)],
+                host=[torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)],
+                h2d=[torch.cuda.Event() for _ in range(2)], done=[torch.cuda.Event() for _ in range(2)])
+        k = st["n"] & 1
+        st["n"] += 1
+        B = int(users_host.numel())
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st["copy"]):
+            st["copy"].wait_event(st["done"][k])                      # the step that last used this buffer is over
+            st["users"][k][:B].copy_(users_host, non_blocking=True)
+            st["h2d"][k].record(st["copy"])
+        main.wait_event(st["h2d"][k])
+        st["loss"][k].zero_()
+        self.train_batch(st["users"][k][:B], csr=csr, step_key=step_key, users_unique=users_unique,
+                         loss_slot=st["loss"][k])
+        st["host"][k].copy_(st["loss"][k], non_blocking=True)
+        st["done"][k].record(main)
+        return _StepHandle(st["done"][k], st["host"][k], B)
 
     def fit(self, dataset, exp_config, evaluator=None, early_stop=None, loggers=None):   # MF.py:44-97
         train_matrix = dataset.train_data

@@ -93,8 +93,8 @@ def test_cfg4_lightgcn_propagation_properties(dev, cfg2):
     m.E0.zero_(); m.E0[:, 0] = ev; m.E0[:, 1] = -2.0 * ev
     out = m.propagate(m.E0, m.out)
     live = deg > 0
-    np.testing.assert_allclose(out[live, 0].cpu().numpy(), ev[live].cpu().numpy(), rtol=2e-4)
-    np.testing.assert_allclose(out[live, 1].cpu().numpy(), (-2.0 * ev[live]).cpu().numpy(), rtol=2e-4)
+    np.testing.assert_allclose(out[live, 0].cpu().numpy(), ev[live].cpu().numpy(), rtol=1e-3)
+    np.testing.assert_allclose(out[live, 1].cpu().numpy(), (-2.0 * ev[live]).cpu().numpy(), rtol=1e-3)
     g = torch.Generator(device=dev); g.manual_seed(3)
     a = torch.zeros_like(m.E0); b = torch.zeros_like(m.E0)
     a[:, :64].normal_(generator=g); b[:, :64].normal_(generator=g)

@@ -27,6 +27,9 @@ for tag, std_v in (("random N(0,.1)", None), ("item norms lognormal x(0.3..3)", 
         V *= torch.exp(torch.randn(ni, 1, device=dev, generator=g) * std_v)
     for k in (10, 100):
         for mask in (None, train):
+            only = os.environ.get("ONLY")          # e.g. ONLY="item:10:yes"
+            if only and only != "%s:%d:%s" % (tag[:4], k, "yes" if mask is not None else "no"):
+                continue
             os.environ["B200REC_TC_STATS"] = "1"
             it, _ = engine.score_topk(U, V, d, users, mask, k, algo=_lib.SCORE_TC)
             os.environ.pop("B200REC_TC_STATS")
