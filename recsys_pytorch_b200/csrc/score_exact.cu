@@ -237,6 +237,19 @@ static int launch_exact(const float *U, const float *V, int ld, int d, const int
     const int tiles_per_split = (n_tiles + splits - 1) / splits;
     splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     uint64_t *part = nullptr;
+    {   // keep stream-ordered scratch cached across calls (the default pool trims to zero at every sync)
+        static thread_local int pool_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev != pool_dev) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = 1ull << 30;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_dev = dev;
+        }
+    }
     B200_CUDA(cudaMallocAsync(&part, (size_t)n_users * splits * k * sizeof(uint64_t), s));
     kern<<<dim3(grid, splits), 256, smem, s>>>(U, V, ld, d, users, n_users, num_items, mi, mx, k, nullptr, nullptr,
                                                nullptr, tiles_per_split * C::TN, part);

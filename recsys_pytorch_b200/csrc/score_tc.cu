@@ -41,7 +41,8 @@ int score_topk_exact(const float *U, const float *V, int ld, int d, const int32_
                      cudaStream_t s);
 
 constexpr int kBM = 256;        // user rows per CTA (two M=128 halves)
-constexpr int kBN = 128;        // items per tile
+constexpr int kBN = 128;        // items per tile (N=128 kernel, d > 128)
+constexpr int kPPN = 256;       // items per tile (N=256 ping-pong kernel, d <= 128)
 constexpr int kBK = 64;         // fp16 per k-block = one 128-byte swizzle row
 constexpr int kCand = 512;      // candidate slots per row
 constexpr int kEpiWarps = 8;
@@ -201,9 +202,9 @@ __global__ void iota_kernel(int32_t *out, int n) {
     if (i < n) out[i] = i;
 }
 // tile_norm[t] = largest item norm in tile t (= first entry, norms sorted descending)
-__global__ void tile_norm_kernel(const uint32_t *sorted_norm_bits, int num_items, int n_tiles, float *tile_norm) {
+__global__ void tile_norm_kernel(const uint32_t *sorted_norm_bits, int num_items, int n_tiles, int tile, float *tile_norm) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n_tiles) tile_norm[t] = (t * kBN < num_items) ? __uint_as_float(sorted_norm_bits[t * kBN]) : 0.f;
+    if (t < n_tiles) tile_norm[t] = (t * tile < num_items) ? __uint_as_float(sorted_norm_bits[t * tile]) : 0.f;
 }
 
 struct TcParams {
@@ -222,6 +223,7 @@ struct TcParams {
 
 // warp-cooperative threshold raise for the lanes in `need` (bit per lane); see file header.
 // Entries hold S~ (scaled); e = cu * tile_norm[pos/128]; L = S~ - e, H = S~ + e.
+template <int TILE, int WM>
 __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff, float cu,
                                                  const float *__restrict__ tile_norm, int *hist, int lane) {
     while (need) {
@@ -244,7 +246,7 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
             lo[i] = -INFINITY; hi[i] = -INFINITY;
             if (p < n) {
                 const float s = ord2f((uint32_t)(e[i] >> 32));
-                const float err = c_u * tile_norm[(uint32_t)(e[i] & 0x7FFFFFFFu) / kBN];
+                const float err = c_u * tile_norm[(uint32_t)(e[i] & 0x7FFFFFFFu) / TILE];
                 hi[i] = s + err;
                 if (!((uint32_t)e[i] >> 31)) {
                     lo[i] = s - err;
@@ -308,7 +310,7 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         if (lane == Lsrc) {
             // a raise that frees < 48 slots three times in a row is thrashing (sticky high-uncertainty entries)
             stalls = (n - total < 48) ? stalls + 1 : 0;
-            if (total > kCand - kBN - 32 || stalls >= 3) { cnt = -1; tau = INFINITY; }  // exact kernel re-does the row
+            if (total > kCand - WM - 32 || stalls >= 3) { cnt = -1; tau = INFINITY; }  // exact kernel re-does the row
             else { cnt = total; tau = t_new; }
         }
     }
@@ -476,7 +478,183 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
             const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kBN - 1);
-            if (need) raise_thresholds(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane);
+            if (need) raise_thresholds<kBN, kBN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane);
+        }
+        if (row_ok) p.cand_cnt[row] = cnt;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// N=256 ping-pong variant (d <= 128).  The N=128 kernel above reads A (4 KB) + B (4 KB) from shared memory
+// per 64-cycle MMA = 128 B/clk, the shared-memory limit, while TMA refills the ring: its tensor pipe is
+// active only 42 % (ncu run 5).  Here one M128 x N256 x K16 instruction reads 12 KB per 128 cycles
+// (96 B/clk).  TMEM holds ONE 256-column accumulator per M half; the MMA warp alternates halves, so while
+// the tensor core fills half 1 the four epilogue warps of half 0 drain theirs (and vice versa).  A tile's
+// k-blocks stay in the ring until both halves have consumed them.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kIdescPP = (1u << 4) | ((uint32_t)(kPPN >> 3) << 17) | ((128u >> 4) << 24);
+
+template <int KB, bool DUMP>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const TcParams p, const int n_stages) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem_raw = smem_dyn + ((1024u - (s32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char *smA = smem_raw;                                   // [KB][256 rows][128 B]
+    unsigned char *smB = smA + (size_t)KB * kBM * 128;               // ring [n_stages][256 items][128 B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smB + (size_t)n_stages * kPPN * 128);
+    uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *afull = bars + 20;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
+    int *hist_all = reinterpret_cast<int *>(bars + 22);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kBM;
+    const int n_tiles = p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; ++s) { mbar_init(s32(full + s), 1); mbar_init(s32(empty + s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(s32(tfull + a), 1); mbar_init(s32(tempty + a), kEpiWarps / 2); }
+        mbar_init(s32(afull), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---- TMA producer
+            mbar_expect_tx(s32(afull), (uint32_t)KB * kBM * 128);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(s32(smA + (size_t)kb * kBM * 128), &tmA, kb * kBK, row0, s32(afull));
+            uint32_t it = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+                    mbar_wait(s32(empty + s), ph ^ 1u);
+                    mbar_expect_tx(s32(full + s), kPPN * 128);
+                    tma_load_2d(s32(smB + (size_t)s * kPPN * 128), &tmB, kb * kBK, t * kPPN, s32(full + s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---- MMA issuer: half 0 then half 1 of every tile
+            mbar_wait(s32(afull), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t it0 = 0;
+            for (int t = 0; t < n_tiles; ++t, it0 += KB) {
+                const uint32_t tph = (uint32_t)t & 1u;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(s32(tempty + h), tph ^ 1u);   // the epilogue warps of this half drained tile t-1
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const uint32_t it = it0 + kb;
+                        const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
+                        if (h == 0) {
+                            mbar_wait(s32(full + s), ph);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+                        const uint64_t bdesc = smem_desc_sw128(s32(smB + (size_t)s * kPPN * 128));
+                        const uint64_t adesc = smem_desc_sw128(s32(smA + (size_t)kb * kBM * 128 + (size_t)h * 128 * 128));
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_f16(tmem_base + h * kPPN, adesc + 2 * k, bdesc + 2 * k, kIdescPP, (kb | k) ? 1u : 0u);
+                        if (h == 1) umma_commit(s32(empty + s));   // both halves have read this k-block
+                    }
+                    umma_commit(s32(tfull + h));
+                }
+            }
+        }
+    } else {
+        // ---- epilogue: thread == user row; warps 2-5 own half 0, warps 6-9 half 1
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int h = ew >> 2;
+        const int r_local = h * 128 + q * 32 + lane;
+        const int row = row0 + r_local;
+        const bool row_ok = row < p.n_rows;
+        int *hist = hist_all + ew * 32;
+        uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
+        const float *__restrict__ tile_norm = p.tile_norm;
+        const int num_items = p.num_items;
+        int cnt = 0, stalls = 0;
+        const int keff = p.k;
+        float tau = -INFINITY, cu = 0.f;
+        uint64_t f_lo = 0, f_hi = 0;
+        if (row_ok) {
+            if (p.mask_indptr) {
+                const int u = p.users[row];
+                const int64_t mb = p.mask_indptr[u], me = p.mask_indptr[u + 1];
+                for (int64_t m = mb; m < me; ++m) {
+                    const uint32_t hsh = ((uint32_t)p.inv_perm[p.mask_indices[m]] * 2654435761u) >> 25;
+                    if (hsh & 64u) f_hi |= 1ull << (hsh & 63u); else f_lo |= 1ull << (hsh & 63u);
+                }
+            }
+            const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;
+            cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);
+        } else {
+            tau = INFINITY;
+        }
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kPPN;
+        for (int t = 0; t < n_tiles; ++t) {
+            const float e_t = cu * tile_norm[t];
+            mbar_wait(s32(tfull + h), (uint32_t)t & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int n0 = t * kPPN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kPPN; c0 += 64) {
+                const float thr = tau - e_t;   // tau may have been raised by the previous chunk
+                float v[64];
+                tmem_ld64(lane_addr + c0, v);
+                if (c0 == kPPN - 64) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s32(tempty + h));
+                }
+                if (DUMP) {
+                    float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * kPPN) + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) dst[j] = v[j];
+                }
+                float gm[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float a = max3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
+                    const float b = max3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
+                    gm[g] = max3(a, b, fmaxf(v[8 * g + 6], v[8 * g + 7]));
+                }
+                const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
+                if (m >= thr && cnt >= 0) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (gm[g] >= thr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float s = v[8 * g + j];
+                                const uint32_t pos = (uint32_t)(n0 + c0 + 8 * g + j);
+                                if (s >= thr && pos < (uint32_t)num_items) {
+                                    const uint32_t hsh = (pos * 2654435761u) >> 25;
+                                    const uint32_t flag = (uint32_t)(((hsh & 64u) ? f_hi : f_lo) >> (hsh & 63u)) & 1u;
+                                    my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (flag << 31) | pos;
+                                    ++cnt;
+                                }
+                            }
+                        }
+                    }
+                }
+                const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - 64 - 1);
+                if (need) raise_thresholds<kPPN, 64>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane);
+            }
         }
         if (row_ok) p.cand_cnt[row] = cnt;
     }
@@ -498,7 +676,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t *rk = reinterpret_cast<uint64_t *>(smem_raw) + (size_t)wid * k;
-    float *us = reinterpret_cast<float *>(smem_raw + (size_t)8 * k * 8) + (size_t)wid * d;
+    float *us = reinterpret_cast<float *>(smem_raw + (size_t)8 * k * 8) + (size_t)wid * ((d + 3) & ~3);   // 16-byte aligned per warp
     for (int row = blockIdx.x * 8 + wid; row < n_rows; row += gridDim.x * 8) {
         const int n = cand_cnt[row];
         if (n < 0) {  // overflow / too many masked items: the exact kernel re-does this row
@@ -524,7 +702,16 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
                 if (ok) {
                     const float *pv = V + (int64_t)item * ld;
                     float acc = 0.f;
-                    for (int kk = 0; kk < d; ++kk) acc = fmaf(us[kk], pv[kk], acc);  // ascending k: the oracle's chain
+                    int kk = 0;
+                    if ((ld & 3) == 0) {  // 16-byte row pieces; the FMA chain stays in ascending k (the oracle's order)
+                        for (; kk + 4 <= d; kk += 4) {
+                            const float4 x = *reinterpret_cast<const float4 *>(us + kk);
+                            const float4 y = __ldg(reinterpret_cast<const float4 *>(pv + kk));
+                            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+                            acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+                        }
+                    }
+                    for (; kk < d; ++kk) acc = fmaf(us[kk], pv[kk], acc);
                     key = make_key(acc, item);
                 }
             }
@@ -594,7 +781,7 @@ static size_t sort_temp_bytes(int num_items) {
 }
 
 struct TcLayout {
-    int dpad, KB, rows_cap, items_pad, n_tiles;
+    int dpad, KB, rows_cap, items_pad, n_tiles, tile;
     size_t off_vh, off_uh, off_unorm, off_vnorm, off_vnorm_sorted, off_iota, off_perm, off_inv, off_tnorm, off_scalars, off_sort,
         sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, total;
 };
@@ -603,8 +790,9 @@ static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     L.dpad = (int)align_up(d, kBK);
     L.KB = L.dpad / kBK;
     L.rows_cap = n_users < kRowsPerLaunch ? (int)align_up(n_users > 0 ? n_users : 1, kBM) : kRowsPerLaunch;
-    L.items_pad = (int)align_up(num_items, kBN);
-    L.n_tiles = L.items_pad / kBN;
+    L.tile = (L.KB <= 2) ? kPPN : kBN;   // d <= 128: the N=256 ping-pong kernel; wider rows: the N=128 kernel
+    L.items_pad = (int)align_up(num_items, L.tile);
+    L.n_tiles = L.items_pad / L.tile;
     L.sort_bytes = sort_temp_bytes(num_items);
     size_t o = 0;
     auto take = [&](size_t bytes, size_t al) { size_t at = align_up(o, al); o = at + bytes; return at; };
@@ -648,6 +836,27 @@ static int launch_candidates(const CUtensorMap &ma, const CUtensorMap &mb, const
         kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
     } else {
         auto kern = tc_candidate_kernel<KB, false>;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
+    }
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+template <int KB>
+static int launch_candidates_pp(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &p, int n_blocks,
+                                cudaStream_t s) {
+    const size_t a_bytes = (size_t)KB * kBM * 128;
+    int stages = (int)((224 * 1024 - a_bytes - 4096) / (kPPN * 128));
+    if (stages > 8) stages = 8;
+    B200_REQUIRE(stages >= 2 * KB, B200REC_EUNSUPPORTED, "score_topk TC: ping-pong kernel needs 2 tiles of stages");
+    const size_t smem = 1024 + a_bytes + (size_t)stages * kPPN * 128 + 22 * 8 + kEpiWarps * 32 * 4 + 64;
+    if (p.dump) {
+        auto kern = tc_candidate_pp_kernel<KB, true>;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
+    } else {
+        auto kern = tc_candidate_pp_kernel<KB, false>;
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
     }
@@ -700,10 +909,10 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
     to_f16_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, perm, num_items, L.items_pad, L.dpad, scal + 0, vh,
                                            reinterpret_cast<float *>(scal + 2));
     B200_LAUNCH_CHECK();
-    tile_norm_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(vnorm_sorted, num_items, L.n_tiles, tnorm);
+    tile_norm_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(vnorm_sorted, num_items, L.n_tiles, L.tile, tnorm);
     B200_LAUNCH_CHECK();
     CUtensorMap mb;
-    int rc = make_map(&mb, vh, (uint64_t)L.items_pad, (uint64_t)L.dpad, kBN);
+    int rc = make_map(&mb, vh, (uint64_t)L.items_pad, (uint64_t)L.dpad, (uint32_t)L.tile);
     if (rc) return rc;
 
     for (int r0 = 0; r0 < n_users; r0 += L.rows_cap) {
@@ -724,15 +933,15 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         p.scale_v = reinterpret_cast<float *>(scal + 2); p.scale_u = reinterpret_cast<float *>(scal + 3);
         p.cand = cand; p.cand_cnt = cnt; p.dump = dump ? dump + (size_t)r0 * L.items_pad : nullptr;
         switch (L.KB) {
-            case 1: rc = launch_candidates<1>(ma, mb, p, nr_pad / kBM, s); break;
-            case 2: rc = launch_candidates<2>(ma, mb, p, nr_pad / kBM, s); break;
+            case 1: rc = launch_candidates_pp<1>(ma, mb, p, nr_pad / kBM, s); break;
+            case 2: rc = launch_candidates_pp<2>(ma, mb, p, nr_pad / kBM, s); break;
             case 3: rc = launch_candidates<3>(ma, mb, p, nr_pad / kBM, s); break;
             default: rc = launch_candidates<4>(ma, mb, p, nr_pad / kBM, s); break;
         }
         if (rc) return rc;
         if (!oi) continue;  // dump-only bring-up call
         B200_CUDA(cudaMemsetAsync(redo_n, 0, 4, s));
-        const size_t rsmem = (size_t)8 * k * 8 + (size_t)8 * d * 4;
+        const size_t rsmem = (size_t)8 * k * 8 + (size_t)8 * ((d + 3) & ~3) * 4;
         B200_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         int rgrid = (nr + 7) / 8;
         if (rgrid > sms * 8) rgrid = sms * 8;
