@@ -790,7 +790,10 @@ static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     L.dpad = (int)align_up(d, kBK);
     L.KB = L.dpad / kBK;
     L.rows_cap = n_users < kRowsPerLaunch ? (int)align_up(n_users > 0 ? n_users : 1, kBM) : kRowsPerLaunch;
-    L.tile = (L.KB <= 2) ? kPPN : kBN;   // d <= 128: the N=256 ping-pong kernel; wider rows: the N=128 kernel
+    // B200REC_TC_PP=1 selects the N=256 ping-pong kernel for d <= 128 (measured slower in-kernel than the N=128
+    // kernel, ncu run 11: 1.57 ms vs 1.14 ms - four epilogue warps per half cannot keep up); default: N=128
+    static const bool use_pp = getenv("B200REC_TC_PP") && atoi(getenv("B200REC_TC_PP")) != 0;
+    L.tile = (use_pp && L.KB <= 2) ? kPPN : kBN;
     L.items_pad = (int)align_up(num_items, L.tile);
     L.n_tiles = L.items_pad / L.tile;
     L.sort_bytes = sort_temp_bytes(num_items);
@@ -933,8 +936,10 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         p.scale_v = reinterpret_cast<float *>(scal + 2); p.scale_u = reinterpret_cast<float *>(scal + 3);
         p.cand = cand; p.cand_cnt = cnt; p.dump = dump ? dump + (size_t)r0 * L.items_pad : nullptr;
         switch (L.KB) {
-            case 1: rc = launch_candidates_pp<1>(ma, mb, p, nr_pad / kBM, s); break;
-            case 2: rc = launch_candidates_pp<2>(ma, mb, p, nr_pad / kBM, s); break;
+            case 1: rc = (L.tile == kPPN) ? launch_candidates_pp<1>(ma, mb, p, nr_pad / kBM, s)
+                                          : launch_candidates<1>(ma, mb, p, nr_pad / kBM, s); break;
+            case 2: rc = (L.tile == kPPN) ? launch_candidates_pp<2>(ma, mb, p, nr_pad / kBM, s)
+                                          : launch_candidates<2>(ma, mb, p, nr_pad / kBM, s); break;
             case 3: rc = launch_candidates<3>(ma, mb, p, nr_pad / kBM, s); break;
             default: rc = launch_candidates<4>(ma, mb, p, nr_pad / kBM, s); break;
         }
