@@ -146,6 +146,14 @@ int b200rec_adam_dense(float *param, const float *grad, float *exp_avg, float *e
                        int64_t n, float lr, float beta1, float beta2, float eps, int step,
                        void *stream);
 
+/* Row-wise (lazy) Adam = torch.optim.SparseAdam semantics: only the rows listed in
+ * ids[0..n) move.  `grad` holds the per-row gradient sums produced by b200rec_bpr_step(SINK_GRAD) and is zeroed
+ * again row by row; `stamp` (int32 per table row, zero-initialised once) de-duplicates ids within a step; ids < 0
+ * are skipped.  `step` is the optimiser's global step count (>= 1, bias correction as in SparseAdam). */
+int b200rec_adam_rows(float *W, float *grad, float *exp_avg, float *exp_avg_sq, int32_t *stamp, int ld,
+                      const int32_t *ids, int n, float lr, float beta1, float beta2, float eps, int step,
+                      void *stream);
+
 /* Scoring algorithms */
 #define B200REC_SCORE_EXACT 0 /* fp32 FMA chain in k order on CUDA cores (bit-exact vs oracle) */
 #define B200REC_SCORE_TC 1    /* tcgen05 bf16 candidate pass + exact fp32 re-rank               */

@@ -59,6 +59,7 @@ _PROTOS = {
     "b200rec_rows_add": (_I, [_P, _I, _P, _I, _P, _I, _F, _P]),
     "b200rec_sgd_dense": (_I, [_P, _P, _L, _F, _P]),
     "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
+    "b200rec_adam_rows": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _F, _F, _F, _F, _I, _P]),
     "b200rec_score_topk_workspace": (_L, [_I, _I, _I, _I, _I]),
     "b200rec_score_topk": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _P, _P, _L, _I, _P]),
     "b200rec_debug_tc_layout": (_I, [_I, _I, _I, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

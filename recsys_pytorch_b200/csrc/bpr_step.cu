@@ -868,3 +868,97 @@ extern "C" int b200rec_rows_add(float *W, int ld, const int32_t *ids, int n, con
     B200_LAUNCH_CHECK();
     return B200REC_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Row-wise (lazy) Adam - SURVEY section 8(f) rank 1.  torch.optim.SparseAdam semantics: only the rows present in the
+// batch move; for such a row (gradient g summed over its occurrences, all from pre-step weights):
+//   m = m + (1-b1)(g - m);  v = v + (1-b2)(g*g - v);  w -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)
+// The fused step first accumulates g into dense scratch rows (SINK_GRAD); this kernel then walks the batch ids,
+// lets exactly one occurrence of each row claim it (atomicExch on a per-row stamp holding the step number),
+// applies the update and zeroes the scratch row again (so the scratch never needs a dense memset).
+// ---------------------------------------------------------------------------
+namespace b200 {
+template <int G, int CPL>
+__global__ void __launch_bounds__(256) adam_rows_kernel(float *__restrict__ W, float *__restrict__ g,
+                                                        float *__restrict__ m, float *__restrict__ v,
+                                                        int32_t *__restrict__ stamp, int ld,
+                                                        const int32_t *__restrict__ ids, int n, float b1, float b2,
+                                                        float eps, float step_size, int step) {
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % G, sg = lane / G;
+    const int d4 = ld >> 2;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sg * G));
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t tb = warp_global * RPW; tb < n; tb += n_warps * RPW) {
+        const int64_t t = tb + sg;
+        int id = -1;
+        if (t < n) id = ids[t];
+        int mine = 0;
+        if (sl == 0 && id >= 0) mine = (atomicExch(stamp + id, step) != step);
+        mine = __shfl_sync(gmask, mine, sg * G);
+        if (!mine) continue;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const int q = sl + k * G;
+            if (q < d4) {
+                const int64_t off = (int64_t)id * ld + q * 4;
+                const float4 gg = ld4(g + off);
+                float4 mm = ld4(m + off), vv = ld4(v + off), ww = ld4(W + off);
+                mm.x += (1.f - b1) * (gg.x - mm.x); mm.y += (1.f - b1) * (gg.y - mm.y);
+                mm.z += (1.f - b1) * (gg.z - mm.z); mm.w += (1.f - b1) * (gg.w - mm.w);
+                vv.x += (1.f - b2) * (gg.x * gg.x - vv.x); vv.y += (1.f - b2) * (gg.y * gg.y - vv.y);
+                vv.z += (1.f - b2) * (gg.z * gg.z - vv.z); vv.w += (1.f - b2) * (gg.w * gg.w - vv.w);
+                ww.x -= step_size * (mm.x / (sqrtf(vv.x) + eps)); ww.y -= step_size * (mm.y / (sqrtf(vv.y) + eps));
+                ww.z -= step_size * (mm.z / (sqrtf(vv.z) + eps)); ww.w -= step_size * (mm.w / (sqrtf(vv.w) + eps));
+                st4(m + off, mm); st4(v + off, vv); st4(W + off, ww);
+                st4(g + off, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        }
+    }
+}
+
+template <int G, int CPL>
+static int launch_adam_rows(float *W, float *g, float *m, float *v, int32_t *stamp, int ld, const int32_t *ids, int n,
+                            float b1, float b2, float eps, float step_size, int step, cudaStream_t s) {
+    constexpr int RPW = 32 / G;
+    int64_t blocks = ((int64_t)n + 8 * RPW - 1) / (8 * RPW);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    adam_rows_kernel<G, CPL><<<(int)(blocks < cap ? blocks : cap), 256, 0, s>>>(W, g, m, v, stamp, ld, ids, n, b1, b2,
+                                                                                eps, step_size, step);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+}  // namespace b200
+
+extern "C" int b200rec_adam_rows(float *W, float *grad, float *exp_avg, float *exp_avg_sq, int32_t *stamp, int ld,
+                                 const int32_t *ids, int n, float lr, float beta1, float beta2, float eps, int step,
+                                 void *stream) {
+    B200_REQUIRE(W && grad && exp_avg && exp_avg_sq && stamp && ids, B200REC_EINVAL, "adam_rows: null argument");
+    B200_REQUIRE(ld > 0 && ld % 4 == 0 && ld <= 512 && step >= 1, B200REC_EINVAL, "adam_rows: bad ld/step");
+    if (n <= 0) return B200REC_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+    const int d4 = ld / 4;
+    int G = 1;
+    while (G < d4 && G < 32) G <<= 1;
+    const int CPL = (d4 + G - 1) / G;
+    cudaStream_t s = (cudaStream_t)stream;
+#define B200_AR(GG, CC) return launch_adam_rows<GG, CC>(W, grad, exp_avg, exp_avg_sq, stamp, ld, ids, n, beta1, beta2, eps, step_size, step, s)
+    switch (G) {
+        case 1: B200_AR(1, 1);
+        case 2: B200_AR(2, 1);
+        case 4: B200_AR(4, 1);
+        case 8: B200_AR(8, 1);
+        case 16: B200_AR(16, 1);
+        default:
+            switch (CPL) {
+                case 1: B200_AR(32, 1);
+                case 2: B200_AR(32, 2);
+                case 3: B200_AR(32, 3);
+                default: B200_AR(32, 4);
+            }
+    }
+#undef B200_AR
+}

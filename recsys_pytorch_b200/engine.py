@@ -131,6 +131,13 @@ def adam_dense(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, beta1=0.9, beta2
                                         current_stream()))
 
 
+def adam_rows(W, grad, exp_avg, exp_avg_sq, stamp, ids, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.SparseAdam on the rows ids[] (see b200rec_adam_rows); zeroes the used grad rows."""
+    check(_lib.lib().b200rec_adam_rows(ptr(W), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(_i32(stamp, "stamp")),
+                                       W.shape[1], ptr(_i32(ids, "ids")), ids.numel(), float(lr), float(beta1),
+                                       float(beta2), float(eps), int(step), current_stream()))
+
+
 def score_topk(U, V, d, users, mask: DeviceCSR | None, k, algo=SCORE_EXACT, want_scores=True):
     """models/MF.py:109-132 + func.h:12-31 fused: (idx int32 [n,k], score fp32 [n,k])."""
     require_cuda(U, "U", torch.float32); require_cuda(V, "V", torch.float32)

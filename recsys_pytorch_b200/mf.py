@@ -9,7 +9,8 @@ the path is a hand-written sm_100a kernel reached through the C ABI
 
 Extra hparams (all optional; defaults keep `conf/MF.yaml` working):
     optimizer   'sgd' (default: L2-regularised SGD, BASELINE north_star) |
-                'adam' (the reference's dense torch.optim.Adam(lr=1e-3), MF.py:30)
+                'adam' (the reference's dense torch.optim.Adam(lr=1e-3), MF.py:30) |
+                'lazy_adam' (row-wise Adam = torch.optim.SparseAdam semantics: only touched rows move)
     lr, reg     SGD step size / per-occurrence L2 (reference has neither: Q1)
     step        'fused' (ONE kernel per batch, Hogwild inside a step) |
                 'exact' (stage + apply: autograd's pre-step-weights semantics)
@@ -105,7 +106,7 @@ class MF(BaseModel):
             raise B200RecError(ECUDA, "recsys_pytorch_b200.MF needs a CUDA device: there is no CPU path")
 
         self.optimizer_name = str(_hp(hparams, "optimizer", "sgd")).lower()
-        self.lr = float(_hp(hparams, "lr", 1e-3 if self.optimizer_name == "adam" else 0.05))
+        self.lr = float(_hp(hparams, "lr", 1e-3 if "adam" in self.optimizer_name else 0.05))
         self.reg = float(_hp(hparams, "reg", 0.0))
         self.step_mode = str(_hp(hparams, "step", "fused")).lower()
         self.sampler = str(_hp(hparams, "sampler", "device")).lower()
@@ -181,6 +182,26 @@ class MF(BaseModel):
             t = self._adam[4]
             engine.adam_dense(self.U, gU, self._adam[0], self._adam[1], t, lr=self.lr)
             engine.adam_dense(self.V, gV, self._adam[2], self._adam[3], t, lr=self.lr)
+        elif self.optimizer_name in ("lazy_adam", "sparse_adam"):
+            # row-wise Adam (torch.optim.SparseAdam semantics): gradients into dense scratch rows,
+            # then one claimed update per touched row; the scratch is zeroed row by row, never memset
+            if getattr(self, "_lazy", None) is None:
+                gU, gV = self._grad_buffers()
+                gU.zero_(); gV.zero_()
+                self._lazy = dict(mU=torch.zeros_like(self.U), vU=torch.zeros_like(self.U), mV=torch.zeros_like(self.V),
+                                  vV=torch.zeros_like(self.V),
+                                  sU=torch.zeros(self.U.shape[0], dtype=torch.int32, device=self.device),
+                                  sV=torch.zeros(self.V.shape[0], dtype=torch.int32, device=self.device), t=0)
+            lz = self._lazy
+            gU, gV = self._grad_buffers()
+            if pos is None or neg is None:
+                pos, neg = engine.sample_triples(users, csr, self.seed, step_key)
+            engine.bpr_step(self.U, self.V, d, users, pos, neg, reg=self.reg, sink=SINK_GRAD, gU=gU, gV=gV,
+                            loss_sum=loss_slot, flags=self._flags(False))
+            lz["t"] += 1
+            engine.adam_rows(self.U, gU, lz["mU"], lz["vU"], lz["sU"], users, lz["t"], lr=self.lr)
+            engine.adam_rows(self.V, gV, lz["mV"], lz["vV"], lz["sV"], pos, lz["t"], lr=self.lr)
+            engine.adam_rows(self.V, gV, lz["mV"], lz["vV"], lz["sV"], neg, lz["t"], lr=self.lr)
         elif self.step_mode == "exact":
             if pos is None or neg is None:
                 pos, neg = engine.sample_triples(users, csr, self.seed, step_key)

@@ -204,3 +204,19 @@ def test_torch_port_reproduces_reference_adam(golden):
     np.testing.assert_allclose(m.user_embedding.weight.detach().numpy(), g["adam_U"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(m.item_embedding.weight.detach().numpy(), g["adam_V"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(losses, g["adam_loss"], rtol=1e-6)
+
+
+def test_oracle_sparse_adam(golden):
+    """Row-wise (lazy) Adam restatement vs the reference MF driven by torch.optim.SparseAdam (6 steps)."""
+    g, t = golden["tiny_bpr"], golden["tiny_lazy_adam"]
+    U, V = g["U0"].copy(), g["V0"].copy()
+    opt = O.SparseAdam([U.shape, V.shape])
+    s = 0
+    for rep in range(2):
+        for b in range(3):
+            u, i, j = g["users"][b], g["pos"][b], g["neg"][b]
+            dU, dV, _, _ = O.bpr_grads(U, V, u, i, j)
+            U, V = opt.step([U, V], [dU, dV], [u, np.concatenate([i, j])])
+            np.testing.assert_allclose(U, t["U"][s], rtol=1e-4, atol=2e-6)
+            np.testing.assert_allclose(V, t["V"][s], rtol=1e-4, atol=2e-6)
+            s += 1
