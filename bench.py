@@ -347,6 +347,8 @@ def main():
                     help="N>1: user_sharded (default; also measures the north_star item_sharded layout and reports it "
                          "under 'north_star_item_sharded') or item_sharded only")
     ap.add_argument("--no-secondary", dest="no_secondary", action="store_true")
+    ap.add_argument("--wire", default="fp32", choices=["fp32", "bf16"],
+                    help="N>1 user_sharded: dtype of the all-reduced item-delta buffer")
     ap.add_argument("--small", action="store_true", help="tiny shapes for a quick functional run (NOT a bench value)")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -86,6 +86,7 @@ int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int3
 #define B200REC_F_ITEM_DELTA 4   /* SINK_UPDATE: item-row deltas accumulate into dense gV (user-sharded layout) */
 #define B200REC_F_GENERIC 8      /* force the general kernel where the lean d=128/256 fast path would be taken */
 #define B200REC_F_ASYNC_GATHER 16 /* fast path with the deep cp.async (LDGSTS) per-warp row ring */
+#define B200REC_F_ITEM_DELTA_BF16 32 /* with F_ITEM_DELTA: gV is a bf16 [num_items, ld] buffer (REDG.ADD.BF16x4) */
 
 typedef struct b200rec_bpr_args {
     float *U;              /* [num_users, ld]  user_embedding.weight (models/MF.py:23)   */
@@ -138,6 +139,9 @@ int b200rec_bpr_apply(float *U, float *V, int ld, const int32_t *users, const in
  * rows of the item-sharded layout to every replica. */
 int b200rec_rows_add(float *W, int ld, const int32_t *ids, int n, const float *delta, int ld_delta,
                      float scale, void *stream);
+
+/* W[0..n) += float(delta_bf16[0..n)) - applies the all-reduced bf16 item-delta buffer (n % 4 == 0). */
+int b200rec_add_bf16(float *W, const void *delta_bf16, int64_t n, void *stream);
 
 /* dense SGD / Adam sweeps: torch.optim.SGD(lr) and torch.optim.Adam(lr, betas,
  * eps, weight_decay=0) as constructed at models/MF.py:30 - every element moves. */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libb200rec.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SINK_UPDATE, SINK_STAGE, SINK_GRAD, SINK_NONE = 0, 1, 2, 3
-F_USERS_UNIQUE, F_TMA_GATHER, F_ITEM_DELTA, F_GENERIC, F_ASYNC_GATHER = 1, 2, 4, 8, 16
+F_USERS_UNIQUE, F_TMA_GATHER, F_ITEM_DELTA, F_GENERIC, F_ASYNC_GATHER, F_ITEM_DELTA_BF16 = 1, 2, 4, 8, 16, 32
 GATHER_FLAGS = {"ldg": 0, "tma": F_TMA_GATHER, "async": F_ASYNC_GATHER, "generic": F_GENERIC}
 SCORE_EXACT, SCORE_TC = 0, 1
 
@@ -57,6 +57,7 @@ _PROTOS = {
     "b200rec_sample_triples": (_I, [_P, _I, _P, _P, _I, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "b200rec_bpr_apply": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _P]),
     "b200rec_rows_add": (_I, [_P, _I, _P, _I, _P, _I, _F, _P]),
+    "b200rec_add_bf16": (_I, [_P, _P, _L, _P]),
     "b200rec_sgd_dense": (_I, [_P, _P, _L, _F, _P]),
     "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
     "b200rec_adam_rows": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _F, _F, _F, _F, _I, _P]),

@@ -19,6 +19,7 @@
 //   TMA  : warp-private ring of shared-memory stages filled by cp.async.bulk
 //          (UBLKCP) row copies that complete on a warp-private mbarrier - no CTA
 //          level synchronisation at all; many rows in flight per warp.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -88,6 +89,14 @@ __device__ __forceinline__ void fetch_triple(const b200rec_bpr_args &a, int64_t 
     }
 }
 
+// four floats -> four bf16 (round to nearest), added atomically as two bf16x2 words (REDG.E.ADD.BF16x4)
+__device__ __forceinline__ void red4_bf16(__nv_bfloat16 *p, float4 v) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    asm volatile("red.relaxed.gpu.global.add.noftz.v2.bf16x2 [%0], {%1,%2};" ::"l"(p),
+                 "r"(*reinterpret_cast<const uint32_t *>(&lo)), "r"(*reinterpret_cast<const uint32_t *>(&hi))
+                 : "memory");
+}
+
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -117,9 +126,15 @@ __device__ __forceinline__ void sink_chunk(const b200rec_bpr_args &a, int64_t t,
             else red4(pu, du);
         }
         // user-sharded: item deltas accumulate in a dense exchange buffer instead of the replica
-        float *vdst = (a.flags & B200REC_F_ITEM_DELTA) ? a.gV : a.V;
-        red4(vdst + (int64_t)(ti - a.item_lo) * ld + q * 4, di);
-        red4(vdst + (int64_t)(tj - a.item_lo) * ld + q * 4, dj);
+        if (a.flags & B200REC_F_ITEM_DELTA_BF16) {   // ... held in bf16: half the L2 footprint and half the wire bytes
+            __nv_bfloat16 *vb = reinterpret_cast<__nv_bfloat16 *>(a.gV);
+            red4_bf16(vb + (int64_t)ti * ld + q * 4, di);
+            red4_bf16(vb + (int64_t)tj * ld + q * 4, dj);
+        } else {
+            float *vdst = (a.flags & B200REC_F_ITEM_DELTA) ? a.gV : a.V;
+            red4(vdst + (int64_t)(ti - a.item_lo) * ld + q * 4, di);
+            red4(vdst + (int64_t)(tj - a.item_lo) * ld + q * 4, dj);
+        }
     } else if (SINK == B200REC_SINK_STAGE) {
         float *s = a.stage + (t * 3) * ld + q * 4;
         st4(s, du); st4(s + ld, di); st4(s + 2 * ld, dj);
@@ -706,6 +721,8 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
     B200_REQUIRE(a.sink != B200REC_SINK_STAGE || a.stage, B200REC_EINVAL, "bpr_step: SINK_STAGE needs stage");
     B200_REQUIRE(a.sink != B200REC_SINK_GRAD || (a.gU && a.gV), B200REC_EINVAL, "bpr_step: SINK_GRAD needs gU,gV");
     B200_REQUIRE(!(a.flags & B200REC_F_ITEM_DELTA) || a.gV, B200REC_EINVAL, "bpr_step: F_ITEM_DELTA needs gV");
+    B200_REQUIRE(!(a.flags & B200REC_F_ITEM_DELTA_BF16) || ((a.flags & B200REC_F_ITEM_DELTA) && a.sink == B200REC_SINK_UPDATE),
+                 B200REC_EINVAL, "bpr_step: F_ITEM_DELTA_BF16 refines F_ITEM_DELTA (SINK_UPDATE)");
     B200_REQUIRE(a.item_hi >= a.item_lo && a.item_lo >= 0, B200REC_EINVAL, "bpr_step: bad item shard range");
     B200_REQUIRE(a.item_hi == a.item_lo || (a.pos == nullptr && a.neg == nullptr) || a.item_lo == 0, B200REC_EINVAL,
                  "bpr_step: item-sharded mode samples its own triples (pos/neg must be NULL)");
@@ -961,4 +978,31 @@ extern "C" int b200rec_adam_rows(float *W, float *grad, float *exp_avg, float *e
             }
     }
 #undef B200_AR
+}
+
+// V += float(dV) for the bf16 item-delta exchange buffer of the user-sharded layout
+namespace b200 {
+__global__ void __launch_bounds__(256) add_bf16_kernel(float *__restrict__ W, const __nv_bfloat16 *__restrict__ delta,
+                                                       int64_t n4) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 raw = *reinterpret_cast<const uint2 *>(delta + e * 4);
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162 *>(&raw.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162 *>(&raw.y);
+        float4 w = ld4(W + e * 4);
+        w.x += __low2float(lo); w.y += __high2float(lo); w.z += __low2float(hi); w.w += __high2float(hi);
+        st4(W + e * 4, w);
+    }
+}
+}  // namespace b200
+
+extern "C" int b200rec_add_bf16(float *W, const void *delta_bf16, int64_t n, void *stream) {
+    B200_REQUIRE(W && delta_bf16 && n % 4 == 0, B200REC_EINVAL, "add_bf16: null argument or n %% 4 != 0");
+    if (n <= 0) return B200REC_OK;
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    add_bf16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        W, reinterpret_cast<const __nv_bfloat16 *>(delta_bf16), n4);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
 }

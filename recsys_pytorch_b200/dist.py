@@ -34,7 +34,7 @@ import torch
 import torch.distributed as dist
 
 from . import engine
-from ._lib import F_ITEM_DELTA, F_TMA_GATHER, F_USERS_UNIQUE, SINK_UPDATE
+from ._lib import F_ITEM_DELTA, F_ITEM_DELTA_BF16, F_TMA_GATHER, F_USERS_UNIQUE, SINK_UPDATE
 
 
 def shard_range(n: int, world: int, rank: int):
@@ -98,8 +98,12 @@ class UserShardedBPR:
     """transpose layout.  `train_local` holds the CSR rows of this rank's users (local row ids)."""
 
     def __init__(self, num_users, num_items, d, train_local, rank, world, device, lr=0.05, reg=0.0, init_std=0.01,
-                 seed=2020, gather="ldg"):
+                 seed=2020, gather="ldg", wire_dtype="fp32"):
+        """wire_dtype='bf16': the item-delta buffer (what crosses NVLink and what the kernel's vector atomics hit in
+        L2) is bf16 - half the bytes; each atomic add rounds to 8 mantissa bits, so the per-step item update carries
+        ~1e-2 relative noise (SGD-level).  'fp32' (default) is exact and is what the equivalence tests use."""
         self.num_users, self.num_items, self.d = num_users, num_items, d
+        self.wire_bf16 = str(wire_dtype).lower() == "bf16"
         self.rank, self.world, self.device = rank, world, device
         self.lr, self.reg, self.seed = lr, reg, seed
         self.train = train_local
@@ -108,8 +112,8 @@ class UserShardedBPR:
         self.U = engine.alloc_table(self.hi - self.lo, d, device, init_std, gu)   # rows [lo, hi)
         g = torch.Generator(device=device); g.manual_seed(seed)
         self.V = engine.alloc_table(num_items, d, device, init_std, g)            # identical replica on every rank
-        self.dV = torch.zeros_like(self.V)
-        self.flags = (F_TMA_GATHER if gather == "tma" else 0) | F_ITEM_DELTA
+        self.dV = torch.zeros_like(self.V, dtype=torch.bfloat16 if self.wire_bf16 else torch.float32)
+        self.flags = (F_TMA_GATHER if gather == "tma" else 0) | F_ITEM_DELTA | (F_ITEM_DELTA_BF16 if self.wire_bf16 else 0)
 
     def local_compute(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True, out_pos=None,
                       out_neg=None):
@@ -123,7 +127,10 @@ class UserShardedBPR:
         return self.dV
 
     def apply_item_delta(self, dV):
-        engine.sgd_dense(self.V, dV, -1.0)                                         # V += dV on every replica
+        if self.wire_bf16:
+            engine.add_bf16(self.V, dV)
+        else:
+            engine.sgd_dense(self.V, dV, -1.0)                                     # V += dV on every replica
 
     def step(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True, out_pos=None, out_neg=None):
         """users_local: int32 [B_local] local row ids of this rank's batch."""
@@ -203,7 +210,7 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_g
         ulo, uhi = shard_range(nu, world, rank)
         train, _ = synthetic.make_interactions(uhi - ulo, ni, seed=c["seed"] + rank, device=dev)
         tr = UserShardedBPR(nu, ni, d, train, rank, world, dev, lr=c["lr"], reg=c["reg"], init_std=c["init_std"],
-                            seed=c["seed"], gather=args.gather)
+                            seed=c["seed"], gather=args.gather, wire_dtype=getattr(args, "wire", "fp32"))
         g = torch.Generator(device=dev); g.manual_seed(c["seed"] + rank)
         perms = [torch.randperm(uhi - ulo, device=dev, generator=g)[:B_local].to(torch.int32).contiguous() for _ in range(2)]
         B_glob = B_local * world
@@ -215,8 +222,9 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_g
                 tr.step(perms[s % 2], s + 1, B_glob, loss_sum=loss)
             else:
                 tr.step_overlapped(perms[s % 2], s + 1, B_glob, loss_sum=loss)
-        coll = ("all_reduce(sum) of the dense [I, ld] fp32 item-delta buffer (%d MiB) per step, on a side stream, "
-                "overlapped with the next step's kernel (item rows one step stale)" % (ni * 4 * tr.V.shape[1] >> 20))
+        coll = ("all_reduce(sum) of the dense [I, ld] %s item-delta buffer (%d MiB) per step, on a side stream, "
+                "overlapped with the next step's kernel (item rows one step stale)"
+                % ("bf16" if tr.wire_bf16 else "fp32", tr.dV.numel() * tr.dV.element_size() >> 20))
 
     for s in range(args.warmup):
         step(s)

@@ -90,7 +90,7 @@ def bpr_step(U, V, d, users, pos=None, neg=None, csr: DeviceCSR | None = None, l
     a.lr, a.reg, a.sink, a.flags = float(lr), float(reg), int(sink), int(flags)
     a.stage = ptr(require_cuda(stage, "stage", torch.float32)) if stage is not None else None
     a.gU = ptr(require_cuda(gU, "gU", torch.float32)) if gU is not None else None
-    a.gV = ptr(require_cuda(gV, "gV", torch.float32)) if gV is not None else None
+    a.gV = ptr(require_cuda(gV, "gV")) if gV is not None else None        # fp32, or bf16 with F_ITEM_DELTA_BF16
     a.loss_sum = ptr(require_cuda(loss_sum, "loss_sum", torch.float64)) if loss_sum is not None else None
     a.x_out = ptr(require_cuda(x_out, "x_out", torch.float32)) if x_out is not None else None
     if item_range is not None:
@@ -119,6 +119,11 @@ def sample_triples(users, csr: DeviceCSR, seed, step):
                                             csr.shape[1], int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
                                             ptr(pos), ptr(neg), current_stream()))
     return pos, neg
+
+
+def add_bf16(param, delta_bf16):
+    """param += float(delta) for a torch.bfloat16 delta of the same shape (user-sharded exchange buffer)."""
+    check(_lib.lib().b200rec_add_bf16(ptr(param), ptr(delta_bf16), param.numel(), current_stream()))
 
 
 def sgd_dense(param, grad, lr):

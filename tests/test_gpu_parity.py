@@ -456,3 +456,33 @@ def test_plugin_fit_lazy_adam_learns(golden, dev):
     exp = types.SimpleNamespace(num_epochs=60, batch_size=256, verbose=0, test_from=60, test_step=60)
     ret = m.fit(ds, exp, evaluator=ev)
     assert float(ret["scores"]["NDCG@10"]) > 0.12      # CPU-oracle simulation of this recipe: 0.200
+
+
+@pytest.mark.parametrize("d", [128, 50])
+def test_item_delta_bf16_sink_and_apply(dev, d):
+    """F_ITEM_DELTA_BF16: the item deltas land in a bf16 [I, ld] buffer (REDG.ADD.BF16x4); with no item shared between
+    triples every element is ONE rounding of the fp32 delta (rel 2^-9), and b200rec_add_bf16 applies it exactly."""
+    from recsys_pytorch_b200._lib import F_ITEM_DELTA, F_ITEM_DELTA_BF16
+    rng = np.random.default_rng(5)
+    nu, ni, B = 2048, 4096, 1024
+    U0 = (rng.standard_normal((nu, d)) * 0.3).astype(np.float32)
+    V0 = (rng.standard_normal((ni, d)) * 0.3).astype(np.float32)
+    u = rng.permutation(nu)[:B]
+    items = rng.permutation(ni)[:2 * B]
+    i, j = items[:B], items[B:]
+    tu, ti, tj = _ids(dev, u, i, j)
+    out = {}
+    for tag, fl, dt in (("f32", F_ITEM_DELTA, torch.float32), ("bf16", F_ITEM_DELTA | F_ITEM_DELTA_BF16, torch.bfloat16)):
+        U, V = _dev_table(U0, dev), _dev_table(V0, dev)
+        dV = torch.zeros(V.shape, dtype=dt, device=dev)
+        engine.bpr_step(U, V, d, tu, ti, tj, lr=0.9, reg=0.01, sink=SINK_UPDATE, flags=fl | F_USERS_UNIQUE, gV=dV)
+        assert torch.equal(V.cpu(), _dev_table(V0, dev).cpu())            # item table untouched, delta is separate
+        out[tag] = (U.cpu().numpy(), dV.float().cpu().numpy(), V, dV)
+    np.testing.assert_array_equal(out["f32"][0], out["bf16"][0])          # user rows do not depend on the wire dtype
+    ref, got = out["f32"][1], out["bf16"][1]
+    assert np.all(np.abs(got - ref) <= np.abs(ref) * 2.0 ** -8 + 1e-30)
+    _, _, V, dV = out["bf16"]
+    engine.add_bf16(V, dV)
+    np.testing.assert_array_equal(V.cpu().numpy(), _dev_table(V0, dev).cpu().numpy() + got)
+    with pytest.raises(_lib.B200RecError):                                 # refines F_ITEM_DELTA only
+        engine.bpr_step(U, V, d, tu, ti, tj, lr=0.1, sink=SINK_UPDATE, flags=F_ITEM_DELTA_BF16, gV=dV)
