@@ -207,25 +207,54 @@ __global__ void tile_norm_kernel(const uint32_t *sorted_norm_bits, int num_items
     if (t < n_tiles) tile_norm[t] = (t * tile < num_items) ? __uint_as_float(sorted_norm_bits[t * tile]) : 0.f;
 }
 
+// 128-bit "maybe masked" filter per scored row: one bit per hashed sorted position of a train positive (no false
+// negatives).  One warp per row, coalesced over the row's positives.
+__global__ void __launch_bounds__(256) bloom_kernel(const int32_t *__restrict__ users, int n_rows,
+                                                    const int64_t *__restrict__ mask_indptr,
+                                                    const int32_t *__restrict__ mask_indices,
+                                                    const int32_t *__restrict__ inv_perm, uint4 *__restrict__ bloom) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= n_rows) return;
+    const int u = users[row];
+    const int64_t mb = mask_indptr[u], me = mask_indptr[u + 1];
+    unsigned w[4] = {0u, 0u, 0u, 0u};
+    for (int64_t m = mb + lane; m < me; m += 32) {
+        const uint32_t hsh = ((uint32_t)inv_perm[mask_indices[m]] * 2654435761u) >> 25;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] |= ((hsh >> 5) == (uint32_t)q) ? (1u << (hsh & 31u)) : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = __reduce_or_sync(0xffffffffu, w[q]);
+    if (lane == 0) bloom[row] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 struct TcParams {
     int n_rows, num_items, n_tiles, k, d;
     const int32_t *users;            // row -> user id (mask row)
     const int64_t *mask_indptr;      // may be NULL
     const int32_t *mask_indices;
     const int32_t *inv_perm;         // item id -> sorted position
+    const uint4 *bloom;              // [n_rows] 128-bit "maybe masked" filter per row (NULL without a mask)
+    int append_budget;               // a row that appends more than this is handed to the exact kernel
     const float *row_norm;           // [n_rows]
     const float *tile_norm;          // [n_tiles]
     const float *scale_u, *scale_v;  // device scalars (powers of two)
     uint64_t *cand;                  // [n_rows, kCand]  (ordered approx score << 32 | sorted item position)
     int32_t *cand_cnt;               // [n_rows]  (-1 = overflow: re-do with the exact kernel)
     float *dump;                     // bring-up: dense [n_rows_pad, n_tiles*kBN] approx scores (sorted order), else NULL
+    int ablate;                      // diagnostics (B200REC_TC_ABLATE): 1 no appends, 2 no filter, 4 no TMEM loads, 8 no TMA
+    float *dbg_row;                  // diagnostics: per row [appends, final count, tau, cu]; or NULL
+    unsigned long long *dbg_warp;    // diagnostics: per (block, epilogue warp) [total, wait, raise cycles, raises]; or NULL
+    unsigned long long *dbg;         // diagnostics: [0] appends, [1] raises, [2] warp-chunks with a hit, [3] warp-chunks; or NULL
 };
 
 // warp-cooperative threshold raise for the lanes in `need` (bit per lane); see file header.
 // Entries hold S~ (scaled); e = cu * tile_norm[pos/128]; L = S~ - e, H = S~ + e.
-template <int TILE, int WM>
+template <int TILE, int WM, bool LAZY_FLAG = false>
 __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff, float cu,
-                                                 const float *__restrict__ tile_norm, int *hist, int lane) {
+                                                 const float *__restrict__ tile_norm, int *hist, int lane, uint64_t f_lo = 0,
+                                                 uint64_t f_hi = 0) {
     while (need) {
         const int Lsrc = __ffs(need) - 1;
         need &= need - 1;
@@ -234,6 +263,11 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         const int kf = __shfl_sync(0xffffffffu, keff, Lsrc);
         const float c_u = __shfl_sync(0xffffffffu, cu, Lsrc);
         const float old_tau = __shfl_sync(0xffffffffu, tau, Lsrc);
+        uint64_t flo = 0, fhi = 0;
+        if (LAZY_FLAG) {   // appends left the "maybe masked" bit clear: fill it in on first sight
+            flo = __shfl_sync(0xffffffffu, (unsigned long long)f_lo, Lsrc);
+            fhi = __shfl_sync(0xffffffffu, (unsigned long long)f_hi, Lsrc);
+        }
         // lo[] = lower bound of the CLEAN entries only (bit 31 of the position = "maybe masked": such an
         // entry never counts towards the K items that justify tau); hi[] = upper bound of every entry
         uint64_t e[kCand / 32];
@@ -244,6 +278,10 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
             const int p = lane + 32 * i;
             e[i] = (p < n) ? base[p] : 0ull;
             lo[i] = -INFINITY; hi[i] = -INFINITY;
+            if (LAZY_FLAG && p < n) {
+                const uint32_t hsh = (((uint32_t)e[i] & 0x7FFFFFFFu) * 2654435761u) >> 25;
+                e[i] |= (uint64_t)((uint32_t)(((hsh & 64u) ? fhi : flo) >> (hsh & 63u)) & 1u) << 31;
+            }
             if (p < n) {
                 const float s = ord2f((uint32_t)(e[i] >> 32));
                 const float err = c_u * tile_norm[(uint32_t)(e[i] & 0x7FFFFFFFu) / TILE];
@@ -316,6 +354,111 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
     }
 }
 
+// asynchronous 64-column load (no wait) and the wait that also pins the destination registers: the
+// "+r" operands make every later use of r[] depend on the wait, and keep r[] allocated in between
+__device__ __forceinline__ void tmem_ld64_async(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,"
+        "%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait64(uint32_t (&r)[64]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+    asm volatile(""
+                 : "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]), "+r"(r[37]), "+r"(r[38]), "+r"(r[39]),
+                   "+r"(r[40]), "+r"(r[41]), "+r"(r[42]), "+r"(r[43]), "+r"(r[44]), "+r"(r[45]), "+r"(r[46]), "+r"(r[47]),
+                   "+r"(r[48]), "+r"(r[49]), "+r"(r[50]), "+r"(r[51]), "+r"(r[52]), "+r"(r[53]), "+r"(r[54]), "+r"(r[55]),
+                   "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]), "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])
+                 :
+                 : "memory");
+}
+
+// Cheap threshold raise for K <= 32 (one row at a time, warp-cooperative).  Any tau with at least K clean
+// entries at or above it is a valid lower bound of the exact K-th score, so instead of an exact selection the
+// warp takes the K-th largest of the 32 per-lane maxima of L = S~ - e (K distinct entries by construction;
+// for n >> 32 it is close to the exact K-th largest).  Entries whose upper bound still reaches the new tau are
+// compacted in place.
+template <int TILE, int WM>
+__device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff,
+                                           float cu, const float *__restrict__ tile_norm, int lane, uint64_t f_lo,
+                                           uint64_t f_hi) {
+    constexpr int E = kCand / 32;
+    while (need) {
+        const int Lsrc = __ffs(need) - 1;
+        need &= need - 1;
+        __syncwarp();
+        uint64_t *base = reinterpret_cast<uint64_t *>(__shfl_sync(0xffffffffu, (unsigned long long)my_cand, Lsrc));
+        const int n = __shfl_sync(0xffffffffu, cnt, Lsrc);
+        const int kf = __shfl_sync(0xffffffffu, keff, Lsrc);
+        const float c_u = __shfl_sync(0xffffffffu, cu, Lsrc);
+        const float old_tau = __shfl_sync(0xffffffffu, tau, Lsrc);
+        const uint64_t flo = __shfl_sync(0xffffffffu, (unsigned long long)f_lo, Lsrc);
+        const uint64_t fhi = __shfl_sync(0xffffffffu, (unsigned long long)f_hi, Lsrc);
+        uint64_t e[E];
+        float hi[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) e[i] = (lane + 32 * i < n) ? base[lane + 32 * i] : 0ull;   // one round trip
+        float lmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            hi[i] = -INFINITY;
+            if (lane + 32 * i < n) {
+                const float sc = ord2f((uint32_t)(e[i] >> 32));
+                const float err = c_u * tile_norm[(uint32_t)(e[i] & 0x7FFFFFFFu) / TILE];
+                hi[i] = sc + err;
+                // "maybe masked" bit, computed on first sight (appends leave it clear) and kept in the entry
+                const uint32_t hsh = (((uint32_t)e[i] & 0x7FFFFFFFu) * 2654435761u) >> 25;
+                const uint32_t flag = (uint32_t)(((hsh & 64u) ? fhi : flo) >> (hsh & 63u)) & 1u;
+                e[i] |= (uint64_t)flag << 31;
+                if (!((uint32_t)e[i] >> 31)) lmax = fmaxf(lmax, sc - err);
+            }
+        }
+        int rank = 0;   // lanes ordered by (lmax desc, lane asc): a permutation of 0..31
+#pragma unroll
+        for (int o = 1; o < 32; ++o) {
+            const int ol = (lane + o) & 31;
+            const float other = __shfl_sync(0xffffffffu, lmax, ol);
+            rank += (other > lmax || (other == lmax && ol < lane)) ? 1 : 0;
+        }
+        const unsigned sel = __ballot_sync(0xffffffffu, rank == kf - 1);
+        float t_new = __shfl_sync(0xffffffffu, lmax, __ffs(sel) - 1);
+        t_new = (t_new > -INFINITY) ? fmaxf(old_tau, t_new) : old_tau;   // fewer than K lanes hold a clean entry
+        // every ballot depends on every lane's loads, so all loads have landed before the first store below
+        unsigned kb[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) kb[i] = __ballot_sync(0xffffffffu, hi[i] >= t_new);
+        int total = 0;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            if ((kb[i] >> lane) & 1u) base[total + __popc(kb[i] & ((1u << lane) - 1u))] = e[i];
+            total += __popc(kb[i]);
+        }
+        __syncwarp();
+        if (lane == Lsrc) {
+            stalls = (n - total < 48) ? stalls + 1 : 0;
+            if (total > kCand - WM - 32 || stalls >= 3) { cnt = -1; tau = INFINITY; }
+            else { cnt = total; tau = t_new; }
+        }
+    }
+}
+
 template <int KB, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -362,6 +505,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
                     mbar_wait(s32(empty + s), ph ^ 1u);
+                    if ((p.ablate & 8) && it >= (uint32_t)n_stages) { mbar_arrive(s32(full + s)); continue; }
                     mbar_expect_tx(s32(full + s), kBN * 128);
                     tma_load_2d(s32(smB + (size_t)s * kBN * 128), &tmB, kb * kBK, t * kBN, s32(full + s));
                 }
@@ -414,13 +558,10 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // (no false negatives).  Flagged candidates are kept but never counted towards the K items behind tau.
         uint64_t f_lo = 0, f_hi = 0;
         if (row_ok) {
-            if (p.mask_indptr) {
-                const int u = p.users[row];
-                const int64_t mb = p.mask_indptr[u], me = p.mask_indptr[u + 1];
-                for (int64_t m = mb; m < me; ++m) {
-                    const uint32_t hsh = ((uint32_t)p.inv_perm[p.mask_indices[m]] * 2654435761u) >> 25;
-                    if (hsh & 64u) f_hi |= 1ull << (hsh & 63u); else f_lo |= 1ull << (hsh & 63u);
-                }
+            if (p.bloom) {
+                const uint4 bw = p.bloom[row];
+                f_lo = (uint64_t)bw.x | ((uint64_t)bw.y << 32);
+                f_hi = (uint64_t)bw.z | ((uint64_t)bw.w << 32);
             }
             const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;   // 2^-10 (+5%) + fp32 accumulation slack
             cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);         // error bound per unit item norm, scaled domain
@@ -428,11 +569,23 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tau = INFINITY;
         }
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kBN;
+        const int abl = p.ablate;
+        unsigned long long d_app = 0, d_raise = 0, d_hit = 0, d_chunks = 0;
+        long long d_wait = 0, d_rcyc = 0, d_acyc = 0;
+        const long long c_start = clock64();
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t as = t & 1, aph = (t >> 1) & 1u;
             const float thr = tau - cu * tile_norm[t];   // keep S~ with S~ + e_t >= tau
+            const long long c_w0 = p.dbg ? clock64() : 0;
             mbar_wait(s32(tfull + as), aph);
+            if (p.dbg) d_wait += clock64() - c_w0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (abl & 4) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s32(tempty + as));
+                continue;
+            }
             const int n0 = t * kBN;
 #pragma unroll 1
             for (int c0 = 0; c0 < kBN; c0 += 64) {
@@ -450,6 +603,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 64; ++j) dst[j] = v[j];
                 }
+                if (abl & 2) continue;
                 float gm[8];
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
@@ -458,7 +612,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     gm[g] = max3(a, b, fmaxf(v[8 * g + 6], v[8 * g + 7]));
                 }
                 const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
-                if (m >= thr && cnt >= 0) {
+                if (m >= thr && cnt >= 0 && !(abl & 1)) {
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         if (gm[g] >= thr) {
@@ -471,6 +625,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     const uint32_t flag = (uint32_t)(((hsh & 64u) ? f_hi : f_lo) >> (hsh & 63u)) & 1u;
                                     my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (flag << 31) | pos;
                                     ++cnt;
+                                    ++d_app;
                                 }
                             }
                         }
@@ -478,9 +633,32 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
             const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kBN - 1);
-            if (need) raise_thresholds<kBN, kBN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane);
+            if (need) {
+                d_raise += __popc(need);
+                const long long c_r0 = p.dbg ? clock64() : 0;
+                raise_thresholds<kBN, kBN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane);
+                if (p.dbg) d_rcyc += clock64() - c_r0;
+            }
         }
         if (row_ok) p.cand_cnt[row] = cnt;
+        if (p.dbg) {
+            atomicAdd(p.dbg + 0, d_app);
+            if (lane == 0) {
+                atomicAdd(p.dbg + 1, d_raise); atomicAdd(p.dbg + 2, d_hit); atomicAdd(p.dbg + 3, d_chunks);
+                atomicAdd(p.dbg + 4, (unsigned long long)d_wait); atomicAdd(p.dbg + 5, (unsigned long long)d_rcyc);
+                atomicAdd(p.dbg + 6, (unsigned long long)d_acyc);
+                atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - c_start));
+                if (p.dbg_warp) {
+                    unsigned long long *w = p.dbg_warp + ((size_t)blockIdx.x * kEpiWarps + ew) * 4;
+                    w[0] = (unsigned long long)(clock64() - c_start); w[1] = (unsigned long long)d_wait;
+                    w[2] = (unsigned long long)d_rcyc; w[3] = d_raise;
+                }
+                atomicMax(p.dbg + 8, (unsigned long long)(clock64() - c_start));
+                atomicMax(p.dbg + 9, (unsigned long long)d_rcyc);
+                atomicMax(p.dbg + 10, (unsigned long long)d_wait);
+                atomicMax(p.dbg + 11, (unsigned long long)d_raise);
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -498,7 +676,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t kIdescPP = (1u << 4) | ((uint32_t)(kPPN >> 3) << 17) | ((128u >> 4) << 24);
 
-template <int KB, bool DUMP>
+template <int KB, bool DUMP, bool DIAG>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const TcParams p, const int n_stages) {
@@ -541,6 +719,7 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
                     mbar_wait(s32(empty + s), ph ^ 1u);
+                    if (DIAG && (p.ablate & 8) && it >= (uint32_t)n_stages) { mbar_arrive(s32(full + s)); continue; }
                     mbar_expect_tx(s32(full + s), kPPN * 128);
                     tma_load_2d(s32(smB + (size_t)s * kPPN * 128), &tmB, kb * kBK, t * kPPN, s32(full + s));
                 }
@@ -576,7 +755,11 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else {
-        // ---- epilogue: thread == user row; warps 2-5 own half 0, warps 6-9 half 1
+        // ---- epilogue: thread == user row; warps 2-5 own half 0, warps 6-9 half 1.
+        // TMEM loads are software-pipelined (two 64-column register buffers): the load of chunk c+1 is in
+        // flight while chunk c is filtered, and the accumulator is handed back to the MMA warp as soon as the
+        // last load has landed - the filtering of the last chunk and any threshold raise run while the tensor
+        // core already works on this half's next tile.
         const int ew = warp - 2;
         const int q = warp & 3;
         const int h = ew >> 2;
@@ -586,19 +769,17 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int *hist = hist_all + ew * 32;
         uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
         const float *__restrict__ tile_norm = p.tile_norm;
-        const int num_items = p.num_items;
-        int cnt = 0, stalls = 0;
+        const uint32_t num_items = (uint32_t)p.num_items;
+        int cnt = 0, stalls = 0, napp = 0;
         const int keff = p.k;
+        const int budget = p.append_budget;
         float tau = -INFINITY, cu = 0.f;
         uint64_t f_lo = 0, f_hi = 0;
         if (row_ok) {
-            if (p.mask_indptr) {
-                const int u = p.users[row];
-                const int64_t mb = p.mask_indptr[u], me = p.mask_indptr[u + 1];
-                for (int64_t m = mb; m < me; ++m) {
-                    const uint32_t hsh = ((uint32_t)p.inv_perm[p.mask_indices[m]] * 2654435761u) >> 25;
-                    if (hsh & 64u) f_hi |= 1ull << (hsh & 63u); else f_lo |= 1ull << (hsh & 63u);
-                }
+            if (p.bloom) {
+                const uint4 bw = p.bloom[row];
+                f_lo = (uint64_t)bw.x | ((uint64_t)bw.y << 32);
+                f_hi = (uint64_t)bw.z | ((uint64_t)bw.w << 32);
             }
             const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;
             cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);
@@ -606,57 +787,141 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tau = INFINITY;
         }
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kPPN;
-        for (int t = 0; t < n_tiles; ++t) {
-            const float e_t = cu * tile_norm[t];
-            mbar_wait(s32(tfull + h), (uint32_t)t & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int n0 = t * kPPN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < kPPN; c0 += 64) {
-                const float thr = tau - e_t;   // tau may have been raised by the previous chunk
-                float v[64];
-                tmem_ld64(lane_addr + c0, v);
-                if (c0 == kPPN - 64) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(s32(tempty + h));
-                }
-                if (DUMP) {
-                    float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * kPPN) + n0 + c0;
+        const int abl = DIAG ? p.ablate : 0;
+        unsigned long long d_app = 0, d_raise = 0, d_hit = 0, d_chunks = 0;
+        long long d_wait = 0, d_rcyc = 0, d_acyc = 0;
+        const long long c_start = DIAG ? clock64() : 0;
+        uint32_t ra[64], rb[64];
+        // one 64-column chunk: FMNMX3 max tree against the row threshold, survivors appended
+        // one 64-column chunk: FMNMX3 max tree against the row threshold.  Survivors of a hit group are appended
+        // branch-free: every element is stored at the current slot and the slot only advances for a survivor (the
+        // "maybe masked" bit is filled in lazily by the raise; the re-rank does the exact mask test anyway).
+        auto filter_chunk = [&](const uint32_t (&r)[64], const float thr, const uint32_t pos0) {
+            if (DUMP) {
+                float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * kPPN) + pos0;
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) dst[j] = v[j];
-                }
-                float gm[8];
+                for (int j = 0; j < 64; ++j) dst[j] = __uint_as_float(r[j]);
+            }
+            if (abl & 2) return;
+            float gm[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float a = max3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+                const float b = max3(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+                gm[g] = max3(a, b, fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+            }
+            const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
+            if (m >= thr && cnt >= 0 && !(abl & 1)) {
+                const int c_in = cnt;
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    const float a = max3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
-                    const float b = max3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
-                    gm[g] = max3(a, b, fmaxf(v[8 * g + 6], v[8 * g + 7]));
-                }
-                const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
-                if (m >= thr && cnt >= 0) {
+                    if (gm[g] >= thr) {
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        if (gm[g] >= thr) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float s = v[8 * g + j];
-                                const uint32_t pos = (uint32_t)(n0 + c0 + 8 * g + j);
-                                if (s >= thr && pos < (uint32_t)num_items) {
-                                    const uint32_t hsh = (pos * 2654435761u) >> 25;
-                                    const uint32_t flag = (uint32_t)(((hsh & 64u) ? f_hi : f_lo) >> (hsh & 63u)) & 1u;
-                                    my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (flag << 31) | pos;
-                                    ++cnt;
-                                }
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            const float sc = __uint_as_float(r[8 * g + j]);
+                            const uint32_t pos = pos0 + 8 * g + j;
+                            my_cand[cnt] = ((uint64_t)f2ord(sc) << 32) | pos;
+                            cnt += (sc >= thr && pos < num_items) ? 1 : 0;
                         }
                     }
                 }
-                const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - 64 - 1);
-                if (need) raise_thresholds<kPPN, 64>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane);
+                napp += cnt - c_in;
+            }
+        };
+        for (int t = 0; t < n_tiles; ++t) {
+            float thr = tau - cu * tile_norm[t];   // tau only moves at the end of a tile (and in the bootstrap)
+            const long long c_w0 = (DIAG && p.dbg) ? clock64() : 0;
+            mbar_wait(s32(tfull + h), (uint32_t)t & 1u);
+            if (DIAG && p.dbg) d_wait += clock64() - c_w0;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (abl & 4) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s32(tempty + h));
+                continue;
+            }
+            const uint32_t n0 = (uint32_t)t * kPPN;
+            {
+            tmem_ld64_async(lane_addr, ra);
+            tmem_ld_wait64(ra);
+            if (t == 0 && keff <= 32 && !(abl & 128)) {
+                // Bootstrap (all 32 rows of the warp at once, in registers): tau0 = K-th largest lower bound among
+                // the certainly-unmasked items of the first chunk - the 64 items of largest norm.  Without it every
+                // row would append all of tile 0 and need a warp-cooperative raise at the same moment.
+                const float e0 = cu * tile_norm[0];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const uint32_t hsh = ((uint32_t)j * 2654435761u) >> 25;
+                    const uint32_t flag = (uint32_t)(((hsh & 64u) ? f_hi : f_lo) >> (hsh & 63u)) & 1u;
+                    rb[j] = (flag || (uint32_t)j >= num_items) ? 0xFF800000u : ra[j];
+                }
+                float prev = INFINITY;
+                for (int r = 0; r < keff; ++r) {   // r-th largest distinct value (duplicates only lower the bound)
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        const float w = __uint_as_float(rb[j]);
+                        m = fmaxf(m, w < prev ? w : -INFINITY);
+                    }
+                    prev = m;
+                }
+                if (row_ok && prev > -INFINITY) { tau = prev - e0; thr = tau - e0; }
+            }
+            tmem_ld64_async(lane_addr + 64, rb);
+            filter_chunk(ra, thr, n0);
+            tmem_ld_wait64(rb);
+            tmem_ld64_async(lane_addr + 128, ra);
+            filter_chunk(rb, thr, n0 + 64);
+            tmem_ld_wait64(ra);
+            tmem_ld64_async(lane_addr + 192, rb);
+            filter_chunk(ra, thr, n0 + 128);
+            tmem_ld_wait64(rb);
+            }
+            // every TMEM read of this warp for tile t has landed: hand the accumulator back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s32(tempty + h));
+            filter_chunk(rb, thr, n0 + 192);
+            // a full tile (256 appends) must always fit: raise when fewer than 256 slots are left
+            const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kPPN - 1);
+            if (need) {
+                if (DIAG) d_raise += __popc(need);
+                const long long c_r0 = (DIAG && p.dbg) ? clock64() : 0;
+                if (keff <= 32 && !(abl & 16))
+                    raise_fast<kPPN, kPPN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, lane, f_lo, f_hi);
+                else
+                    raise_thresholds<kPPN, kPPN, true>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane, f_lo, f_hi);
+                if (DIAG && p.dbg) d_rcyc += clock64() - c_r0;
+            }
+            // a row that keeps beating its own threshold (scores rising along the sweep: a user anti-aligned with
+            // the popularity direction) would drag its warp through the append path on every chunk: hand it to the
+            // exact kernel instead
+            if (napp > budget && cnt >= 0) { cnt = -1; tau = INFINITY; }
+        }
+        if (DIAG) d_app = (unsigned long long)napp;
+        if (row_ok) p.cand_cnt[row] = cnt;
+        if (DIAG && p.dbg_row && row_ok) {
+            float *w = p.dbg_row + (size_t)row * 4;
+            w[0] = (float)d_app; w[1] = (float)cnt; w[2] = tau; w[3] = cu;
+        }
+        if (DIAG && p.dbg) {
+            atomicAdd(p.dbg + 0, d_app);
+            if (lane == 0) {
+                atomicAdd(p.dbg + 1, d_raise); atomicAdd(p.dbg + 2, d_hit); atomicAdd(p.dbg + 3, d_chunks);
+                atomicAdd(p.dbg + 4, (unsigned long long)d_wait); atomicAdd(p.dbg + 5, (unsigned long long)d_rcyc);
+                atomicAdd(p.dbg + 6, (unsigned long long)d_acyc);
+                atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - c_start));
+                if (p.dbg_warp) {
+                    unsigned long long *w = p.dbg_warp + ((size_t)blockIdx.x * kEpiWarps + ew) * 4;
+                    w[0] = (unsigned long long)(clock64() - c_start); w[1] = (unsigned long long)d_wait;
+                    w[2] = (unsigned long long)d_rcyc; w[3] = d_raise;
+                }
+                atomicMax(p.dbg + 8, (unsigned long long)(clock64() - c_start));
+                atomicMax(p.dbg + 9, (unsigned long long)d_rcyc);
+                atomicMax(p.dbg + 10, (unsigned long long)d_wait);
+                atomicMax(p.dbg + 11, (unsigned long long)d_raise);
             }
         }
-        if (row_ok) p.cand_cnt[row] = cnt;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -783,16 +1048,17 @@ static size_t sort_temp_bytes(int num_items) {
 struct TcLayout {
     int dpad, KB, rows_cap, items_pad, n_tiles, tile;
     size_t off_vh, off_uh, off_unorm, off_vnorm, off_vnorm_sorted, off_iota, off_perm, off_inv, off_tnorm, off_scalars, off_sort,
-        sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, total;
+        sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, off_bloom, total;
 };
 static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     TcLayout L;
     L.dpad = (int)align_up(d, kBK);
     L.KB = L.dpad / kBK;
     L.rows_cap = n_users < kRowsPerLaunch ? (int)align_up(n_users > 0 ? n_users : 1, kBM) : kRowsPerLaunch;
-    // B200REC_TC_PP=1 selects the N=256 ping-pong kernel for d <= 128 (measured slower in-kernel than the N=128
-    // kernel, ncu run 11: 1.57 ms vs 1.14 ms - four epilogue warps per half cannot keep up); default: N=128
-    static const bool use_pp = getenv("B200REC_TC_PP") && atoi(getenv("B200REC_TC_PP")) != 0;
+    // d <= 128: N=256 ping-pong kernel (ncu r16: tensor pipe 91.6 % of peak sustained active, 0.58 ms for 32768 x 100k);
+    // d > 128: N=128 kernel (the ping-pong ring would need 2*KB stages of 32 KB).  B200REC_TC_KERNEL=0 forces N=128.
+    const char *kenv = getenv("B200REC_TC_KERNEL");
+    const bool use_pp = !(kenv && atoi(kenv) == 0);
     L.tile = (use_pp && L.KB <= 2) ? kPPN : kBN;
     L.items_pad = (int)align_up(num_items, L.tile);
     L.n_tiles = L.items_pad / L.tile;
@@ -808,13 +1074,14 @@ static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     L.off_perm = take((size_t)L.items_pad * 4, 256);
     L.off_inv = take((size_t)L.items_pad * 4, 256);
     L.off_tnorm = take((size_t)L.n_tiles * 4, 256);
-    L.off_scalars = take(64, 256);   // [0] max|v| bits, [1] max|u| bits, [2] scale_v, [3] scale_u
+    L.off_scalars = take(256, 256);   // [0] max|v| bits, [1] max|u| bits, [2] scale_v, [3] scale_u
     L.off_sort = take(L.sort_bytes, 256);
     L.off_cand = take((size_t)L.rows_cap * kCand * 8, 256);
     L.off_cnt = take((size_t)L.rows_cap * 4, 256);
     L.off_redo = take((size_t)L.rows_cap * 4, 256);
     L.off_redo_n = take(4, 256);
     L.off_ruser = take((size_t)L.rows_cap * 4, 256);
+    L.off_bloom = take((size_t)L.rows_cap * 16, 256);
     L.off_ridx = take((size_t)L.rows_cap * k * 4, 256);
     L.off_rsc = take((size_t)L.rows_cap * k * 4, 256);
     L.total = align_up(o, 256);
@@ -855,11 +1122,15 @@ static int launch_candidates_pp(const CUtensorMap &ma, const CUtensorMap &mb, co
     B200_REQUIRE(stages >= 2 * KB, B200REC_EUNSUPPORTED, "score_topk TC: ping-pong kernel needs 2 tiles of stages");
     const size_t smem = 1024 + a_bytes + (size_t)stages * kPPN * 128 + 22 * 8 + kEpiWarps * 32 * 4 + 64;
     if (p.dump) {
-        auto kern = tc_candidate_pp_kernel<KB, true>;
+        auto kern = tc_candidate_pp_kernel<KB, true, false>;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
+    } else if (p.dbg || p.ablate) {
+        auto kern = tc_candidate_pp_kernel<KB, false, true>;
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
     } else {
-        auto kern = tc_candidate_pp_kernel<KB, false>;
+        auto kern = tc_candidate_pp_kernel<KB, false, false>;
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<n_blocks, kThreads, smem, s>>>(ma, mb, p, stages);
     }
@@ -897,7 +1168,7 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
     const int sms = sm_count();
 
     // ---- item side, once per call: norms, descending-norm order, fp16 copy in that order, per-tile bound ----
-    B200_CUDA(cudaMemsetAsync(scal, 0, 64, s));
+    B200_CUDA(cudaMemsetAsync(scal, 0, 256, s));
     row_stats_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, num_items, vnorm, scal + 0);
     B200_LAUNCH_CHECK();
     iota_kernel<<<(num_items + 255) / 256, 256, 0, s>>>(iota, num_items);
@@ -932,9 +1203,37 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         TcParams p;
         p.n_rows = nr; p.num_items = num_items; p.n_tiles = L.n_tiles; p.k = k; p.d = d;
         p.users = users + r0; p.mask_indptr = mi; p.mask_indices = mx; p.inv_perm = inv_perm;
+        p.bloom = nullptr;
+        p.append_budget = 1024 + 8 * k;
+        if (mi) {
+            uint4 *bloom = reinterpret_cast<uint4 *>(base + L.off_bloom);
+            bloom_kernel<<<(nr + 7) / 8, 256, 0, s>>>(users + r0, nr, mi, mx, inv_perm, bloom);
+            B200_LAUNCH_CHECK();
+            p.bloom = bloom;
+        }
         p.row_norm = unorm; p.tile_norm = tnorm;
         p.scale_v = reinterpret_cast<float *>(scal + 2); p.scale_u = reinterpret_cast<float *>(scal + 3);
         p.cand = cand; p.cand_cnt = cnt; p.dump = dump ? dump + (size_t)r0 * L.items_pad : nullptr;
+        // diagnostics only: ablation flags, kernel time and filter counters on stderr
+        const char *abl_env = getenv("B200REC_TC_ABLATE");
+        const bool diag = getenv("B200REC_TC_TIME") != nullptr;
+        p.ablate = abl_env ? atoi(abl_env) : 0;
+        p.dbg = (diag && atoi(getenv("B200REC_TC_TIME")) >= 2) ? reinterpret_cast<unsigned long long *>(scal + 8) : nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        p.dbg_warp = nullptr; p.dbg_row = nullptr;
+        if (p.dbg && atoi(getenv("B200REC_TC_TIME")) >= 4) {
+            cudaMalloc(&p.dbg_row, (size_t)nr * 16);
+            cudaMemset(p.dbg_row, 0, (size_t)nr * 16);
+        }
+        if (p.dbg && atoi(getenv("B200REC_TC_TIME")) == 3) {
+            cudaMalloc(&p.dbg_warp, (size_t)(nr_pad / kBM) * kEpiWarps * 32);
+            cudaMemset(p.dbg_warp, 0, (size_t)(nr_pad / kBM) * kEpiWarps * 32);
+        }
+        if (diag) {
+            B200_CUDA(cudaMemsetAsync(scal + 8, 0, 128, s));
+            cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+            cudaEventRecord(ev0, s);
+        }
         switch (L.KB) {
             case 1: rc = (L.tile == kPPN) ? launch_candidates_pp<1>(ma, mb, p, nr_pad / kBM, s)
                                           : launch_candidates<1>(ma, mb, p, nr_pad / kBM, s); break;
@@ -944,6 +1243,59 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
             default: rc = launch_candidates<4>(ma, mb, p, nr_pad / kBM, s); break;
         }
         if (rc) return rc;
+        if (diag) {
+            cudaEventRecord(ev1, s);
+            cudaEventSynchronize(ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            unsigned long long h[16];
+            cudaMemcpy(h, scal + 8, 128, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[b200rec tc] candidate kernel tile=%d ablate=%d rows=%d: %.3f ms  appends/row=%.1f raises/row=%.2f"
+                            "\n", L.tile, p.ablate, nr, ms, (double)h[0] / nr, (double)h[1] / nr);
+            if (h[7])
+                fprintf(stderr, "        epilogue warp cycles: wait tfull %.1f%%  raise %.1f%%  (mean total %.0f cycles/warp)\n",
+                        100.0 * h[4] / h[7], 100.0 * h[5] / h[7],
+                        (double)h[7] / ((double)(nr_pad / kBM) * kEpiWarps));
+            if (h[7])
+                fprintf(stderr, "        max over warps: total %llu cycles, raise %llu cycles, wait %llu cycles, raises %llu\n", h[8], h[9],
+                        h[10], h[11]);
+            if (p.dbg_warp) {
+                const int nb = nr_pad / kBM;
+                std::vector<unsigned long long> hw((size_t)nb * kEpiWarps * 4);
+                cudaMemcpy(hw.data(), p.dbg_warp, hw.size() * 8, cudaMemcpyDeviceToHost);
+                for (int b = 0; b < nb; ++b) {
+                    unsigned long long mx = 0;
+                    for (int w = 0; w < kEpiWarps; ++w) mx = hw[((size_t)b * kEpiWarps + w) * 4] > mx ? hw[((size_t)b * kEpiWarps + w) * 4] : mx;
+                    if (b < 4 || mx > 1800000ull) {
+                        fprintf(stderr, "        cta %3d:", b);
+                        for (int w = 0; w < kEpiWarps; ++w) {
+                            const unsigned long long *q = &hw[((size_t)b * kEpiWarps + w) * 4];
+                            fprintf(stderr, " [%lluk w%lluk r%lluk n%llu]", q[0] / 1000, q[1] / 1000, q[2] / 1000, q[3]);
+                        }
+                        fprintf(stderr, "\n");
+                    }
+                }
+                cudaFree(p.dbg_warp);
+            }
+            if (p.dbg_row) {
+                std::vector<float> hr((size_t)nr * 4), hn((size_t)nr), tn((size_t)L.n_tiles);
+                cudaMemcpy(hr.data(), p.dbg_row, hr.size() * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(hn.data(), unorm, (size_t)nr * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(tn.data(), tnorm, (size_t)L.n_tiles * 4, cudaMemcpyDeviceToHost);
+                float sc[2];
+                cudaMemcpy(sc, scal + 2, 8, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "        scale_v=%g scale_u=%g tile_norm[0]=%g [1]=%g [last]=%g\n", sc[0], sc[1], tn[0], tn[1], tn[L.n_tiles - 1]);
+                int shown = 0;
+                for (int r = 0; r < nr && shown < 24; ++r)
+                    if (hr[(size_t)r * 4] > 1000.f) {
+                        fprintf(stderr, "        row %5d: appends %.0f cnt %.0f tau %g cu %g |u| %g\n", r, hr[(size_t)r * 4],
+                                hr[(size_t)r * 4 + 1], hr[(size_t)r * 4 + 2], hr[(size_t)r * 4 + 3], hn[r]);
+                        ++shown;
+                    }
+                cudaFree(p.dbg_row);
+            }
+            cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        }
         if (!oi) continue;  // dump-only bring-up call
         B200_CUDA(cudaMemsetAsync(redo_n, 0, 4, s));
         const size_t rsmem = (size_t)8 * k * 8 + (size_t)8 * ((d + 3) & ~3) * 4;

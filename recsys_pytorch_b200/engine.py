@@ -166,7 +166,7 @@ def debug_tc_scores(U, V, d, users):
     users = _i32(users, "users")
     n, ni = users.numel(), V.shape[0]
     import os
-    tile = 256 if (d <= 128 and os.environ.get("B200REC_TC_PP", "0") not in ("", "0")) else 128   # as score_tc.cu
+    tile = 256 if (d <= 128 and os.environ.get("B200REC_TC_KERNEL", "1") != "0") else 128   # as score_tc.cu::tc_layout
     rp, ip = (n + 255) // 256 * 256, (ni + tile - 1) // tile * tile
     out = torch.zeros((rp, ip), dtype=torch.float32, device=U.device)
     ws_bytes = int(_lib.lib().b200rec_score_topk_workspace(n, ni, d, 1, SCORE_TC))
