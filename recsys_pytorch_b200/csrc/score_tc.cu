@@ -201,28 +201,64 @@ __global__ void iota_kernel(int32_t *out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = i;
 }
-// tile_norm[t] = largest item norm in tile t (= first entry, norms sorted descending)
-__global__ void tile_norm_kernel(const uint32_t *sorted_norm_bits, int num_items, int n_tiles, int tile, float *tile_norm) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n_tiles) tile_norm[t] = (t * tile < num_items) ? __uint_as_float(sorted_norm_bits[t * tile]) : 0.f;
+// Final visiting order of the items.  Ranks are positions in the descending-norm order (one radix sort per call):
+//   [0, H)            the H highest-norm items (a user aligned with the popularity direction finds its top-K here),
+//   [H, H+S)          a stratified sample of the rest (every `stride`-th rank): a user whose best items sit anywhere
+//                     else in the norm range (anti-aligned users: corr(score, norm) < 0) gets a usable threshold from
+//                     it instead of beating its own threshold along the whole sweep,
+//   [H+S, N)          everything else, still in descending-norm order.
+__global__ void reorder_kernel(const int32_t *__restrict__ perm, const uint32_t *__restrict__ sorted_norm_bits, int n,
+                               int H, int S, int stride, int32_t *__restrict__ perm_out, float *__restrict__ norm_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int pos = r;
+    if (S > 0 && r >= H) {
+        const int q = r - H;
+        const int j = q / stride;
+        if (q % stride == 0 && j < S) pos = H + j;
+        else pos = H + S + q - (j + 1 < S ? j + 1 : S);
+    }
+    perm_out[pos] = perm[r];
+    norm_out[pos] = __uint_as_float(sorted_norm_bits[r]);
+}
+// tile_norm[t] = largest item norm in tile t of the final order (one warp per tile)
+__global__ void tile_norm_kernel(const float *__restrict__ norm, int num_items, int n_tiles, int tile, float *__restrict__ tile_norm) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= n_tiles) return;
+    float m = 0.f;
+    for (int i = t * tile + lane; i < (t + 1) * tile && i < num_items; i += 32) m = fmaxf(m, norm[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) tile_norm[t] = m;
 }
 
-// 128-bit "maybe masked" filter per scored row: one bit per hashed sorted position of a train positive (no false
-// negatives).  One warp per row, coalesced over the row's positives.
+// "Maybe masked" filters per scored row (no false negatives), one warp per row, coalesced over the row's positives:
+//   bloom[row]            128 bits, kept in registers by the N=128 kernel (one bit per hashed sorted position)
+//   wide[row][0]          EXACT bitmap of the first 64 positions (the bootstrap chunk of the ping-pong kernel)
+//   wide[row][1..32]      2048-bit filter read from global memory by the (rare) threshold raises
+constexpr int kWideWords = 33;   // uint64 words per row
+__device__ __forceinline__ uint32_t wide_hash(uint32_t pos) { return (pos * 2654435761u) >> 21; }   // 11 bits
 __global__ void __launch_bounds__(256) bloom_kernel(const int32_t *__restrict__ users, int n_rows,
                                                     const int64_t *__restrict__ mask_indptr,
                                                     const int32_t *__restrict__ mask_indices,
-                                                    const int32_t *__restrict__ inv_perm, uint4 *__restrict__ bloom) {
+                                                    const int32_t *__restrict__ inv_perm, uint4 *__restrict__ bloom,
+                                                    unsigned long long *__restrict__ wide) {
     const int lane = threadIdx.x & 31;
     const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (row >= n_rows) return;
     const int u = users[row];
     const int64_t mb = mask_indptr[u], me = mask_indptr[u + 1];
+    unsigned long long *wrow = wide + (size_t)row * kWideWords;
+    for (int q = lane; q < kWideWords; q += 32) wrow[q] = 0ull;
+    __syncwarp();
     unsigned w[4] = {0u, 0u, 0u, 0u};
     for (int64_t m = mb + lane; m < me; m += 32) {
-        const uint32_t hsh = ((uint32_t)inv_perm[mask_indices[m]] * 2654435761u) >> 25;
+        const uint32_t pos = (uint32_t)inv_perm[mask_indices[m]];
+        const uint32_t hsh = (pos * 2654435761u) >> 25;
 #pragma unroll
         for (int q = 0; q < 4; ++q) w[q] |= ((hsh >> 5) == (uint32_t)q) ? (1u << (hsh & 31u)) : 0u;
+        if (pos < 64u) atomicOr(wrow, 1ull << pos);
+        const uint32_t h2 = wide_hash(pos);
+        atomicOr(wrow + 1 + (h2 >> 6), 1ull << (h2 & 63u));
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) w[q] = __reduce_or_sync(0xffffffffu, w[q]);
@@ -236,6 +272,7 @@ struct TcParams {
     const int32_t *mask_indices;
     const int32_t *inv_perm;         // item id -> sorted position
     const uint4 *bloom;              // [n_rows] 128-bit "maybe masked" filter per row (NULL without a mask)
+    const unsigned long long *wide;  // [n_rows][kWideWords] exact head bitmap + 2048-bit filter (NULL without a mask)
     int append_budget;               // a row that appends more than this is handed to the exact kernel
     const float *row_norm;           // [n_rows]
     const float *tile_norm;          // [n_tiles]
@@ -253,8 +290,8 @@ struct TcParams {
 // Entries hold S~ (scaled); e = cu * tile_norm[pos/128]; L = S~ - e, H = S~ + e.
 template <int TILE, int WM, bool LAZY_FLAG = false>
 __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff, float cu,
-                                                 const float *__restrict__ tile_norm, int *hist, int lane, uint64_t f_lo = 0,
-                                                 uint64_t f_hi = 0) {
+                                                 const float *__restrict__ tile_norm, int *hist, int lane,
+                                                 const unsigned long long *my_wide = nullptr) {
     while (need) {
         const int Lsrc = __ffs(need) - 1;
         need &= need - 1;
@@ -263,11 +300,9 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
         const int kf = __shfl_sync(0xffffffffu, keff, Lsrc);
         const float c_u = __shfl_sync(0xffffffffu, cu, Lsrc);
         const float old_tau = __shfl_sync(0xffffffffu, tau, Lsrc);
-        uint64_t flo = 0, fhi = 0;
-        if (LAZY_FLAG) {   // appends left the "maybe masked" bit clear: fill it in on first sight
-            flo = __shfl_sync(0xffffffffu, (unsigned long long)f_lo, Lsrc);
-            fhi = __shfl_sync(0xffffffffu, (unsigned long long)f_hi, Lsrc);
-        }
+        const unsigned long long *wf = nullptr;
+        if (LAZY_FLAG)   // appends left the "maybe masked" bit clear: fill it in on first sight
+            wf = reinterpret_cast<const unsigned long long *>(__shfl_sync(0xffffffffu, (unsigned long long)my_wide, Lsrc));
         // lo[] = lower bound of the CLEAN entries only (bit 31 of the position = "maybe masked": such an
         // entry never counts towards the K items that justify tau); hi[] = upper bound of every entry
         uint64_t e[kCand / 32];
@@ -278,9 +313,9 @@ __device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_can
             const int p = lane + 32 * i;
             e[i] = (p < n) ? base[p] : 0ull;
             lo[i] = -INFINITY; hi[i] = -INFINITY;
-            if (LAZY_FLAG && p < n) {
-                const uint32_t hsh = (((uint32_t)e[i] & 0x7FFFFFFFu) * 2654435761u) >> 25;
-                e[i] |= (uint64_t)((uint32_t)(((hsh & 64u) ? fhi : flo) >> (hsh & 63u)) & 1u) << 31;
+            if (LAZY_FLAG && p < n && wf) {
+                const uint32_t h2 = wide_hash((uint32_t)e[i] & 0x7FFFFFFFu);
+                e[i] |= (uint64_t)((uint32_t)(wf[1 + (h2 >> 6)] >> (h2 & 63u)) & 1u) << 31;
             }
             if (p < n) {
                 const float s = ord2f((uint32_t)(e[i] >> 32));
@@ -397,8 +432,8 @@ __device__ __forceinline__ void tmem_ld_wait64(uint32_t (&r)[64]) {
 // compacted in place.
 template <int TILE, int WM>
 __device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff,
-                                           float cu, const float *__restrict__ tile_norm, int lane, uint64_t f_lo,
-                                           uint64_t f_hi) {
+                                           float cu, const float *__restrict__ tile_norm, int lane,
+                                           const unsigned long long *my_wide) {
     constexpr int E = kCand / 32;
     while (need) {
         const int Lsrc = __ffs(need) - 1;
@@ -409,8 +444,8 @@ __device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int
         const int kf = __shfl_sync(0xffffffffu, keff, Lsrc);
         const float c_u = __shfl_sync(0xffffffffu, cu, Lsrc);
         const float old_tau = __shfl_sync(0xffffffffu, tau, Lsrc);
-        const uint64_t flo = __shfl_sync(0xffffffffu, (unsigned long long)f_lo, Lsrc);
-        const uint64_t fhi = __shfl_sync(0xffffffffu, (unsigned long long)f_hi, Lsrc);
+        const unsigned long long *wf =
+            reinterpret_cast<const unsigned long long *>(__shfl_sync(0xffffffffu, (unsigned long long)my_wide, Lsrc));
         uint64_t e[E];
         float hi[E];
 #pragma unroll
@@ -424,9 +459,10 @@ __device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int
                 const float err = c_u * tile_norm[(uint32_t)(e[i] & 0x7FFFFFFFu) / TILE];
                 hi[i] = sc + err;
                 // "maybe masked" bit, computed on first sight (appends leave it clear) and kept in the entry
-                const uint32_t hsh = (((uint32_t)e[i] & 0x7FFFFFFFu) * 2654435761u) >> 25;
-                const uint32_t flag = (uint32_t)(((hsh & 64u) ? fhi : flo) >> (hsh & 63u)) & 1u;
-                e[i] |= (uint64_t)flag << 31;
+                if (wf) {
+                    const uint32_t h2 = wide_hash((uint32_t)e[i] & 0x7FFFFFFFu);
+                    e[i] |= (uint64_t)((uint32_t)(wf[1 + (h2 >> 6)] >> (h2 & 63u)) & 1u) << 31;
+                }
                 if (!((uint32_t)e[i] >> 31)) lmax = fmaxf(lmax, sc - err);
             }
         }
@@ -774,13 +810,8 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int keff = p.k;
         const int budget = p.append_budget;
         float tau = -INFINITY, cu = 0.f;
-        uint64_t f_lo = 0, f_hi = 0;
+        const unsigned long long *my_wide = (p.wide && row_ok) ? p.wide + (size_t)row * kWideWords : nullptr;
         if (row_ok) {
-            if (p.bloom) {
-                const uint4 bw = p.bloom[row];
-                f_lo = (uint64_t)bw.x | ((uint64_t)bw.y << 32);
-                f_hi = (uint64_t)bw.z | ((uint64_t)bw.w << 32);
-            }
             const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;
             cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);
         } else {
@@ -792,7 +823,6 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         long long d_wait = 0, d_rcyc = 0, d_acyc = 0;
         const long long c_start = DIAG ? clock64() : 0;
         uint32_t ra[64], rb[64];
-        // one 64-column chunk: FMNMX3 max tree against the row threshold, survivors appended
         // one 64-column chunk: FMNMX3 max tree against the row threshold.  Survivors of a hit group are appended
         // branch-free: every element is stored at the current slot and the slot only advances for a survivor (the
         // "maybe masked" bit is filled in lazily by the raise; the re-rank does the exact mask test anyway).
@@ -849,12 +879,10 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 // the certainly-unmasked items of the first chunk - the 64 items of largest norm.  Without it every
                 // row would append all of tile 0 and need a warp-cooperative raise at the same moment.
                 const float e0 = cu * tile_norm[0];
+                const unsigned long long head = my_wide ? my_wide[0] : 0ull;   // exact mask bitmap of positions 0..63
 #pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    const uint32_t hsh = ((uint32_t)j * 2654435761u) >> 25;
-                    const uint32_t flag = (uint32_t)(((hsh & 64u) ? f_hi : f_lo) >> (hsh & 63u)) & 1u;
-                    rb[j] = (flag || (uint32_t)j >= num_items) ? 0xFF800000u : ra[j];
-                }
+                for (int j = 0; j < 64; ++j)
+                    rb[j] = (((head >> j) & 1ull) || (uint32_t)j >= num_items) ? 0xFF800000u : ra[j];
                 float prev = INFINITY;
                 for (int r = 0; r < keff; ++r) {   // r-th largest distinct value (duplicates only lower the bound)
                     float m = -INFINITY;
@@ -888,9 +916,9 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 if (DIAG) d_raise += __popc(need);
                 const long long c_r0 = (DIAG && p.dbg) ? clock64() : 0;
                 if (keff <= 32 && !(abl & 16))
-                    raise_fast<kPPN, kPPN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, lane, f_lo, f_hi);
+                    raise_fast<kPPN, kPPN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, lane, my_wide);
                 else
-                    raise_thresholds<kPPN, kPPN, true>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane, f_lo, f_hi);
+                    raise_thresholds<kPPN, kPPN, true>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane, my_wide);
                 if (DIAG && p.dbg) d_rcyc += clock64() - c_r0;
             }
             // a row that keeps beating its own threshold (scores rising along the sweep: a user anti-aligned with
@@ -1048,7 +1076,7 @@ static size_t sort_temp_bytes(int num_items) {
 struct TcLayout {
     int dpad, KB, rows_cap, items_pad, n_tiles, tile;
     size_t off_vh, off_uh, off_unorm, off_vnorm, off_vnorm_sorted, off_iota, off_perm, off_inv, off_tnorm, off_scalars, off_sort,
-        sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, off_bloom, total;
+        sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, off_bloom, off_wide, total;
 };
 static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     TcLayout L;
@@ -1082,6 +1110,7 @@ static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     L.off_redo_n = take(4, 256);
     L.off_ruser = take((size_t)L.rows_cap * 4, 256);
     L.off_bloom = take((size_t)L.rows_cap * 16, 256);
+    L.off_wide = take((size_t)L.rows_cap * kWideWords * 8, 256);
     L.off_ridx = take((size_t)L.rows_cap * k * 4, 256);
     L.off_rsc = take((size_t)L.rows_cap * k * 4, 256);
     L.total = align_up(o, 256);
@@ -1178,12 +1207,23 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
                                                          reinterpret_cast<const uint32_t *>(vnorm), vnorm_sorted,
                                                          (const int32_t *)iota, perm, num_items, 0, 32, s));
     count_launch(3);
-    inverse_perm_kernel<<<(num_items + 255) / 256, 256, 0, s>>>(perm, num_items, inv_perm);
+    // final visiting order (head | stratified sample | rest): the iota and unsorted-norm buffers are free again
+    int32_t *order = iota;
+    float *norm_final = vnorm;
+    {
+        const int H = L.tile, S = 16 * L.tile;
+        const bool sample = num_items >= 8 * (H + S);
+        const int stride = sample ? (num_items - H) / S : 1;
+        reorder_kernel<<<(num_items + 255) / 256, 256, 0, s>>>(perm, vnorm_sorted, num_items, H, sample ? S : 0, stride, order,
+                                                                norm_final);
+        B200_LAUNCH_CHECK();
+    }
+    inverse_perm_kernel<<<(num_items + 255) / 256, 256, 0, s>>>(order, num_items, inv_perm);
     B200_LAUNCH_CHECK();
-    to_f16_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, perm, num_items, L.items_pad, L.dpad, scal + 0, vh,
+    to_f16_kernel<<<sms * 8, 256, 0, s>>>(V, ld, d, nullptr, order, num_items, L.items_pad, L.dpad, scal + 0, vh,
                                            reinterpret_cast<float *>(scal + 2));
     B200_LAUNCH_CHECK();
-    tile_norm_kernel<<<(L.n_tiles + 255) / 256, 256, 0, s>>>(vnorm_sorted, num_items, L.n_tiles, L.tile, tnorm);
+    tile_norm_kernel<<<(L.n_tiles * 32 + 255) / 256, 256, 0, s>>>(norm_final, num_items, L.n_tiles, L.tile, tnorm);
     B200_LAUNCH_CHECK();
     CUtensorMap mb;
     int rc = make_map(&mb, vh, (uint64_t)L.items_pad, (uint64_t)L.dpad, (uint32_t)L.tile);
@@ -1203,13 +1243,14 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         TcParams p;
         p.n_rows = nr; p.num_items = num_items; p.n_tiles = L.n_tiles; p.k = k; p.d = d;
         p.users = users + r0; p.mask_indptr = mi; p.mask_indices = mx; p.inv_perm = inv_perm;
-        p.bloom = nullptr;
-        p.append_budget = 1024 + 8 * k;
+        p.bloom = nullptr; p.wide = nullptr;
+        p.append_budget = getenv("B200REC_TC_BUDGET") ? atoi(getenv("B200REC_TC_BUDGET")) : 1536 + 8 * k;
         if (mi) {
             uint4 *bloom = reinterpret_cast<uint4 *>(base + L.off_bloom);
-            bloom_kernel<<<(nr + 7) / 8, 256, 0, s>>>(users + r0, nr, mi, mx, inv_perm, bloom);
+            unsigned long long *wide = reinterpret_cast<unsigned long long *>(base + L.off_wide);
+            bloom_kernel<<<(nr + 7) / 8, 256, 0, s>>>(users + r0, nr, mi, mx, inv_perm, bloom, wide);
             B200_LAUNCH_CHECK();
-            p.bloom = bloom;
+            p.bloom = bloom; p.wide = wide;
         }
         p.row_norm = unorm; p.tile_norm = tnorm;
         p.scale_v = reinterpret_cast<float *>(scal + 2); p.scale_u = reinterpret_cast<float *>(scal + 3);
@@ -1302,7 +1343,7 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         B200_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         int rgrid = (nr + 7) / 8;
         if (rgrid > sms * 8) rgrid = sms * 8;
-        rerank_kernel<<<rgrid, 256, rsmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, perm, cand, cnt,
+        rerank_kernel<<<rgrid, 256, rsmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, order, cand, cnt,
                                                 oi + (size_t)r0 * k, os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
         B200_LAUNCH_CHECK();
         int n_redo = 0;
@@ -1357,7 +1398,7 @@ extern "C" int b200rec_debug_tc_scores(const float *U, const float *V, int ld, i
 extern "C" int b200rec_debug_tc_layout(int n_users, int num_items, int d, int64_t *off_perm, int64_t *off_scales) {
     using namespace b200;
     const TcLayout L = tc_layout(n_users, num_items, d, 1);
-    *off_perm = (int64_t)L.off_perm;
+    *off_perm = (int64_t)L.off_iota;   // the final visiting order lives in the iota buffer
     *off_scales = (int64_t)L.off_scalars + 8;
     return B200REC_OK;
 }
