@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 CFG = dict(num_users=1_000_000, num_items=100_000, d=128, batch=1_000_000, seed=2020, lr=0.05 * 1_000_000, reg=1e-4,
-           init_std=0.01, eval_users=32_768, eval_k=10)
+           init_std=0.01, eval_users=37_888, eval_k=10)   # 148 SMs x 256 rows: one full wave of the scoring kernel
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -50,9 +50,13 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    nvidia-smi needs ~0.1-0.3 s to deliver its first row and samples every 20 ms, while K steps of this kernel last a
+    few milliseconds; `timed_under_load` therefore keeps the GPU running the very same step (learning rate 0) before
+    and after the timed K steps, and only rows stamped inside that busy window are used."""
+
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -70,23 +74,32 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_lo=None, t_hi=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        # a row is printed right after it is sampled: keep the rows that arrived inside the busy window
+        rows = [r for (t, r) in self.rows if len(r) >= 8 and (t_lo is None or t_lo <= t <= t_hi)]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [v for v in (num(r[1]) for r in rows) if v is not None]
+        mx = [v for v in (num(r[2]) for r in rows) if v is not None]
+        pw = [v for v in (num(r[3]) for r in rows) if v is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "window": "GPU kept busy with the same step (lr=0) before and after the timed K steps; rows inside it"}
 
 
 def dist_env():
@@ -114,6 +127,25 @@ def timed_region(fn, steps, world):
         ms = float(t.item())
         dist.barrier()
     return ms
+
+
+def timed_under_load(step, idle_step, steps, world, gpu_index, rank=0, pre_steps=900, post_steps=250):
+    """`timed_region(step, K)` bracketed by `pre_steps` / `post_steps` launches of `idle_step` (the same kernel on the
+    same inputs with learning rate 0: identical traffic, tables unchanged) so that the clock sampler sees the GPU under
+    this load on both sides of the timed region.  The counts are fixed so every rank issues the same collectives."""
+    clocks = ClockSampler(gpu_index)
+    if rank == 0:
+        clocks.start()
+    torch.cuda.synchronize()
+    t_lo = time.time()
+    for s in range(pre_steps):
+        idle_step(s)
+    ms = timed_region(step, steps, world)
+    for s in range(post_steps):
+        idle_step(s)
+    torch.cuda.synchronize()
+    t_hi = time.time()
+    return ms, (clocks.stop(t_lo + 0.02, t_hi) if rank == 0 else None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -147,11 +179,11 @@ def run_b200(args):
     c = dict(CFG)
     if args.small:
         c.update(num_users=50_000, num_items=20_000, batch=50_000, eval_users=4096)
-    hbm_gbs, _, peak_src = measured_peaks()
+    hbm_gbs, bf16_tf, peak_src = measured_peaks()
 
     if world > 1:
         from recsys_pytorch_b200 import dist as bdist
-        return bdist.bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_gbs, peak_src)
+        return bdist.bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs, peak_src)
 
     train, target = synthetic.make_interactions(c["num_users"], c["num_items"], seed=c["seed"], device=dev)
     ds = types.SimpleNamespace(num_users=c["num_users"], num_items=c["num_items"], train_data=train,
@@ -171,13 +203,24 @@ def run_b200(args):
         engine.bpr_step(model.U, model.V, d, perms[s % n_perm], csr=train, lr=c["lr"], reg=c["reg"],
                         sink=_lib.SINK_UPDATE, flags=flags, seed=c["seed"], step=s + 1, loss_sum=loss)
 
+    scratch_loss = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step_idle(s):      # same kernel, same traffic, learning rate 0 (tables unchanged): clock-sampling window only
+        engine.bpr_step(model.U, model.V, d, perms[s % n_perm], csr=train, lr=0.0, reg=c["reg"],
+                        sink=_lib.SINK_UPDATE, flags=flags, seed=c["seed"], step=100000 + s, loss_sum=scratch_loss)
+
     for s in range(args.warmup):
         step_dev(s)
-    clocks = ClockSampler(local); clocks.start()
-    l0 = _lib.launch_count()
-    ms = timed_region(step_dev, args.steps, world)
-    launches = _lib.launch_count() - l0
-    clk = clocks.stop()
+    counted = [0, 0]
+
+    def step_counted(s):   # the library counts every kernel it launches: read the counter at both ends of the region
+        if s == 0:
+            counted[0] = _lib.launch_count()
+        step_dev(s)
+        if s == args.steps - 1:
+            counted[1] = _lib.launch_count()
+    ms, clk = timed_under_load(step_counted, step_idle, args.steps, world, local)
+    launches = counted[1] - counted[0]
     triples_per_s = B * args.steps / (ms * 1e-3)
     ms_per_step = ms / args.steps
 
@@ -226,7 +269,12 @@ def run_b200(args):
     eval_leg = {"scored_pairs_per_sec": pairs / t_dev, "e2e_pairs_per_sec": pairs / t_eval,
                 "ndcg@%d" % c["eval_k"]: float(scores["NDCG@%d" % c["eval_k"]]), "users": c["eval_users"],
                 "k": c["eval_k"], "algo": args.score_algo,
-                "flops_per_pair": 2 * d}
+                "flops_per_pair": 2 * d,
+                # whole predict_topk call (pre-pass + tcgen05 candidate kernel + fp32 re-rank) against the measured
+                # dense bf16 peak; the candidate kernel's own tensor-pipe % is in profiles/ (ncu)
+                "tensor_roofline": {"bound": "tensor", "achieved": pairs * 2 * d / t_dev / 1e12, "peak": bf16_tf,
+                                    "unit": "TFLOP/s", "frac": pairs * 2 * d / t_dev / 1e12 / bf16_tf,
+                                    "peak_source": peak_src}}
 
     # ---- roofline of the dominant kernel (fused BPR step): algorithmic bytes = 24d+8 per triple ----
     bytes_per_triple = 24 * d + 8

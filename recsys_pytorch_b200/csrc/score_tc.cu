@@ -1069,7 +1069,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static size_t sort_temp_bytes(int num_items) {
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                              (const int32_t *)nullptr, (int32_t *)nullptr, num_items);
+                                              (const int32_t *)nullptr, (int32_t *)nullptr, num_items, 16, 32);
     return bytes;
 }
 
@@ -1205,7 +1205,7 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
     size_t sort_bytes = L.sort_bytes;
     B200_CUDA(cub::DeviceRadixSort::SortPairsDescending(base + L.off_sort, sort_bytes,
                                                          reinterpret_cast<const uint32_t *>(vnorm), vnorm_sorted,
-                                                         (const int32_t *)iota, perm, num_items, 0, 32, s));
+                                                         (const int32_t *)iota, perm, num_items, 16, 32, s));
     count_launch(3);
     // final visiting order (head | stratified sample | rest): the iota and unsorted-norm buffers are free again
     int32_t *order = iota;

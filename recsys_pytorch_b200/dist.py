@@ -178,7 +178,7 @@ class UserShardedBPR:
 # ------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
 # ------------------------------------------------------------------------------------------------
-def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_gbs, peak_src):
+def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs, peak_src):
     """Weak scaling: per-GPU work is fixed (B_local = c['batch'] triples per rank per step); the
     user population grows with N (N x num_users) while the item catalogue follows BASELINE
     configs[2] proportionally (N x num_items, capped at 1M)."""
@@ -228,13 +228,25 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, ClockSampler, hbm_g
 
     for s in range(args.warmup):
         step(s)
-    clocks = ClockSampler(dev.index or 0)
-    if rank == 0:
-        clocks.start()
-    l0 = _lib.launch_count()
-    ms = timed_region(step, args.steps, world)
-    launches = _lib.launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
+    counted = [0, 0]
+
+    def step_counted(s):
+        if s == 0:
+            counted[0] = _lib.launch_count()
+        step(s)
+        if s == args.steps - 1:
+            counted[1] = _lib.launch_count()
+
+    def step_idle(s):      # same step (kernel + collective) with learning rate 0: clock-sampling window only
+        lr = tr.lr
+        tr.lr = 0.0
+        try:
+            step(100000 + s)
+        finally:
+            tr.lr = lr
+    ms, clk = timed_under_load(step_counted, step_idle, args.steps, world, dev.index or 0, rank=rank, pre_steps=500,
+                               post_steps=150)
+    launches = counted[1] - counted[0]
     # e2e: same step with the batch's user ids arriving from pinned host memory and the loss read back
     host = [p.cpu().pin_memory() for p in perms]
 

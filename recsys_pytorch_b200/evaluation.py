@@ -154,6 +154,7 @@ class Evaluator:
         self.protocol = protocol
         self._register_eval_func()
         self._dev = {}
+        self._eval_users = None
 
     def _register_eval_func(self):
         self.eval_func = eval_func_router[self.protocol]
@@ -181,7 +182,9 @@ class Evaluator:
 
     def evaluate(self, model, mean=True):
         model.eval()
-        eval_users = np.array(list(self.eval_target.keys()))
+        if self._eval_users is None or len(self._eval_users) != len(self.eval_target):   # evaluator.py:34, cached
+            self._eval_users = np.array(list(self.eval_target.keys()))
+        eval_users = self._eval_users
         if hasattr(model, "predict_topk_device"):
             return self._evaluate_fused(model, eval_users, mean)
         # reference sequence, evaluation/evaluator.py:35-48, with the GPU drop-ins

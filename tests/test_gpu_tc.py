@@ -37,7 +37,9 @@ def test_tc_raw_scores_are_the_bf16_gemm(dev, d):
     got, su, sv, perm = engine.debug_tc_scores(U, V, d, users)
     assert sorted(perm.tolist()) == list(range(ni))                       # a permutation of the items ...
     norms = torch.linalg.norm(V[:, :d], dim=1)[perm]
-    assert bool((norms[:-1] >= norms[1:] * (1 - 1e-6)).all())             # ... by descending norm
+    # ... by descending norm, to the resolution of the 16-bit sort key (sign, exponent, 7 mantissa bits); catalogues
+    # of >= 8*17 tiles are visited head | stratified sample | rest instead (score_tc.cu::reorder_kernel)
+    assert bool((norms[:-1] >= norms[1:] * (1 - 2.0 ** -7 - 1e-6)).all())
     Uh = (U[users.long(), :d] * su).to(torch.float16).to(torch.float64) / su   # power-of-two rescale + fp16 rounding
     Vh = (V[:, :d] * sv).to(torch.float16).to(torch.float64) / sv
     ref = (Uh @ Vh.T).to(torch.float32)
