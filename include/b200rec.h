@@ -87,6 +87,7 @@ int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int3
 #define B200REC_F_GENERIC 8      /* force the general kernel where the lean d=128/256 fast path would be taken */
 #define B200REC_F_ASYNC_GATHER 16 /* fast path with the deep cp.async (LDGSTS) per-warp row ring */
 #define B200REC_F_ITEM_DELTA_BF16 32 /* with F_ITEM_DELTA: gV is a bf16 [num_items, ld] buffer (REDG.ADD.BF16x4) */
+#define B200REC_F_L2_HINTS 64    /* fast path: user rows evict-first, item rows / item deltas evict-last in L2 */
 
 typedef struct b200rec_bpr_args {
     float *U;              /* [num_users, ld]  user_embedding.weight (models/MF.py:23)   */

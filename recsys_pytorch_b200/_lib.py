@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libb200rec.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SINK_UPDATE, SINK_STAGE, SINK_GRAD, SINK_NONE = 0, 1, 2, 3
-F_USERS_UNIQUE, F_TMA_GATHER, F_ITEM_DELTA, F_GENERIC, F_ASYNC_GATHER, F_ITEM_DELTA_BF16 = 1, 2, 4, 8, 16, 32
-GATHER_FLAGS = {"ldg": 0, "tma": F_TMA_GATHER, "async": F_ASYNC_GATHER, "generic": F_GENERIC}
+F_USERS_UNIQUE, F_TMA_GATHER, F_ITEM_DELTA, F_GENERIC, F_ASYNC_GATHER, F_ITEM_DELTA_BF16, F_L2_HINTS = 1, 2, 4, 8, 16, 32, 64
+GATHER_FLAGS = {"ldg": 0, "tma": F_TMA_GATHER, "async": F_ASYNC_GATHER, "generic": F_GENERIC, "ldg_hints": F_L2_HINTS}
 SCORE_EXACT, SCORE_TC = 0, 1
 
 

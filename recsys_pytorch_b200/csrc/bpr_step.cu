@@ -376,10 +376,13 @@ struct RowSet {
     int tu, ti, tj;
 };
 
-template <int CPL, bool UNIQ, bool LOSS>
+// IDELTA: the two item-row updates go to the dense fp32 item-delta buffer gV (user-sharded multi-GPU layout: one
+// all-reduce of gV per step) instead of V itself.
+template <int CPL, bool UNIQ, bool LOSS, bool IDELTA = false>
 __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) bpr_step_fast_kernel(const BprParams p) {
     float *__restrict__ const U = p.a.U;
     float *__restrict__ const V = p.a.V;
+    float *__restrict__ const VD = IDELTA ? p.a.gV : p.a.V;
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -391,6 +394,10 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) bpr_step_fast_kernel(co
     b200rec_bpr_args a = p.a;                       // private copy: lets the compiler keep fields in registers
     a.out_pos = p.a.out_pos; a.out_neg = p.a.out_neg;
     float loss_local = 0.f;
+    // L2 policy (B200REC_F_L2_HINTS): user rows are touched once per step -> evict first; item rows (and the item
+    // delta buffer) are the reused working set -> evict last
+    const bool hints = (p.a.flags & B200REC_F_L2_HINTS) != 0;
+    const uint64_t pol_u = l2_policy_evict_first(), pol_v = l2_policy_evict_last();
 
     for (int64_t c = warp_global; c < n_chunks; c += n_warps) {
         const int64_t t_lane = c * chunk + lane;
@@ -410,7 +417,16 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) bpr_step_fast_kernel(co
                     const float *pi = V + (int64_t)r.ti * LD + lane * 4;
                     const float *pj = V + (int64_t)r.tj * LD + lane * 4;
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) { r.u[k] = ld4(pu + 128 * k); r.i[k] = ld4(pi + 128 * k); r.j[k] = ld4(pj + 128 * k); }
+                    if (hints) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) {
+                            r.u[k] = ld4_hint(pu + 128 * k, pol_u); r.i[k] = ld4_hint(pi + 128 * k, pol_v);
+                            r.j[k] = ld4_hint(pj + 128 * k, pol_v);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) { r.u[k] = ld4(pu + 128 * k); r.i[k] = ld4(pi + 128 * k); r.j[k] = ld4(pj + 128 * k); }
+                    }
                 }
             }
         };
@@ -429,8 +445,8 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) bpr_step_fast_kernel(co
                 const float a1 = c_g * (1.f - s);                   // = -lr * g
                 if (LOSS) loss_local += (x < -15.f) ? -x : -__logf(s);
                 float *pu = U + (int64_t)r.tu * LD + lane * 4;
-                float *pi = V + (int64_t)r.ti * LD + lane * 4;
-                float *pj = V + (int64_t)r.tj * LD + lane * 4;
+                float *pi = VD + (int64_t)r.ti * LD + lane * 4;
+                float *pj = VD + (int64_t)r.tj * LD + lane * 4;
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
                     float4 du, di, dj;
@@ -440,10 +456,17 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) bpr_step_fast_kernel(co
                     di.z = fmaf(a1, r.u[k].z, c_r * r.i[k].z); di.w = fmaf(a1, r.u[k].w, c_r * r.i[k].w);
                     dj.x = fmaf(-a1, r.u[k].x, c_r * r.j[k].x); dj.y = fmaf(-a1, r.u[k].y, c_r * r.j[k].y);
                     dj.z = fmaf(-a1, r.u[k].z, c_r * r.j[k].z); dj.w = fmaf(-a1, r.u[k].w, c_r * r.j[k].w);
-                    if (UNIQ) st4(pu + 128 * k, make_float4(r.u[k].x + du.x, r.u[k].y + du.y, r.u[k].z + du.z, r.u[k].w + du.w));
-                    else red4(pu + 128 * k, du);
-                    red4(pi + 128 * k, di);
-                    red4(pj + 128 * k, dj);
+                    if (hints) {
+                        if (UNIQ) st4_hint(pu + 128 * k, make_float4(r.u[k].x + du.x, r.u[k].y + du.y, r.u[k].z + du.z, r.u[k].w + du.w), pol_u);
+                        else red4_hint(pu + 128 * k, du, pol_u);
+                        red4_hint(pi + 128 * k, di, pol_v);
+                        red4_hint(pj + 128 * k, dj, pol_v);
+                    } else {
+                        if (UNIQ) st4(pu + 128 * k, make_float4(r.u[k].x + du.x, r.u[k].y + du.y, r.u[k].z + du.z, r.u[k].w + du.w));
+                        else red4(pu + 128 * k, du);
+                        red4(pi + 128 * k, di);
+                        red4(pj + 128 * k, dj);
+                    }
                 }
             }
         };
@@ -746,9 +769,11 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     // lean fast path (see bpr_step_fast_kernel): the plain single-device fused update on full-warp rows
     if (a.sink == B200REC_SINK_UPDATE && G == 32 && d4 == 32 * CPL && CPL <= 2 &&
-        !(a.flags & (B200REC_F_TMA_GATHER | B200REC_F_ITEM_DELTA | B200REC_F_GENERIC)) && !a.udelta &&
-        a.item_hi == a.item_lo && !a.x_out) {
+        !(a.flags & (B200REC_F_TMA_GATHER | B200REC_F_ITEM_DELTA_BF16 | B200REC_F_GENERIC)) && !a.udelta &&
+        a.item_hi == a.item_lo && !a.x_out &&
+        !((a.flags & B200REC_F_ITEM_DELTA) && (a.flags & B200REC_F_ASYNC_GATHER))) {
         const bool uniq = (a.flags & B200REC_F_USERS_UNIQUE) != 0, loss = a.loss_sum != nullptr;
+        const bool idelta = (a.flags & B200REC_F_ITEM_DELTA) != 0;
         if (a.flags & B200REC_F_ASYNC_GATHER) {   // deep cp.async ring (bpr_step_async_kernel)
             const size_t smem = (size_t)8 * 8 * 3 * 512;   // 8 warps x (S*CPL = 8) x 3 rows x 512 B = 96 KB
 #define B200_ASYNC(C, Q, L, SS)                                                                                \
@@ -775,13 +800,17 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
         const int64_t need = (p.n_chunks + 7) / 8;
         const int64_t cap = (int64_t)sm_count() * (CPL == 1 ? 3 : 2);
         const int grid = (int)(need < cap ? need : cap);
-#define B200_FAST(C, Q, L) bpr_step_fast_kernel<C, Q, L><<<grid, 256, 0, s>>>(p)
+#define B200_FAST(C, Q, L)                                                              \
+    {                                                                                   \
+        if (idelta) bpr_step_fast_kernel<C, Q, L, true><<<grid, 256, 0, s>>>(p);        \
+        else bpr_step_fast_kernel<C, Q, L, false><<<grid, 256, 0, s>>>(p);              \
+    }
         if (CPL == 1) {
-            if (uniq) { if (loss) B200_FAST(1, true, true); else B200_FAST(1, true, false); }
-            else { if (loss) B200_FAST(1, false, true); else B200_FAST(1, false, false); }
+            if (uniq) { if (loss) B200_FAST(1, true, true) else B200_FAST(1, true, false) }
+            else { if (loss) B200_FAST(1, false, true) else B200_FAST(1, false, false) }
         } else {
-            if (uniq) { if (loss) B200_FAST(2, true, true); else B200_FAST(2, true, false); }
-            else { if (loss) B200_FAST(2, false, true); else B200_FAST(2, false, false); }
+            if (uniq) { if (loss) B200_FAST(2, true, true) else B200_FAST(2, true, false) }
+            else { if (loss) B200_FAST(2, false, true) else B200_FAST(2, false, false) }
         }
 #undef B200_FAST
         B200_LAUNCH_CHECK();

@@ -425,11 +425,8 @@ __device__ __forceinline__ void tmem_ld_wait64(uint32_t (&r)[64]) {
                  : "memory");
 }
 
-// Cheap threshold raise for K <= 32 (one row at a time, warp-cooperative).  Any tau with at least K clean
-// entries at or above it is a valid lower bound of the exact K-th score, so instead of an exact selection the
-// warp takes the K-th largest of the 32 per-lane maxima of L = S~ - e (K distinct entries by construction;
-// for n >> 32 it is close to the exact K-th largest).  Entries whose upper bound still reaches the new tau are
-// compacted in place.
+// Threshold raise (one row at a time, warp-cooperative, entries held in registers: one round trip to L2).
+// Entries whose upper bound still reaches the new tau are compacted in place.
 template <int TILE, int WM>
 __device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff,
                                            float cu, const float *__restrict__ tile_norm, int lane,
@@ -447,13 +444,14 @@ __device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int
         const unsigned long long *wf =
             reinterpret_cast<const unsigned long long *>(__shfl_sync(0xffffffffu, (unsigned long long)my_wide, Lsrc));
         uint64_t e[E];
-        float hi[E];
+        float hi[E], lo_v[E];   // upper bound of every entry; lower bound of the CLEAN (certainly unmasked) ones
 #pragma unroll
         for (int i = 0; i < E; ++i) e[i] = (lane + 32 * i < n) ? base[lane + 32 * i] : 0ull;   // one round trip
-        float lmax = -INFINITY;
+        float vmin = INFINITY, vmax = -INFINITY;
+        int n_clean = 0;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            hi[i] = -INFINITY;
+            hi[i] = -INFINITY; lo_v[i] = -INFINITY;
             if (lane + 32 * i < n) {
                 const float sc = ord2f((uint32_t)(e[i] >> 32));
                 const float err = c_u * tile_norm[(uint32_t)(e[i] & 0x7FFFFFFFu) / TILE];
@@ -463,19 +461,36 @@ __device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int
                     const uint32_t h2 = wide_hash((uint32_t)e[i] & 0x7FFFFFFFu);
                     e[i] |= (uint64_t)((uint32_t)(wf[1 + (h2 >> 6)] >> (h2 & 63u)) & 1u) << 31;
                 }
-                if (!((uint32_t)e[i] >> 31)) lmax = fmaxf(lmax, sc - err);
+                if (!((uint32_t)e[i] >> 31)) {
+                    lo_v[i] = sc - err;
+                    vmin = fminf(vmin, lo_v[i]); vmax = fmaxf(vmax, lo_v[i]);
+                    ++n_clean;
+                }
             }
         }
-        int rank = 0;   // lanes ordered by (lmax desc, lane asc): a permutation of 0..31
-#pragma unroll
-        for (int o = 1; o < 32; ++o) {
-            const int ol = (lane + o) & 31;
-            const float other = __shfl_sync(0xffffffffu, lmax, ol);
-            rank += (other > lmax || (other == lmax && ol < lane)) ? 1 : 0;
+        // Selection by bisection on the value: any t with at least K clean entries at or above it is a valid
+        // lower bound of the exact K-th score, so 12 halvings of [min, max] of the clean lower bounds (each a
+        // per-lane count + one warp reduction) give the K-th largest to 1/4096 of the range, for any K.
+        for (int o = 16; o > 0; o >>= 1) {
+            vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         }
-        const unsigned sel = __ballot_sync(0xffffffffu, rank == kf - 1);
-        float t_new = __shfl_sync(0xffffffffu, lmax, __ffs(sel) - 1);
-        t_new = (t_new > -INFINITY) ? fmaxf(old_tau, t_new) : old_tau;   // fewer than K lanes hold a clean entry
+        n_clean = __reduce_add_sync(0xffffffffu, n_clean);
+        float t_new = old_tau;
+        if (n_clean >= kf) {
+            float a = vmin, b = vmax;          // invariant: count(lo >= a) >= K
+            if (kf == 1) a = vmax;
+            else
+                for (int it = 0; it < 12; ++it) {
+                    const float mid = 0.5f * a + 0.5f * b;
+                    int c = 0;
+#pragma unroll
+                    for (int i = 0; i < E; ++i) c += (lo_v[i] >= mid) ? 1 : 0;
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (c >= kf) a = mid; else b = mid;
+                }
+            t_new = fmaxf(old_tau, a);
+        }
         // every ballot depends on every lane's loads, so all loads have landed before the first store below
         unsigned kb[E];
 #pragma unroll
@@ -672,7 +687,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (need) {
                 d_raise += __popc(need);
                 const long long c_r0 = p.dbg ? clock64() : 0;
-                raise_thresholds<kBN, kBN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane);
+                raise_fast<kBN, kBN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, lane, nullptr);
                 if (p.dbg) d_rcyc += clock64() - c_r0;
             }
         }
@@ -915,7 +930,7 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (need) {
                 if (DIAG) d_raise += __popc(need);
                 const long long c_r0 = (DIAG && p.dbg) ? clock64() : 0;
-                if (keff <= 32 && !(abl & 16))
+                if (!(abl & 16))
                     raise_fast<kPPN, kPPN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, lane, my_wide);
                 else
                     raise_thresholds<kPPN, kPPN, true>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane, my_wide);

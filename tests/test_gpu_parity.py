@@ -472,13 +472,18 @@ def test_item_delta_bf16_sink_and_apply(dev, d):
     i, j = items[:B], items[B:]
     tu, ti, tj = _ids(dev, u, i, j)
     out = {}
-    for tag, fl, dt in (("f32", F_ITEM_DELTA, torch.float32), ("bf16", F_ITEM_DELTA | F_ITEM_DELTA_BF16, torch.bfloat16)):
+    F_GENERIC = _lib.GATHER_FLAGS["generic"]
+    for tag, fl, dt in (("f32", F_ITEM_DELTA | F_GENERIC, torch.float32), ("fast", F_ITEM_DELTA, torch.float32),
+                        ("bf16", F_ITEM_DELTA | F_ITEM_DELTA_BF16, torch.bfloat16)):
         U, V = _dev_table(U0, dev), _dev_table(V0, dev)
         dV = torch.zeros(V.shape, dtype=dt, device=dev)
         engine.bpr_step(U, V, d, tu, ti, tj, lr=0.9, reg=0.01, sink=SINK_UPDATE, flags=fl | F_USERS_UNIQUE, gV=dV)
         assert torch.equal(V.cpu(), _dev_table(V0, dev).cpu())            # item table untouched, delta is separate
         out[tag] = (U.cpu().numpy(), dV.float().cpu().numpy(), V, dV)
     np.testing.assert_array_equal(out["f32"][0], out["bf16"][0])          # user rows do not depend on the wire dtype
+    # the lean fast-path kernel (d in {128, 256}) writes the same delta buffer up to its fast-math intrinsics
+    np.testing.assert_allclose(out["fast"][0], out["f32"][0], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(out["fast"][1], out["f32"][1], rtol=2e-5, atol=2e-6)
     ref, got = out["f32"][1], out["bf16"][1]
     assert np.all(np.abs(got - ref) <= np.abs(ref) * 2.0 ** -8 + 1e-30)
     _, _, V, dV = out["bf16"]

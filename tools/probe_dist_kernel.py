@@ -34,7 +34,16 @@ def kern_inplace_generic():
 def kern_inplace_fast():
     k[0] += 1
     engine.bpr_step(tr.U, tr.V, d, users, csr=train, lr=tr.lr, reg=tr.reg, flags=_lib.F_USERS_UNIQUE, seed=1, step=k[0])
+def kern_delta_hints():
+    k[0] += 1
+    engine.bpr_step(tr.U, tr.V, d, users, csr=train, lr=tr.lr, reg=tr.reg,
+                    flags=_lib.F_ITEM_DELTA | _lib.F_USERS_UNIQUE | _lib.F_L2_HINTS, seed=1, step=k[0], gV=tr.dV)
+def kern_inplace_fast_hints():
+    k[0] += 1
+    engine.bpr_step(tr.U, tr.V, d, users, csr=train, lr=tr.lr, reg=tr.reg, flags=_lib.F_USERS_UNIQUE | _lib.F_L2_HINTS, seed=1, step=k[0])
 print("kernel, item deltas -> dV  : %.3f ms" % timeit(kern_delta))
+print("kernel, deltas -> dV, hints: %.3f ms" % timeit(kern_delta_hints))
+print("kernel, in place fast+hints: %.3f ms" % timeit(kern_inplace_fast_hints))
 print("kernel, in place (generic) : %.3f ms" % timeit(kern_inplace_generic))
 print("kernel, in place (fast)    : %.3f ms" % timeit(kern_inplace_fast))
 print("dV.zero_()                 : %.3f ms" % timeit(lambda: tr.dV.zero_()))
