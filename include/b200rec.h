@@ -213,6 +213,17 @@ int b200rec_spmm_csr(const int64_t *indptr, const int32_t *indices, const float 
                      int n_rows, const float *X, int ldx, int d, float *Y, int ldy, float *acc,
                      int ldacc, float acc_scale, int acc_init, void *stream);
 
+/* Same product with a plan for LONG rows (popular items have up to ~1e6 neighbours): rows with more than seg_len
+ * nonzeros are cut into segments [seg_begin[s], seg_end[s]) of at most seg_len nonzeros (n_seg of them, grouped by
+ * row: long_rows[r] owns segments long_seg_ptr[r] .. long_seg_ptr[r+1]); `partial` is scratch of
+ * n_seg * roundup(d,4) floats.  Partials are added in segment order: results are deterministic.  n_seg == 0 is
+ * b200rec_spmm_csr.  The plan depends on indptr only (recsys_pytorch_b200.engine.spmm_plan builds it once per graph). */
+int b200rec_spmm_csr_split(const int64_t *indptr, const int32_t *indices, const float *values, int n_rows,
+                           const float *X, int ldx, int d, float *Y, int ldy, float *acc, int ldacc,
+                           float acc_scale, int acc_init, int64_t seg_len, const int64_t *seg_begin,
+                           const int64_t *seg_end, int n_seg, const int32_t *long_rows,
+                           const int32_t *long_seg_ptr, int n_long, float *partial, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ from ._lib import (B200RecError, BprArgs, F_TMA_GATHER, F_USERS_UNIQUE, SCORE_EX
 
 __all__ = ["DeviceCSR", "padded_dim", "alloc_table", "mf_forward", "bpr_step", "bpr_apply", "sample_triples",
            "sgd_dense", "adam_dense", "score_topk", "predict_dense", "topk_rows", "holdout_metrics", "loo_metrics",
-           "column_means", "spmm_csr"]
+           "column_means", "spmm_csr", "spmm_plan", "SpmmPlan"]
 
 
 def padded_dim(d: int) -> int:
@@ -229,10 +229,55 @@ def column_means(mat):
     return out
 
 
-def spmm_csr(indptr, indices, values, X, d, Y=None, acc=None, acc_scale=1.0, acc_init=False):
+class SpmmPlan:
+    """Segments of the long rows of a CSR matrix (see b200rec_spmm_csr_split); depends on indptr only."""
+
+    def __init__(self, indptr, seg_len=256):
+        dev = indptr.device
+        deg = indptr[1:] - indptr[:-1]
+        long_rows = torch.nonzero(deg > seg_len).flatten()
+        self.seg_len = int(seg_len)
+        self.n_long = int(long_rows.numel())
+        self.n_seg = 0
+        self._partial = None
+        if self.n_long == 0:
+            return
+        nseg = (deg[long_rows] + seg_len - 1) // seg_len
+        seg_ptr = torch.zeros(self.n_long + 1, dtype=torch.int64, device=dev)
+        seg_ptr[1:] = torch.cumsum(nseg, 0)
+        self.n_seg = int(seg_ptr[-1].item())
+        owner = torch.repeat_interleave(torch.arange(self.n_long, device=dev), nseg)
+        idx = torch.arange(self.n_seg, device=dev) - seg_ptr[owner]
+        row = long_rows[owner]
+        self.seg_begin = (indptr[row] + idx * seg_len).contiguous()
+        self.seg_end = torch.minimum(self.seg_begin + seg_len, indptr[row + 1]).contiguous()
+        self.long_rows = long_rows.to(torch.int32).contiguous()
+        self.long_seg_ptr = seg_ptr.to(torch.int32).contiguous()
+
+    def partial(self, d, device):
+        need = self.n_seg * ((d + 3) // 4 * 4)
+        if self._partial is None or self._partial.numel() < need:
+            self._partial = torch.empty(max(need, 1), dtype=torch.float32, device=device)
+        return self._partial
+
+
+def spmm_plan(indptr, seg_len=256):
+    return SpmmPlan(indptr, seg_len)
+
+
+def spmm_csr(indptr, indices, values, X, d, Y=None, acc=None, acc_scale=1.0, acc_init=False, plan=None):
     """models/LightGCN.py:196: Y = A X; optionally acc += acc_scale * A X, or with
-    acc_init acc = acc_scale * (X + A X) (start of the running layer mean, :198-200)."""
+    acc_init acc = acc_scale * (X + A X) (start of the running layer mean, :198-200).
+    `plan` (spmm_plan(indptr)) spreads rows longer than plan.seg_len over many sub-groups."""
     n_rows = indptr.numel() - 1
+    if plan is not None and plan.n_seg > 0:
+        check(_lib.lib().b200rec_spmm_csr_split(ptr(indptr), ptr(indices), ptr(values), n_rows, ptr(X), X.shape[1], d,
+                                                ptr(Y), Y.shape[1] if Y is not None else 0, ptr(acc),
+                                                acc.shape[1] if acc is not None else 0, float(acc_scale),
+                                                int(bool(acc_init)), plan.seg_len, ptr(plan.seg_begin), ptr(plan.seg_end),
+                                                plan.n_seg, ptr(plan.long_rows), ptr(plan.long_seg_ptr), plan.n_long,
+                                                ptr(plan.partial(d, X.device)), current_stream()))
+        return Y
     check(_lib.lib().b200rec_spmm_csr(ptr(indptr), ptr(indices), ptr(values), n_rows, ptr(X), X.shape[1], d,
                                       ptr(Y), Y.shape[1] if Y is not None else 0, ptr(acc),
                                       acc.shape[1] if acc is not None else 0, float(acc_scale), int(bool(acc_init)),

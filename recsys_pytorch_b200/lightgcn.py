@@ -106,6 +106,8 @@ class LightGCN(MF):
     def propagate(self, src, dst):
         """dst = mean_{l=0..L} A_hat^l src  (LightGCN.py:174-202).  2L reads/writes of an [N, ld] table."""
         indptr, cols, vals = self.Graph
+        if getattr(self, "_plan_for", None) is not indptr:          # long rows (popular items) are split: plan per graph
+            self._plan, self._plan_for = engine.spmm_plan(indptr), indptr
         L, d = self.num_layers, self.emb_dim
         s = 1.0 / (L + 1)
         if L == 0:
@@ -115,7 +117,7 @@ class LightGCN(MF):
         for layer in range(L):
             nxt = self._tmp[layer & 1]
             engine.spmm_csr(indptr, cols, vals, cur, d, Y=nxt if layer + 1 < L else None, acc=dst, acc_scale=s,
-                            acc_init=(layer == 0))
+                            acc_init=(layer == 0), plan=self._plan)
             cur = nxt
         return dst
 

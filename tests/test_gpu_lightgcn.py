@@ -72,3 +72,39 @@ def test_lightgcn_plugin_fit_runs_and_scores(golden, dev):
     top = np.argsort(-pred[:5], 1)[:, :10]
     idx = m.predict_topk(np.arange(5), ds.train_data, 10)
     assert (np.sort(top, 1) == np.sort(idx, 1)).mean() > 0.9
+
+
+@pytest.mark.parametrize("d", [64, 50, 128, 200, 8])
+def test_spmm_split_long_rows_matches_plain_and_fp64(dev, d):
+    """b200rec_spmm_csr_split: rows longer than seg_len are cut into segments (popular items have ~1e6 neighbours
+    at cfg4); same result as the plain kernel and as an fp64 product, for Y, the running mean and its init."""
+    rng = np.random.default_rng(d)
+    n_rows, n_cols = 700, 900
+    deg = rng.integers(0, 40, n_rows)
+    deg[[3, 77, 500]] = [5000, 257, 1024]                        # long rows, incl. one segment boundary case
+    deg[10] = 0
+    indptr = np.zeros(n_rows + 1, np.int64); indptr[1:] = np.cumsum(deg)
+    cols = rng.integers(0, n_cols, int(indptr[-1])).astype(np.int32)
+    vals = rng.standard_normal(int(indptr[-1])).astype(np.float32)
+    ld = (d + 3) // 4 * 4
+    X = torch.zeros((n_cols, ld), device=dev); X[:, :d] = torch.from_numpy(rng.standard_normal((n_cols, d)).astype(np.float32)).to(dev)
+    ip, cc, vv = (torch.from_numpy(a).to(dev) for a in (indptr, cols, vals))
+    plan = engine.spmm_plan(ip, seg_len=256)
+    assert plan.n_long == 3 and plan.n_seg == 20 + 2 + 4
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vals.astype(np.float64), cols, indptr), shape=(n_rows, n_cols))
+    ref = A @ X[:, :d].double().cpu().numpy()
+    Xr = np.zeros((n_rows, d)); Xr[:min(n_rows, n_cols)] = X[:n_rows, :d].double().cpu().numpy()[:min(n_rows, n_cols)]
+    for use_plan in (None, plan):
+        Y = torch.full((n_rows, ld), 7.0, device=dev)
+        acc = torch.full((n_rows, ld), 3.0, device=dev)
+        engine.spmm_csr(ip, cc, vv, X, d, Y=Y, acc=acc, acc_scale=0.25, acc_init=False, plan=use_plan)
+        np.testing.assert_allclose(Y[:, :d].cpu().numpy(), ref, rtol=2e-5, atol=2e-4)
+        np.testing.assert_allclose(acc[:, :d].cpu().numpy(), 3.0 + 0.25 * ref, rtol=2e-5, atol=2e-4)
+        acc2 = torch.full((n_rows, ld), 9.0, device=dev)
+        engine.spmm_csr(ip, cc, vv, X, d, Y=None, acc=acc2, acc_scale=0.5, acc_init=True, plan=use_plan)   # square part only
+        np.testing.assert_allclose(acc2[:, :d].cpu().numpy(), 0.5 * (Xr + ref), rtol=2e-5, atol=2e-4)
+    # deterministic: segment partials are added in order
+    Y1 = torch.empty((n_rows, ld), device=dev); Y2 = torch.empty((n_rows, ld), device=dev)
+    engine.spmm_csr(ip, cc, vv, X, d, Y=Y1, plan=plan); engine.spmm_csr(ip, cc, vv, X, d, Y=Y2, plan=plan)
+    assert torch.equal(Y1[:, :d], Y2[:, :d])
