@@ -376,10 +376,13 @@ struct RowSet {
     int tu, ti, tj;
 };
 
+#ifndef B200REC_FAST_MINB
+#define B200REC_FAST_MINB 3
+#endif
 // IDELTA: the two item-row updates go to the dense fp32 item-delta buffer gV (user-sharded multi-GPU layout: one
 // all-reduce of gV per step) instead of V itself.
 template <int CPL, bool UNIQ, bool LOSS, bool IDELTA = false>
-__global__ void __launch_bounds__(256, CPL == 1 ? 3 : 2) bpr_step_fast_kernel(const BprParams p) {
+__global__ void __launch_bounds__(256, CPL == 1 ? B200REC_FAST_MINB : 2) bpr_step_fast_kernel(const BprParams p) {
     float *__restrict__ const U = p.a.U;
     float *__restrict__ const V = p.a.V;
     float *__restrict__ const VD = IDELTA ? p.a.gV : p.a.V;
@@ -798,7 +801,7 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
             return B200REC_OK;
         }
         const int64_t need = (p.n_chunks + 7) / 8;
-        const int64_t cap = (int64_t)sm_count() * (CPL == 1 ? 3 : 2);
+        const int64_t cap = (int64_t)sm_count() * (CPL == 1 ? B200REC_FAST_MINB : 2);
         const int grid = (int)(need < cap ? need : cap);
 #define B200_FAST(C, Q, L)                                                              \
     {                                                                                   \
