@@ -1012,6 +1012,19 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
                     float acc = 0.f;
                     int kk = 0;
                     if ((ld & 3) == 0) {  // 16-byte row pieces; the FMA chain stays in ascending k (the oracle's order)
+                        // 16 loads in flight per lane, then their 64 FMAs: 2 round trips to L2 per 128 columns
+                        // instead of one per unrolled iteration
+                        for (; kk + 64 <= d; kk += 64) {
+                            float4 y[16];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) y[q] = __ldg(reinterpret_cast<const float4 *>(pv + kk + 4 * q));
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const float4 x = *reinterpret_cast<const float4 *>(us + kk + 4 * q);
+                                acc = fmaf(x.x, y[q].x, acc); acc = fmaf(x.y, y[q].y, acc);
+                                acc = fmaf(x.z, y[q].z, acc); acc = fmaf(x.w, y[q].w, acc);
+                            }
+                        }
                         for (; kk + 4 <= d; kk += 4) {
                             const float4 x = *reinterpret_cast<const float4 *>(us + kk);
                             const float4 y = __ldg(reinterpret_cast<const float4 *>(pv + kk));
@@ -1357,10 +1370,23 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         const size_t rsmem = (size_t)8 * k * 8 + (size_t)8 * ((d + 3) & ~3) * 4;
         B200_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         int rgrid = (nr + 7) / 8;
-        if (rgrid > sms * 8) rgrid = sms * 8;
+        {   // whole waves of resident CTAs (registers decide how many fit), rows are grid-strided
+            int occ = 0;
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rerank_kernel, 256, rsmem));
+            if (occ < 1) occ = 1;
+            if (rgrid > sms * occ) rgrid = sms * occ;
+        }
+        cudaEvent_t er0 = nullptr, er1 = nullptr;
+        if (diag) { cudaEventCreate(&er0); cudaEventCreate(&er1); cudaEventRecord(er0, s); }
         rerank_kernel<<<rgrid, 256, rsmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, order, cand, cnt,
                                                 oi + (size_t)r0 * k, os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
         B200_LAUNCH_CHECK();
+        if (diag) {
+            cudaEventRecord(er1, s); cudaEventSynchronize(er1);
+            float ms = 0.f; cudaEventElapsedTime(&ms, er0, er1);
+            fprintf(stderr, "[b200rec tc] rerank kernel rows=%d: %.3f ms\n", nr, ms);
+            cudaEventDestroy(er0); cudaEventDestroy(er1);
+        }
         int n_redo = 0;
         B200_CUDA(cudaMemcpyAsync(&n_redo, redo_n, 4, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaStreamSynchronize(s));

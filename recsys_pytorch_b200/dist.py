@@ -54,6 +54,43 @@ def allreduce_sum(t):
     return t
 
 
+def allgather_rows(shard, total_rows: int, world: int, rank: int):
+    """Full [total_rows, ld] table from its contiguous row shards (shard_range), identical on every rank: ONE
+    all-gather, used once per evaluation to give every GPU the whole item table (SURVEY section 8(e) "Scoring").
+    Shards may differ by one row: they are padded to the largest shard for the collective."""
+    ld = shard.shape[1]
+    sizes = [shard_range(total_rows, world, r)[1] - shard_range(total_rows, world, r)[0] for r in range(world)]
+    assert shard.shape[0] == sizes[rank], "shard does not match shard_range"
+    if world == 1 or not dist.is_initialized():
+        return shard
+    mx = max(sizes)
+    send = shard if sizes[rank] == mx else torch.cat([shard, shard.new_zeros((mx - sizes[rank], ld))])
+    parts = [shard.new_empty((mx, ld)) for _ in range(world)]
+    dist.all_gather(parts, send.contiguous())
+    return torch.cat([parts[r][:sizes[r]] for r in range(world)])
+
+
+def evaluate_user_shard(U, V, d, users, mask, truth, ks, protocol="holdout", row_ids=None, algo=None):
+    """Scoring + masked top-K + metrics for THIS rank's users (no collective on the data path: users are independent),
+    then one tiny all-reduce of the metric sums.  `users` index rows of U; `mask` / `truth` are DeviceCSRs whose rows
+    are addressed by `row_ids` (default: `users`).  Returns ({metric@k: global mean}, n_users_global)."""
+    from ._lib import SCORE_TC
+    ks = sorted(ks)
+    metrics = ("Prec", "Recall", "NDCG") if protocol == "holdout" else ("HR", "NDCG")
+    fn = engine.holdout_metrics if protocol == "holdout" else engine.loo_metrics
+    sums = torch.zeros(len(metrics) * len(ks) + 1, dtype=torch.float64, device=U.device)
+    if users.numel() > 0:
+        idx, _ = engine.score_topk(U, V, d, users, mask, max(ks), algo=SCORE_TC if algo is None else algo)
+        rows = fn(idx, truth, ks, row_ids=users if row_ids is None else row_ids)
+        sums[:-1] = rows.double().sum(0)
+        sums[-1] = users.numel()
+    allreduce_sum(sums)
+    n = int(sums[-1].item())
+    means = (sums[:-1] / max(n, 1)).cpu().numpy()
+    nk = len(ks)
+    return {"%s@%d" % (m, k): float(means[i * nk + j]) for i, m in enumerate(metrics) for j, k in enumerate(ks)}, n
+
+
 class ItemShardedBPR:
     """north_star layout.  `train` is the GLOBAL DeviceCSR of positives (replicated)."""
 
@@ -92,6 +129,13 @@ class ItemShardedBPR:
         ud = self.local_compute(users, step_key, loss_sum, out_pos, out_neg)
         allreduce_sum(ud)                                                          # the ONE collective of the step
         self.apply_user_delta(users, ud)
+
+    def evaluate(self, eval_users, truth, ks, protocol="holdout"):
+        """Evaluation: ONE all-gather of the item shards, then every rank scores its contiguous slice of
+        `eval_users` (global ids, same tensor on every rank) against the full table; metric sums are all-reduced."""
+        V_full = allgather_rows(self.V, self.num_items, self.world, self.rank)
+        lo, hi = shard_range(eval_users.numel(), self.world, self.rank)
+        return evaluate_user_shard(self.U, V_full, self.d, eval_users[lo:hi].contiguous(), self.train, truth, ks, protocol)
 
 
 class UserShardedBPR:
@@ -167,6 +211,12 @@ class UserShardedBPR:
         ov["pending"] = cur
         ov["n"] += 1
 
+    def evaluate(self, eval_users_local, truth_local, ks, protocol="holdout"):
+        """Evaluation: the item table is already replicated, every rank scores its own users (local row
+        ids of this rank's shard; `truth_local` rows are local too); metric sums are all-reduced."""
+        self.flush()
+        return evaluate_user_shard(self.U, self.V, self.d, eval_users_local, self.train, truth_local, ks, protocol)
+
     def flush(self):
         ov = getattr(self, "_ov", None)
         if ov and ov["pending"] is not None:
@@ -208,7 +258,7 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
         coll = "all_reduce(sum) of the [B, ld] fp32 user-delta buffer (%d MiB) per step" % (B_glob * wire >> 20)
     else:
         ulo, uhi = shard_range(nu, world, rank)
-        train, _ = synthetic.make_interactions(uhi - ulo, ni, seed=c["seed"] + rank, device=dev)
+        train, target = synthetic.make_interactions(uhi - ulo, ni, seed=c["seed"] + rank, device=dev)
         tr = UserShardedBPR(nu, ni, d, train, rank, world, dev, lr=c["lr"], reg=c["reg"], init_std=c["init_std"],
                             seed=c["seed"], gather=args.gather, wire_dtype=getattr(args, "wire", "fp32"))
         g = torch.Generator(device=dev); g.manual_seed(c["seed"] + rank)
@@ -262,6 +312,23 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
     for s in range(2):
         step_e2e(s)
     ms_e2e = timed_region(step_e2e, args.steps, world)
+    # evaluation leg: users are independent - every rank scores the same number of its OWN users against
+    # the replicated item table (weak scaling), no collective on the data path, one all-reduce of the metric sums
+    eval_leg = None
+    if layout == "user_sharded":
+        n_ev = min(int(c["eval_users"]), uhi - ulo)
+        ev_users = torch.arange(n_ev, dtype=torch.int32, device=dev)
+        tr.evaluate(ev_users, target, [c["eval_k"]])                                  # warm-up
+        res = {}
+
+        def ev_step(s):
+            res["scores"], res["n"] = tr.evaluate(ev_users, target, [c["eval_k"]])
+        ms_ev = timed_region(ev_step, 3, world) / 3
+        eval_leg = {"scored_pairs_per_sec": float(res["n"]) * ni / (ms_ev * 1e-3), "ms": ms_ev,
+                    "ndcg@%d" % c["eval_k"]: res["scores"]["NDCG@%d" % c["eval_k"]], "users": res["n"],
+                    "k": c["eval_k"], "algo": "tc", "flops_per_pair": 2 * d,
+                    "note": "whole evaluate() per rank incl. metrics and the metric all-reduce; users sharded, item "
+                            "table replicated"}
     if rank == 0:
         val = B_glob * args.steps / (ms * 1e-3)
         bpt = 24 * d + 8
@@ -283,6 +350,8 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
                             "note": "per-GPU algorithmic bytes of the step kernel over the WHOLE step time "
                                     "(collective included)"},
                "cpu_baseline": None}
+        if eval_leg is not None:
+            out["eval"] = eval_leg
         if secondary is not None:
             out["north_star_item_sharded"] = secondary
         print(json.dumps(out))

@@ -44,6 +44,21 @@ def main():
     chk = tu.V.double().sum().reshape(1)
     dist.all_gather(both, chk)
     assert all(torch.equal(b, both[0]) for b in both), "item replicas diverged (overlapped steps)"
+    # evaluation: item-sharded = one all-gather of the item shards + user slices; user-sharded = local users
+    from recsys_pytorch_b200 import engine
+    from recsys_pytorch_b200.dist import allgather_rows, evaluate_user_shard
+    _, truth = synthetic.make_interactions(nu, ni, seed=1, device=dev)      # any CSR over the global users works as truth
+    ev_users = torch.arange(4000, dtype=torch.int32, device=dev)
+    got, n = tr.evaluate(ev_users, truth, [10])
+    assert n == 4000
+    V_full = allgather_rows(tr.V, ni, world, rank)
+    idx, _ = engine.score_topk(tr.U, V_full, d, ev_users, train, 10)
+    ref = float(engine.holdout_metrics(idx, truth, [10], row_ids=ev_users)[:, 2].double().mean())
+    assert abs(got["NDCG@10"] - ref) < 1e-6, (got, ref)
+    _, truth_l = synthetic.make_interactions(uhi - ulo, ni, seed=2 + rank, device=dev)
+    ev_l = torch.arange(min(3000, uhi - ulo), dtype=torch.int32, device=dev)
+    got_u, n_u = tu.evaluate(ev_l, truth_l, [10])
+    assert n_u == world * ev_l.numel() and 0.0 <= got_u["NDCG@10"] <= 1.0
     dist.barrier()
     if rank == 0:
         print("DIST_OK")

@@ -66,6 +66,34 @@ def test_gloo_world2_user_delta_exchange():
     assert abs(res[0][2] - res[1][2]) < 1e-6           # every replica ends with the same buffer
 
 
+def _gloo_gather_worker(rank, world, port, q):
+    """allgather_rows on CPU with uneven shards: every rank ends with the whole table, rows in id order."""
+    import torch.distributed as dist
+    from recsys_pytorch_b200.dist import allgather_rows, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, ld = 11, 4                                          # 11 rows over 2 ranks: shards of 5 and 6
+    full = torch.arange(n * ld, dtype=torch.float32).reshape(n, ld)
+    lo, hi = shard_range(n, world, rank)
+    got = allgather_rows(full[lo:hi].clone(), n, world, rank)
+    q.put((rank, bool(torch.equal(got, full)), 0.0))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_allgather_rows_uneven_shards():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok, _ in res)
+
+
 # ---- GPU: both layouts emulated rank by rank on one device, checked against the oracle ----
 def _csr(rng, nu, ni, lo, hi, dev):
     from recsys_pytorch_b200 import engine
@@ -143,6 +171,34 @@ def test_user_sharded_equals_single_device_oracle(dev):
     np.testing.assert_allclose(np.concatenate([r.U.cpu().numpy() for r in ranks]), Ur, rtol=2e-5, atol=2e-6)
     for tr in ranks:
         np.testing.assert_allclose(tr.V.cpu().numpy(), Vr, rtol=2e-5, atol=2e-6)   # deltas from pre-step V: exact
+
+
+@pytest.mark.gpu
+def test_sharded_evaluation_matches_evaluator(dev):
+    """SURVEY 8(e) scoring: users are independent units - the per-shard metric sums add up to the Evaluator's means."""
+    from recsys_pytorch_b200 import engine
+    from recsys_pytorch_b200.dist import evaluate_user_shard, shard_range
+    rng = np.random.default_rng(3)
+    nu, ni, d = 600, 900, 32
+    _, train = _csr(rng, nu, ni, 1, 30, dev)
+    _, truth = _csr(rng, nu, ni, 1, 6, dev)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    U = engine.alloc_table(nu, d, dev, 0.5, g); V = engine.alloc_table(ni, d, dev, 0.5, g)
+    users = torch.arange(nu, dtype=torch.int32, device=dev)
+    whole, n = evaluate_user_shard(U, V, d, users, train, truth, [5, 10])
+    assert n == nu
+    sums = {k: 0.0 for k in whole}
+    for r in range(3):                                     # three "ranks": contiguous user slices
+        lo, hi = shard_range(nu, 3, r)
+        part, m = evaluate_user_shard(U, V, d, users[lo:hi].contiguous(), train, truth, [5, 10])
+        assert m == hi - lo
+        for k in part:
+            sums[k] += part[k] * m
+    for k in whole:
+        assert abs(sums[k] / nu - whole[k]) < 1e-6
+    idx, _ = engine.score_topk(U, V, d, users, train, 10)
+    rows = engine.holdout_metrics(idx, truth, [5, 10], row_ids=users)
+    np.testing.assert_allclose([whole["NDCG@10"]], [float(rows[:, 5].double().mean())], rtol=1e-6)
 
 
 @pytest.mark.gpu
