@@ -824,6 +824,7 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int cnt = 0, stalls = 0, napp = 0;
         const int keff = p.k;
         const int budget = p.append_budget;
+        const int raise_at = min(kCand - kPPN - 1, max(64, (5 * keff) / 2));
         float tau = -INFINITY, cu = 0.f;
         const unsigned long long *my_wide = (p.wide && row_ok) ? p.wide + (size_t)row * kWideWords : nullptr;
         if (row_ok) {
@@ -925,8 +926,9 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(s32(tempty + h));
             filter_chunk(rb, thr, n0 + 192);
-            // a full tile (256 appends) must always fit: raise when fewer than 256 slots are left
-            const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kPPN - 1);
+            // a full tile (256 appends) must always fit, and a stale tau costs appends (~100 cycles of the whole warp
+            // each): raise as soon as the list holds ~2.5 K entries (>= 64), at the latest with 256 slots left
+            const unsigned need = __ballot_sync(0xffffffffu, cnt > raise_at);
             if (need) {
                 if (DIAG) d_raise += __popc(need);
                 const long long c_r0 = (DIAG && p.dbg) ? clock64() : 0;
