@@ -428,8 +428,8 @@ __device__ __forceinline__ void tmem_ld_wait64(uint32_t (&r)[64]) {
 // Threshold raise (one row at a time, warp-cooperative, entries held in registers: one round trip to L2).
 // Entries whose upper bound still reaches the new tau are compacted in place.
 template <int TILE, int WM>
-__device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff,
-                                           float cu, const float *__restrict__ tile_norm, int lane,
+__device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &my_raise_at,
+                                           int keff, float cu, const float *__restrict__ tile_norm, int lane,
                                            const unsigned long long *my_wide) {
     constexpr int E = kCand / 32;
     while (need) {
@@ -503,9 +503,188 @@ __device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int
         }
         __syncwarp();
         if (lane == Lsrc) {
-            stalls = (n - total < 48) ? stalls + 1 : 0;
-            if (total > kCand - WM - 32 || stalls >= 3) { cnt = -1; tau = INFINITY; }
-            else { cnt = total; tau = t_new; }
+            // a list that stays long (many maybe-masked entries of a heavy user cannot be dropped) gets a later
+            // trigger instead of a raise on every tile; past the hard limit the exact kernel re-does the row
+            if (total > kCand - WM - 48) { cnt = -1; tau = INFINITY; }
+            else {
+                cnt = total; tau = t_new;
+                if (total + 48 > my_raise_at) my_raise_at = min(kCand - WM - 1, total + 48);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogue shared by both candidate kernels: thread == user row (warps 2-5 own M half 0, warps 6-9 half 1).
+// PP = true : N=256 ping-pong kernel - one TILE-column accumulator per half, barriers indexed by the half.
+// PP = false: N=128 kernel - two stages of a pair of TILE-column accumulators, barriers indexed by the stage.
+// TMEM loads are software-pipelined (two 64-column register buffers): the load of chunk c+1 is in flight while
+// chunk c is filtered, and the accumulator is handed back to the MMA warp as soon as the last load has landed -
+// the filtering of the last chunk and any threshold raise run while the tensor core already works on the next tile.
+// ---------------------------------------------------------------------------------------------------
+template <int TILE, bool PP, bool DUMP, bool DIAG>
+__device__ __forceinline__ void tc_epilogue(const TcParams &p, const int row0, const int n_tiles, const int warp,
+                                            const int lane, const uint32_t tmem_base, uint64_t *tfull, uint64_t *tempty,
+                                            int *hist_all) {
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int h = ew >> 2;            // M half
+    const int r_local = h * 128 + q * 32 + lane;
+    const int row = row0 + r_local;
+    const bool row_ok = row < p.n_rows;
+    int *hist = hist_all + ew * 32;
+    uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
+    const float *__restrict__ tile_norm = p.tile_norm;
+    const uint32_t num_items = (uint32_t)p.num_items;
+    int cnt = 0, stalls = 0, napp = 0;
+    const int keff = p.k;
+    const int budget = p.append_budget;
+    int raise_at = min(kCand - TILE - 1, max(64, (5 * keff) / 2));   // per row: moves up when the list stays long
+    float tau = -INFINITY, cu = 0.f;
+    const unsigned long long *my_wide = (p.wide && row_ok) ? p.wide + (size_t)row * kWideWords : nullptr;
+    if (row_ok) {
+        const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;
+        cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);
+    } else {
+        tau = INFINITY;
+    }
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * TILE;   // + stage offset (N=128 kernel)
+    const int abl = DIAG ? p.ablate : 0;
+    unsigned long long d_app = 0, d_raise = 0, d_hit = 0, d_chunks = 0;
+    long long d_wait = 0, d_rcyc = 0, d_acyc = 0;
+    const long long c_start = DIAG ? clock64() : 0;
+    uint32_t ra[64], rb[64];
+    // one 64-column chunk: FMNMX3 max tree against the row threshold.  Survivors of a hit group are appended
+    // branch-free: every element is stored at the current slot and the slot only advances for a survivor (the
+    // "maybe masked" bit is filled in lazily by the raise; the re-rank does the exact mask test anyway).
+    auto filter_chunk = [&](const uint32_t (&r)[64], const float thr, const uint32_t pos0) {
+        if (DUMP) {
+            float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * TILE) + pos0;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) dst[j] = __uint_as_float(r[j]);
+        }
+        if (abl & 2) return;
+        float gm[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float a = max3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+            const float b = max3(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+            gm[g] = max3(a, b, fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+        }
+        const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
+        if (m >= thr && cnt >= 0 && !(abl & 1)) {
+            const int c_in = cnt;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                if (gm[g] >= thr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float sc = __uint_as_float(r[8 * g + j]);
+                        const uint32_t pos = pos0 + 8 * g + j;
+                        my_cand[cnt] = ((uint64_t)f2ord(sc) << 32) | pos;
+                        cnt += (sc >= thr && pos < num_items) ? 1 : 0;
+                    }
+                }
+            }
+            napp += cnt - c_in;
+        }
+    };
+    for (int t = 0; t < n_tiles; ++t) {
+        float thr = tau - cu * tile_norm[t];   // tau only moves at the end of a tile (and in the bootstrap)
+        const long long c_w0 = (DIAG && p.dbg) ? clock64() : 0;
+        const uint32_t bsel = PP ? (uint32_t)h : ((uint32_t)t & 1u);           // barrier / accumulator stage of tile t
+        const uint32_t bpar = PP ? ((uint32_t)t & 1u) : (((uint32_t)t >> 1) & 1u);
+        const uint32_t ta = PP ? lane_addr : lane_addr + bsel * 2 * TILE;
+        mbar_wait(s32(tfull + bsel), bpar);
+        if (DIAG && p.dbg) d_wait += clock64() - c_w0;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (abl & 4) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s32(tempty + bsel));
+            continue;
+        }
+        const uint32_t n0 = (uint32_t)t * TILE;
+        {
+        tmem_ld64_async(ta, ra);
+        tmem_ld_wait64(ra);
+        if (t == 0 && keff <= 32 && !(abl & 128)) {
+            // Bootstrap (all 32 rows of the warp at once, in registers): tau0 = K-th largest lower bound among
+            // the certainly-unmasked items of the first chunk - the 64 items of largest norm.  Without it every
+            // row would append all of tile 0 and need a warp-cooperative raise at the same moment.
+            const float e0 = cu * tile_norm[0];
+            const unsigned long long head = my_wide ? my_wide[0] : 0ull;   // exact mask bitmap of positions 0..63
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                rb[j] = (((head >> j) & 1ull) || (uint32_t)j >= num_items) ? 0xFF800000u : ra[j];
+            float prev = INFINITY;
+            for (int r = 0; r < keff; ++r) {   // r-th largest distinct value (duplicates only lower the bound)
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const float w = __uint_as_float(rb[j]);
+                    m = fmaxf(m, w < prev ? w : -INFINITY);
+                }
+                prev = m;
+            }
+            if (row_ok && prev > -INFINITY) { tau = prev - e0; thr = tau - e0; }
+        }
+#pragma unroll
+        for (int c = 0; c < TILE / 64; c += 2) {                 // ra holds chunk c (landed)
+            tmem_ld64_async(ta + 64 * (c + 1), rb);
+            filter_chunk(ra, thr, n0 + 64 * c);
+            tmem_ld_wait64(rb);
+            if (c + 2 < TILE / 64) {
+                tmem_ld64_async(ta + 64 * (c + 2), ra);
+                filter_chunk(rb, thr, n0 + 64 * (c + 1));
+                tmem_ld_wait64(ra);
+            }
+        }
+        }
+        // every TMEM read of this warp for tile t has landed: hand the accumulator back
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s32(tempty + bsel));
+        filter_chunk(rb, thr, n0 + TILE - 64);
+        // a full tile (256 appends) must always fit, and a stale tau costs appends (~100 cycles of the whole warp
+        // each): raise as soon as the list holds ~2.5 K entries (>= 64), at the latest with 256 slots left
+        const unsigned need = __ballot_sync(0xffffffffu, cnt > raise_at);
+        if (need) {
+            if (DIAG) d_raise += __popc(need);
+            const long long c_r0 = (DIAG && p.dbg) ? clock64() : 0;
+            if (!(abl & 16))
+                raise_fast<TILE, TILE>(need, my_cand, cnt, tau, raise_at, keff, cu, tile_norm, lane, my_wide);
+            else
+                raise_thresholds<TILE, TILE, true>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane, my_wide);
+            if (DIAG && p.dbg) d_rcyc += clock64() - c_r0;
+        }
+        // a row that keeps beating its own threshold (scores rising along the sweep: a user anti-aligned with
+        // the popularity direction) would drag its warp through the append path on every chunk: hand it to the
+        // exact kernel instead
+        if (napp > budget && cnt >= 0) { cnt = -1; tau = INFINITY; }
+    }
+    if (DIAG) d_app = (unsigned long long)napp;
+    if (row_ok) p.cand_cnt[row] = cnt;
+    if (DIAG && p.dbg_row && row_ok) {
+        float *w = p.dbg_row + (size_t)row * 4;
+        w[0] = (float)d_app; w[1] = (float)cnt; w[2] = tau; w[3] = cu;
+    }
+    if (DIAG && p.dbg) {
+        atomicAdd(p.dbg + 0, d_app);
+        if (lane == 0) {
+            atomicAdd(p.dbg + 1, d_raise); atomicAdd(p.dbg + 2, d_hit); atomicAdd(p.dbg + 3, d_chunks);
+            atomicAdd(p.dbg + 4, (unsigned long long)d_wait); atomicAdd(p.dbg + 5, (unsigned long long)d_rcyc);
+            atomicAdd(p.dbg + 6, (unsigned long long)d_acyc);
+            atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - c_start));
+            if (p.dbg_warp) {
+                unsigned long long *w = p.dbg_warp + ((size_t)blockIdx.x * kEpiWarps + ew) * 4;
+                w[0] = (unsigned long long)(clock64() - c_start); w[1] = (unsigned long long)d_wait;
+                w[2] = (unsigned long long)d_rcyc; w[3] = d_raise;
+            }
+            atomicMax(p.dbg + 8, (unsigned long long)(clock64() - c_start));
+            atomicMax(p.dbg + 9, (unsigned long long)d_rcyc);
+            atomicMax(p.dbg + 10, (unsigned long long)d_wait);
+            atomicMax(p.dbg + 11, (unsigned long long)d_raise);
         }
     }
 }
@@ -556,7 +735,6 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % n_stages, ph = (it / n_stages) & 1u;
                     mbar_wait(s32(empty + s), ph ^ 1u);
-                    if ((p.ablate & 8) && it >= (uint32_t)n_stages) { mbar_arrive(s32(full + s)); continue; }
                     mbar_expect_tx(s32(full + s), kBN * 128);
                     tma_load_2d(s32(smB + (size_t)s * kBN * 128), &tmB, kb * kBK, t * kBN, s32(full + s));
                 }
@@ -591,125 +769,8 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // ================= epilogue: thread == user row =================
-        const int ew = warp - 2;
-        const int q = warp & 3;            // TMEM lane quadrant this warp may touch
-        const int h = ew >> 2;             // M half
-        const int r_local = h * 128 + q * 32 + lane;
-        const int row = row0 + r_local;
-        const bool row_ok = row < p.n_rows;
-        int *hist = hist_all + ew * 32;
-        uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
-        const float *__restrict__ tile_norm = p.tile_norm;
-        const int num_items = p.num_items;
-        int cnt = 0, stalls = 0;
-        const int keff = p.k;
-        float tau = -INFINITY, cu = 0.f;
-        // 128-bit "maybe masked" filter of this row: one bit per hashed sorted-position of a train positive
-        // (no false negatives).  Flagged candidates are kept but never counted towards the K items behind tau.
-        uint64_t f_lo = 0, f_hi = 0;
-        if (row_ok) {
-            if (p.bloom) {
-                const uint4 bw = p.bloom[row];
-                f_lo = (uint64_t)bw.x | ((uint64_t)bw.y << 32);
-                f_hi = (uint64_t)bw.z | ((uint64_t)bw.w << 32);
-            }
-            const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;   // 2^-10 (+5%) + fp32 accumulation slack
-            cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);         // error bound per unit item norm, scaled domain
-        } else {
-            tau = INFINITY;
-        }
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kBN;
-        const int abl = p.ablate;
-        unsigned long long d_app = 0, d_raise = 0, d_hit = 0, d_chunks = 0;
-        long long d_wait = 0, d_rcyc = 0, d_acyc = 0;
-        const long long c_start = clock64();
-        for (int t = 0; t < n_tiles; ++t) {
-            const uint32_t as = t & 1, aph = (t >> 1) & 1u;
-            const float thr = tau - cu * tile_norm[t];   // keep S~ with S~ + e_t >= tau
-            const long long c_w0 = p.dbg ? clock64() : 0;
-            mbar_wait(s32(tfull + as), aph);
-            if (p.dbg) d_wait += clock64() - c_w0;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (abl & 4) {
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s32(tempty + as));
-                continue;
-            }
-            const int n0 = t * kBN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < kBN; c0 += 64) {
-                float v[64];
-                tmem_ld64(lane_addr + as * 2 * kBN + c0, v);
-                if (c0 == kBN - 64) {
-                    // every TMEM read of this warp for tile t has landed: hand the accumulator pair back
-                    // before filtering the last half
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(s32(tempty + as));
-                }
-                if (DUMP) {
-                    float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * kBN) + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 64; ++j) dst[j] = v[j];
-                }
-                if (abl & 2) continue;
-                float gm[8];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float a = max3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
-                    const float b = max3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
-                    gm[g] = max3(a, b, fmaxf(v[8 * g + 6], v[8 * g + 7]));
-                }
-                const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
-                if (m >= thr && cnt >= 0 && !(abl & 1)) {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        if (gm[g] >= thr) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float s = v[8 * g + j];
-                                const uint32_t pos = (uint32_t)(n0 + c0 + 8 * g + j);
-                                if (s >= thr && pos < (uint32_t)num_items) {
-                                    const uint32_t hsh = (pos * 2654435761u) >> 25;
-                                    const uint32_t flag = (uint32_t)(((hsh & 64u) ? f_hi : f_lo) >> (hsh & 63u)) & 1u;
-                                    my_cand[cnt] = ((uint64_t)f2ord(s) << 32) | (flag << 31) | pos;
-                                    ++cnt;
-                                    ++d_app;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            const unsigned need = __ballot_sync(0xffffffffu, cnt > kCand - kBN - 1);
-            if (need) {
-                d_raise += __popc(need);
-                const long long c_r0 = p.dbg ? clock64() : 0;
-                raise_fast<kBN, kBN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, lane, nullptr);
-                if (p.dbg) d_rcyc += clock64() - c_r0;
-            }
-        }
-        if (row_ok) p.cand_cnt[row] = cnt;
-        if (p.dbg) {
-            atomicAdd(p.dbg + 0, d_app);
-            if (lane == 0) {
-                atomicAdd(p.dbg + 1, d_raise); atomicAdd(p.dbg + 2, d_hit); atomicAdd(p.dbg + 3, d_chunks);
-                atomicAdd(p.dbg + 4, (unsigned long long)d_wait); atomicAdd(p.dbg + 5, (unsigned long long)d_rcyc);
-                atomicAdd(p.dbg + 6, (unsigned long long)d_acyc);
-                atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - c_start));
-                if (p.dbg_warp) {
-                    unsigned long long *w = p.dbg_warp + ((size_t)blockIdx.x * kEpiWarps + ew) * 4;
-                    w[0] = (unsigned long long)(clock64() - c_start); w[1] = (unsigned long long)d_wait;
-                    w[2] = (unsigned long long)d_rcyc; w[3] = d_raise;
-                }
-                atomicMax(p.dbg + 8, (unsigned long long)(clock64() - c_start));
-                atomicMax(p.dbg + 9, (unsigned long long)d_rcyc);
-                atomicMax(p.dbg + 10, (unsigned long long)d_wait);
-                atomicMax(p.dbg + 11, (unsigned long long)d_raise);
-            }
-        }
+        // ================= epilogue: thread == user row (shared with the ping-pong kernel) =================
+        tc_epilogue<kBN, false, DUMP, false>(p, row0, n_tiles, warp, lane, tmem_base, tfull, tempty, hist_all);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -806,167 +867,7 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else {
-        // ---- epilogue: thread == user row; warps 2-5 own half 0, warps 6-9 half 1.
-        // TMEM loads are software-pipelined (two 64-column register buffers): the load of chunk c+1 is in
-        // flight while chunk c is filtered, and the accumulator is handed back to the MMA warp as soon as the
-        // last load has landed - the filtering of the last chunk and any threshold raise run while the tensor
-        // core already works on this half's next tile.
-        const int ew = warp - 2;
-        const int q = warp & 3;
-        const int h = ew >> 2;
-        const int r_local = h * 128 + q * 32 + lane;
-        const int row = row0 + r_local;
-        const bool row_ok = row < p.n_rows;
-        int *hist = hist_all + ew * 32;
-        uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
-        const float *__restrict__ tile_norm = p.tile_norm;
-        const uint32_t num_items = (uint32_t)p.num_items;
-        int cnt = 0, stalls = 0, napp = 0;
-        const int keff = p.k;
-        const int budget = p.append_budget;
-        const int raise_at = min(kCand - kPPN - 1, max(64, (5 * keff) / 2));
-        float tau = -INFINITY, cu = 0.f;
-        const unsigned long long *my_wide = (p.wide && row_ok) ? p.wide + (size_t)row * kWideWords : nullptr;
-        if (row_ok) {
-            const float c = 0.0009765625f * 1.05f + (float)p.d * 2.4e-7f;
-            cu = c * p.row_norm[row] * (*p.scale_u) * (*p.scale_v);
-        } else {
-            tau = INFINITY;
-        }
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * kPPN;
-        const int abl = DIAG ? p.ablate : 0;
-        unsigned long long d_app = 0, d_raise = 0, d_hit = 0, d_chunks = 0;
-        long long d_wait = 0, d_rcyc = 0, d_acyc = 0;
-        const long long c_start = DIAG ? clock64() : 0;
-        uint32_t ra[64], rb[64];
-        // one 64-column chunk: FMNMX3 max tree against the row threshold.  Survivors of a hit group are appended
-        // branch-free: every element is stored at the current slot and the slot only advances for a survivor (the
-        // "maybe masked" bit is filled in lazily by the raise; the re-rank does the exact mask test anyway).
-        auto filter_chunk = [&](const uint32_t (&r)[64], const float thr, const uint32_t pos0) {
-            if (DUMP) {
-                float *dst = p.dump + (size_t)(row0 + r_local) * ((size_t)n_tiles * kPPN) + pos0;
-#pragma unroll
-                for (int j = 0; j < 64; ++j) dst[j] = __uint_as_float(r[j]);
-            }
-            if (abl & 2) return;
-            float gm[8];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const float a = max3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
-                const float b = max3(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-                gm[g] = max3(a, b, fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
-            }
-            const float m = max3(max3(gm[0], gm[1], gm[2]), max3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
-            if (m >= thr && cnt >= 0 && !(abl & 1)) {
-                const int c_in = cnt;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    if (gm[g] >= thr) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float sc = __uint_as_float(r[8 * g + j]);
-                            const uint32_t pos = pos0 + 8 * g + j;
-                            my_cand[cnt] = ((uint64_t)f2ord(sc) << 32) | pos;
-                            cnt += (sc >= thr && pos < num_items) ? 1 : 0;
-                        }
-                    }
-                }
-                napp += cnt - c_in;
-            }
-        };
-        for (int t = 0; t < n_tiles; ++t) {
-            float thr = tau - cu * tile_norm[t];   // tau only moves at the end of a tile (and in the bootstrap)
-            const long long c_w0 = (DIAG && p.dbg) ? clock64() : 0;
-            mbar_wait(s32(tfull + h), (uint32_t)t & 1u);
-            if (DIAG && p.dbg) d_wait += clock64() - c_w0;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (abl & 4) {
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s32(tempty + h));
-                continue;
-            }
-            const uint32_t n0 = (uint32_t)t * kPPN;
-            {
-            tmem_ld64_async(lane_addr, ra);
-            tmem_ld_wait64(ra);
-            if (t == 0 && keff <= 32 && !(abl & 128)) {
-                // Bootstrap (all 32 rows of the warp at once, in registers): tau0 = K-th largest lower bound among
-                // the certainly-unmasked items of the first chunk - the 64 items of largest norm.  Without it every
-                // row would append all of tile 0 and need a warp-cooperative raise at the same moment.
-                const float e0 = cu * tile_norm[0];
-                const unsigned long long head = my_wide ? my_wide[0] : 0ull;   // exact mask bitmap of positions 0..63
-#pragma unroll
-                for (int j = 0; j < 64; ++j)
-                    rb[j] = (((head >> j) & 1ull) || (uint32_t)j >= num_items) ? 0xFF800000u : ra[j];
-                float prev = INFINITY;
-                for (int r = 0; r < keff; ++r) {   // r-th largest distinct value (duplicates only lower the bound)
-                    float m = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 64; ++j) {
-                        const float w = __uint_as_float(rb[j]);
-                        m = fmaxf(m, w < prev ? w : -INFINITY);
-                    }
-                    prev = m;
-                }
-                if (row_ok && prev > -INFINITY) { tau = prev - e0; thr = tau - e0; }
-            }
-            tmem_ld64_async(lane_addr + 64, rb);
-            filter_chunk(ra, thr, n0);
-            tmem_ld_wait64(rb);
-            tmem_ld64_async(lane_addr + 128, ra);
-            filter_chunk(rb, thr, n0 + 64);
-            tmem_ld_wait64(ra);
-            tmem_ld64_async(lane_addr + 192, rb);
-            filter_chunk(ra, thr, n0 + 128);
-            tmem_ld_wait64(rb);
-            }
-            // every TMEM read of this warp for tile t has landed: hand the accumulator back
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s32(tempty + h));
-            filter_chunk(rb, thr, n0 + 192);
-            // a full tile (256 appends) must always fit, and a stale tau costs appends (~100 cycles of the whole warp
-            // each): raise as soon as the list holds ~2.5 K entries (>= 64), at the latest with 256 slots left
-            const unsigned need = __ballot_sync(0xffffffffu, cnt > raise_at);
-            if (need) {
-                if (DIAG) d_raise += __popc(need);
-                const long long c_r0 = (DIAG && p.dbg) ? clock64() : 0;
-                if (!(abl & 16))
-                    raise_fast<kPPN, kPPN>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, lane, my_wide);
-                else
-                    raise_thresholds<kPPN, kPPN, true>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane, my_wide);
-                if (DIAG && p.dbg) d_rcyc += clock64() - c_r0;
-            }
-            // a row that keeps beating its own threshold (scores rising along the sweep: a user anti-aligned with
-            // the popularity direction) would drag its warp through the append path on every chunk: hand it to the
-            // exact kernel instead
-            if (napp > budget && cnt >= 0) { cnt = -1; tau = INFINITY; }
-        }
-        if (DIAG) d_app = (unsigned long long)napp;
-        if (row_ok) p.cand_cnt[row] = cnt;
-        if (DIAG && p.dbg_row && row_ok) {
-            float *w = p.dbg_row + (size_t)row * 4;
-            w[0] = (float)d_app; w[1] = (float)cnt; w[2] = tau; w[3] = cu;
-        }
-        if (DIAG && p.dbg) {
-            atomicAdd(p.dbg + 0, d_app);
-            if (lane == 0) {
-                atomicAdd(p.dbg + 1, d_raise); atomicAdd(p.dbg + 2, d_hit); atomicAdd(p.dbg + 3, d_chunks);
-                atomicAdd(p.dbg + 4, (unsigned long long)d_wait); atomicAdd(p.dbg + 5, (unsigned long long)d_rcyc);
-                atomicAdd(p.dbg + 6, (unsigned long long)d_acyc);
-                atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - c_start));
-                if (p.dbg_warp) {
-                    unsigned long long *w = p.dbg_warp + ((size_t)blockIdx.x * kEpiWarps + ew) * 4;
-                    w[0] = (unsigned long long)(clock64() - c_start); w[1] = (unsigned long long)d_wait;
-                    w[2] = (unsigned long long)d_rcyc; w[3] = d_raise;
-                }
-                atomicMax(p.dbg + 8, (unsigned long long)(clock64() - c_start));
-                atomicMax(p.dbg + 9, (unsigned long long)d_rcyc);
-                atomicMax(p.dbg + 10, (unsigned long long)d_wait);
-                atomicMax(p.dbg + 11, (unsigned long long)d_raise);
-            }
-        }
+        tc_epilogue<kPPN, true, DUMP, DIAG>(p, row0, n_tiles, warp, lane, tmem_base, tfull, tempty, hist_all);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
