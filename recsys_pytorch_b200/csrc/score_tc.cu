@@ -8,23 +8,28 @@
 // Exactness argument.  Tables are rescaled by powers of two and rounded to
 // fp16 (unit roundoff 2^-11); the tensor cores accumulate exact products in fp32.  For a
 // user u and item i,  |S~ - S| <= e(u,i) = c |u|_2 |v_i|_2,  c = 2^-10 (+5%) + d*2.4e-7.
-// With L = S~ - e <= S <= S~ + e = H:  if tau is any lower bound of the K'-th largest L of
-// the row (K' = K + #masked items of the user, so at least K unmasked items have
-// S >= tau), every item of the exact top-K has H >= tau.  Items are visited in
-// DESCENDING NORM order (one radix sort per call), so a whole 128-item tile shares the
-// bound e_t = c |u| * (largest norm in the tile), which shrinks along the sweep while tau
-// grows.  The candidate pass keeps every item with S~ + e_t >= tau, raising tau by a
-// bucketed selection over the row's candidate buffer when it fills; the re-rank kernel
-// drops masked items, recomputes survivors with the SAME k-ordered fp32 FMA chain as the
-// exact kernel and selects by (score desc, id asc).  Rows whose buffer cannot hold
-// K' + slack are re-done by the exact kernel: the result always equals B200REC_SCORE_EXACT.
+// With L = S~ - e <= S <= S~ + e = H:  any tau with at least K CERTAINLY UNMASKED entries at
+// L >= tau is a lower bound of the exact K-th score, so every item of the exact top-K has
+// H >= tau.  Items are visited head | stratified sample | rest of the descending-norm order
+// (reorder_kernel); a tile shares the bound e_t = c |u| * (largest norm in the tile).  The
+// candidate pass keeps every item with S~ + e_t >= tau, raising tau by bisection over the
+// row's candidate list when it grows (raise_fast); "certainly unmasked" comes from an exact
+// bitmap of the first 64 positions and a 2048-bit Bloom filter per row.  The re-rank kernel
+// drops masked items (exact test), recomputes survivors with the SAME k-ordered fp32 FMA
+// chain as the exact kernel and selects by (score desc, id asc).  Rows whose list cannot be
+// kept short are re-done by the exact kernel: the result always equals B200REC_SCORE_EXACT.
 //
-// Kernel roles (one CTA = 256 user rows x all item tiles of 128):
-//   warp 0      TMA producer: A (users) once, B (items) k-blocks through a smem ring
-//   warp 1      MMA issuer: tcgen05.mma.kind::f16, M=128 x N=128 x K=16, two M halves,
-//               double-buffered 4 x 128 TMEM columns; tcgen05.commit frees smem / signals tiles
-//   warps 2-9   epilogue: tcgen05.ld 32x32b.x64 (thread == user row), FMNMX3 max tree against
-//               the row threshold, candidate append, warp-cooperative threshold raise
+// Kernel roles (one CTA = 256 user rows = two M=128 halves, all item tiles):
+//   warp 0      TMA producer: A (users) once, B (items) k-blocks of 64 fp16 through a smem ring
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM,
+//               tcgen05.commit frees smem slots / signals finished tiles
+//                 d <= 128: M128 x N256 x K16, ONE 256-column accumulator per half, the halves
+//                           ping-pong (tc_candidate_pp_kernel)
+//                 d >  128: M128 x N128 x K16, two stages of a pair of 128-column accumulators
+//                           (tc_candidate_kernel)
+//   warps 2-9   epilogue (tc_epilogue, shared): software-pipelined tcgen05.ld 32x32b.x64
+//               (thread == user row), FMNMX3 max tree against the row threshold, branch-free
+//               append, register bootstrap of tau, warp-cooperative threshold raise
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -84,49 +89,6 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 64 consecutive fp32 accumulator columns of this thread's TMEM lane (row)
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
-    uint32_t r[64];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-        "%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,"
-        "%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
-          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
-          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
-          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
-          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
-}
-// asynchronous 32-column load (no wait) + the wait that also pins the destination registers
-__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-        "%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
-                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
-                   "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
@@ -232,7 +194,6 @@ __global__ void tile_norm_kernel(const float *__restrict__ norm, int num_items, 
 }
 
 // "Maybe masked" filters per scored row (no false negatives), one warp per row, coalesced over the row's positives:
-//   bloom[row]            128 bits, kept in registers by the N=128 kernel (one bit per hashed sorted position)
 //   wide[row][0]          EXACT bitmap of the first 64 positions (the bootstrap chunk of the ping-pong kernel)
 //   wide[row][1..32]      2048-bit filter read from global memory by the (rare) threshold raises
 constexpr int kWideWords = 33;   // uint64 words per row
@@ -240,7 +201,7 @@ __device__ __forceinline__ uint32_t wide_hash(uint32_t pos) { return (pos * 2654
 __global__ void __launch_bounds__(256) bloom_kernel(const int32_t *__restrict__ users, int n_rows,
                                                     const int64_t *__restrict__ mask_indptr,
                                                     const int32_t *__restrict__ mask_indices,
-                                                    const int32_t *__restrict__ inv_perm, uint4 *__restrict__ bloom,
+                                                    const int32_t *__restrict__ inv_perm,
                                                     unsigned long long *__restrict__ wide) {
     const int lane = threadIdx.x & 31;
     const int row = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -250,19 +211,12 @@ __global__ void __launch_bounds__(256) bloom_kernel(const int32_t *__restrict__ 
     unsigned long long *wrow = wide + (size_t)row * kWideWords;
     for (int q = lane; q < kWideWords; q += 32) wrow[q] = 0ull;
     __syncwarp();
-    unsigned w[4] = {0u, 0u, 0u, 0u};
     for (int64_t m = mb + lane; m < me; m += 32) {
         const uint32_t pos = (uint32_t)inv_perm[mask_indices[m]];
-        const uint32_t hsh = (pos * 2654435761u) >> 25;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) w[q] |= ((hsh >> 5) == (uint32_t)q) ? (1u << (hsh & 31u)) : 0u;
         if (pos < 64u) atomicOr(wrow, 1ull << pos);
         const uint32_t h2 = wide_hash(pos);
         atomicOr(wrow + 1 + (h2 >> 6), 1ull << (h2 & 63u));
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) w[q] = __reduce_or_sync(0xffffffffu, w[q]);
-    if (lane == 0) bloom[row] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 struct TcParams {
@@ -271,7 +225,6 @@ struct TcParams {
     const int64_t *mask_indptr;      // may be NULL
     const int32_t *mask_indices;
     const int32_t *inv_perm;         // item id -> sorted position
-    const uint4 *bloom;              // [n_rows] 128-bit "maybe masked" filter per row (NULL without a mask)
     const unsigned long long *wide;  // [n_rows][kWideWords] exact head bitmap + 2048-bit filter (NULL without a mask)
     int append_budget;               // a row that appends more than this is handed to the exact kernel
     const float *row_norm;           // [n_rows]
@@ -285,109 +238,6 @@ struct TcParams {
     unsigned long long *dbg_warp;    // diagnostics: per (block, epilogue warp) [total, wait, raise cycles, raises]; or NULL
     unsigned long long *dbg;         // diagnostics: [0] appends, [1] raises, [2] warp-chunks with a hit, [3] warp-chunks; or NULL
 };
-
-// warp-cooperative threshold raise for the lanes in `need` (bit per lane); see file header.
-// Entries hold S~ (scaled); e = cu * tile_norm[pos/128]; L = S~ - e, H = S~ + e.
-template <int TILE, int WM, bool LAZY_FLAG = false>
-__device__ __forceinline__ void raise_thresholds(unsigned need, uint64_t *my_cand, int &cnt, float &tau, int &stalls, int keff, float cu,
-                                                 const float *__restrict__ tile_norm, int *hist, int lane,
-                                                 const unsigned long long *my_wide = nullptr) {
-    while (need) {
-        const int Lsrc = __ffs(need) - 1;
-        need &= need - 1;
-        uint64_t *base = reinterpret_cast<uint64_t *>(__shfl_sync(0xffffffffu, (unsigned long long)my_cand, Lsrc));
-        const int n = __shfl_sync(0xffffffffu, cnt, Lsrc);
-        const int kf = __shfl_sync(0xffffffffu, keff, Lsrc);
-        const float c_u = __shfl_sync(0xffffffffu, cu, Lsrc);
-        const float old_tau = __shfl_sync(0xffffffffu, tau, Lsrc);
-        const unsigned long long *wf = nullptr;
-        if (LAZY_FLAG)   // appends left the "maybe masked" bit clear: fill it in on first sight
-            wf = reinterpret_cast<const unsigned long long *>(__shfl_sync(0xffffffffu, (unsigned long long)my_wide, Lsrc));
-        // lo[] = lower bound of the CLEAN entries only (bit 31 of the position = "maybe masked": such an
-        // entry never counts towards the K items that justify tau); hi[] = upper bound of every entry
-        uint64_t e[kCand / 32];
-        float lo[kCand / 32], hi[kCand / 32];
-        float mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < kCand / 32; ++i) {
-            const int p = lane + 32 * i;
-            e[i] = (p < n) ? base[p] : 0ull;
-            lo[i] = -INFINITY; hi[i] = -INFINITY;
-            if (LAZY_FLAG && p < n && wf) {
-                const uint32_t h2 = wide_hash((uint32_t)e[i] & 0x7FFFFFFFu);
-                e[i] |= (uint64_t)((uint32_t)(wf[1 + (h2 >> 6)] >> (h2 & 63u)) & 1u) << 31;
-            }
-            if (p < n) {
-                const float s = ord2f((uint32_t)(e[i] >> 32));
-                const float err = c_u * tile_norm[(uint32_t)(e[i] & 0x7FFFFFFFu) / TILE];
-                hi[i] = s + err;
-                if (!((uint32_t)e[i] >> 31)) {
-                    lo[i] = s - err;
-                    mn = fminf(mn, lo[i]); mx = fmaxf(mx, lo[i]);
-                }
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        }
-        hist[lane] = 0;
-        __syncwarp();
-        const float scale = (mx > mn) ? 32.f / (mx - mn) : 0.f;
-#pragma unroll
-        for (int i = 0; i < kCand / 32; ++i) {
-            if (lo[i] > -INFINITY) {
-                int b = (int)((lo[i] - mn) * scale);
-                b = b > 31 ? 31 : (b < 0 ? 0 : b);
-                atomicAdd(&hist[b], 1);
-            }
-        }
-        __syncwarp();
-        int suf = hist[lane];  // suffix sum: entries in buckets >= lane
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_down_sync(0xffffffffu, suf, o);
-            if (lane + o < 32) suf += t;
-        }
-        const unsigned okb = __ballot_sync(0xffffffffu, suf >= kf);
-        const int bstar = okb ? 31 - __clz(okb) : 0;
-        // new tau = smallest L among the clean entries in buckets >= bstar (at least kf clean entries have
-        // L >= tau); with fewer than kf clean entries tau cannot move
-        float t_new = INFINITY;
-#pragma unroll
-        for (int i = 0; i < kCand / 32; ++i) {
-            if (lo[i] > -INFINITY) {
-                int b = (int)((lo[i] - mn) * scale);
-                b = b > 31 ? 31 : (b < 0 ? 0 : b);
-                if (b >= bstar) t_new = fminf(t_new, lo[i]);
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) t_new = fminf(t_new, __shfl_xor_sync(0xffffffffu, t_new, o));
-        t_new = okb ? fmaxf(old_tau, t_new) : old_tau;
-        // compact: keep entries whose upper bound still reaches tau
-        int keep = 0;
-#pragma unroll
-        for (int i = 0; i < kCand / 32; ++i)
-            if (lane + 32 * i < n && hi[i] >= t_new) ++keep;
-        int pre = keep;  // inclusive scan
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, pre, o);
-            if (lane >= o) pre += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, pre, 31);
-        int w = pre - keep;
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < kCand / 32; ++i)
-            if (lane + 32 * i < n && hi[i] >= t_new) base[w++] = e[i];
-        __syncwarp();
-        if (lane == Lsrc) {
-            // a raise that frees < 48 slots three times in a row is thrashing (sticky high-uncertainty entries)
-            stalls = (n - total < 48) ? stalls + 1 : 0;
-            if (total > kCand - WM - 32 || stalls >= 3) { cnt = -1; tau = INFINITY; }  // exact kernel re-does the row
-            else { cnt = total; tau = t_new; }
-        }
-    }
-}
 
 // asynchronous 64-column load (no wait) and the wait that also pins the destination registers: the
 // "+r" operands make every later use of r[] depend on the wait, and keep r[] allocated in between
@@ -524,19 +374,17 @@ __device__ __forceinline__ void raise_fast(unsigned need, uint64_t *my_cand, int
 // ---------------------------------------------------------------------------------------------------
 template <int TILE, bool PP, bool DUMP, bool DIAG>
 __device__ __forceinline__ void tc_epilogue(const TcParams &p, const int row0, const int n_tiles, const int warp,
-                                            const int lane, const uint32_t tmem_base, uint64_t *tfull, uint64_t *tempty,
-                                            int *hist_all) {
+                                            const int lane, const uint32_t tmem_base, uint64_t *tfull, uint64_t *tempty) {
     const int ew = warp - 2;
     const int q = warp & 3;
     const int h = ew >> 2;            // M half
     const int r_local = h * 128 + q * 32 + lane;
     const int row = row0 + r_local;
     const bool row_ok = row < p.n_rows;
-    int *hist = hist_all + ew * 32;
     uint64_t *my_cand = p.cand + (size_t)(row_ok ? row : 0) * kCand;
     const float *__restrict__ tile_norm = p.tile_norm;
     const uint32_t num_items = (uint32_t)p.num_items;
-    int cnt = 0, stalls = 0, napp = 0;
+    int cnt = 0, napp = 0;
     const int keff = p.k;
     const int budget = p.append_budget;
     int raise_at = min(kCand - TILE - 1, max(64, (5 * keff) / 2));   // per row: moves up when the list stays long
@@ -652,10 +500,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, const int row0, c
         if (need) {
             if (DIAG) d_raise += __popc(need);
             const long long c_r0 = (DIAG && p.dbg) ? clock64() : 0;
-            if (!(abl & 16))
-                raise_fast<TILE, TILE>(need, my_cand, cnt, tau, raise_at, keff, cu, tile_norm, lane, my_wide);
-            else
-                raise_thresholds<TILE, TILE, true>(need, my_cand, cnt, tau, stalls, keff, cu, tile_norm, hist, lane, my_wide);
+            raise_fast<TILE, TILE>(need, my_cand, cnt, tau, raise_at, keff, cu, tile_norm, lane, my_wide);
             if (DIAG && p.dbg) d_rcyc += clock64() - c_r0;
         }
         // a row that keeps beating its own threshold (scores rising along the sweep: a user anti-aligned with
@@ -702,7 +547,6 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t *bars = reinterpret_cast<uint64_t *>(smB + (size_t)n_stages * kBN * 128);
     uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *afull = bars + 20;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
-    int *hist_all = reinterpret_cast<int *>(bars + 22);  // [kEpiWarps][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kBM;
@@ -770,7 +614,7 @@ tc_candidate_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ================= epilogue: thread == user row (shared with the ping-pong kernel) =================
-        tc_epilogue<kBN, false, DUMP, false>(p, row0, n_tiles, warp, lane, tmem_base, tfull, tempty, hist_all);
+        tc_epilogue<kBN, false, DUMP, false>(p, row0, n_tiles, warp, lane, tmem_base, tfull, tempty);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -799,7 +643,6 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint64_t *bars = reinterpret_cast<uint64_t *>(smB + (size_t)n_stages * kPPN * 128);
     uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *afull = bars + 20;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
-    int *hist_all = reinterpret_cast<int *>(bars + 22);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kBM;
@@ -867,7 +710,7 @@ tc_candidate_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else {
-        tc_epilogue<kPPN, true, DUMP, DIAG>(p, row0, n_tiles, warp, lane, tmem_base, tfull, tempty, hist_all);
+        tc_epilogue<kPPN, true, DUMP, DIAG>(p, row0, n_tiles, warp, lane, tmem_base, tfull, tempty);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1007,7 +850,7 @@ static size_t sort_temp_bytes(int num_items) {
 struct TcLayout {
     int dpad, KB, rows_cap, items_pad, n_tiles, tile;
     size_t off_vh, off_uh, off_unorm, off_vnorm, off_vnorm_sorted, off_iota, off_perm, off_inv, off_tnorm, off_scalars, off_sort,
-        sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, off_bloom, off_wide, total;
+        sort_bytes, off_cand, off_cnt, off_redo, off_redo_n, off_ridx, off_rsc, off_ruser, off_wide, total;
 };
 static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     TcLayout L;
@@ -1040,7 +883,6 @@ static TcLayout tc_layout(int n_users, int num_items, int d, int k) {
     L.off_redo = take((size_t)L.rows_cap * 4, 256);
     L.off_redo_n = take(4, 256);
     L.off_ruser = take((size_t)L.rows_cap * 4, 256);
-    L.off_bloom = take((size_t)L.rows_cap * 16, 256);
     L.off_wide = take((size_t)L.rows_cap * kWideWords * 8, 256);
     L.off_ridx = take((size_t)L.rows_cap * k * 4, 256);
     L.off_rsc = take((size_t)L.rows_cap * k * 4, 256);
@@ -1174,14 +1016,13 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         TcParams p;
         p.n_rows = nr; p.num_items = num_items; p.n_tiles = L.n_tiles; p.k = k; p.d = d;
         p.users = users + r0; p.mask_indptr = mi; p.mask_indices = mx; p.inv_perm = inv_perm;
-        p.bloom = nullptr; p.wide = nullptr;
+        p.wide = nullptr;
         p.append_budget = getenv("B200REC_TC_BUDGET") ? atoi(getenv("B200REC_TC_BUDGET")) : 1536 + 8 * k;
         if (mi) {
-            uint4 *bloom = reinterpret_cast<uint4 *>(base + L.off_bloom);
             unsigned long long *wide = reinterpret_cast<unsigned long long *>(base + L.off_wide);
-            bloom_kernel<<<(nr + 7) / 8, 256, 0, s>>>(users + r0, nr, mi, mx, inv_perm, bloom, wide);
+            bloom_kernel<<<(nr + 7) / 8, 256, 0, s>>>(users + r0, nr, mi, mx, inv_perm, wide);
             B200_LAUNCH_CHECK();
-            p.bloom = bloom; p.wide = wide;
+            p.wide = wide;
         }
         p.row_norm = unorm; p.tile_norm = tnorm;
         p.scale_v = reinterpret_cast<float *>(scal + 2); p.scale_u = reinterpret_cast<float *>(scal + 3);
