@@ -32,6 +32,7 @@ struct BprParams {
     int chunk;       // triples per warp-chunk (multiple of 32/G, <= 32)
     int stages;      // TMA path: shared-memory stages per warp
     int64_t n_chunks;
+    unsigned int *work;   // fast path: chunk counter (zeroed before the launch) for dynamic distribution, or NULL
 };
 
 // dL/dx of -log(sigmoid(x))/B the way the reference's fp32 autograd evaluates it (models/MF.py:105):
@@ -402,7 +403,20 @@ __global__ void __launch_bounds__(256, CPL == 1 ? B200REC_FAST_MINB : 2) bpr_ste
     const bool hints = (p.a.flags & B200REC_F_L2_HINTS) != 0;
     const uint64_t pol_u = l2_policy_evict_first(), pol_v = l2_policy_evict_last();
 
-    for (int64_t c = warp_global; c < n_chunks; c += n_warps) {
+    // Chunks are handed out dynamically when p.work is set: with a static split a CTA that starts late (another
+    // kernel - NCCL's all-reduce in the multi-GPU step - holds its SM for a while) still owns 1/grid of the batch and
+    // the launch lasts (delay + full kernel time); with the counter late CTAs simply take fewer chunks.
+    unsigned int *const work = p.work;
+    int64_t c = warp_global;
+    int64_t c_next = 0;
+    if (work) {
+        if (lane == 0) c = (int64_t)atomicAdd(work, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+    }
+    for (; c < n_chunks; c = work ? c_next : c + n_warps) {
+        if (work) {   // fetch the next chunk index now: its latency hides behind this chunk's rows
+            if (lane == 0) c_next = (int64_t)atomicAdd(work, 1u);
+        }
         const int64_t t_lane = c * chunk + lane;
         bool valid = (lane < chunk) && (t_lane < B);
         int u, i, j;
@@ -483,6 +497,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? B200REC_FAST_MINB : 2) bpr_ste
             load(r1, it + 4);
             compute(r2, it + 2);
         }
+        if (work) c_next = __shfl_sync(0xffffffffu, c_next, 0);
     }
     if (LOSS) {
         // every lane accumulated the same per-triple value
@@ -761,6 +776,7 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
     const int TPW = 32 / G;
     BprParams p;
     p.a = a;
+    p.work = nullptr;
     p.invB = a.inv_batch > 0.f ? a.inv_batch : 1.0f / (float)a.B;
     // chunk: as large as 32 triples, shrunk (to a multiple of TPW) until every warp slot has work
     const int64_t slots = (int64_t)sm_count() * 48;
@@ -799,6 +815,20 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
 #undef B200_ASYNC
             B200_LAUNCH_CHECK();
             return B200REC_OK;
+        }
+        // dynamic chunk distribution (B200REC_FAST_DYNAMIC=0 to disable): a ring of counters kept per device, so
+        // back-to-back launches on different streams never share one
+        {
+            static unsigned int *ring[64] = {nullptr};
+            static unsigned int slot[64] = {0};
+            static const bool dyn = !(getenv("B200REC_FAST_DYNAMIC") && atoi(getenv("B200REC_FAST_DYNAMIC")) == 0);
+            int dev = 0;
+            p.work = nullptr;
+            if (dyn && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+                if (!ring[dev]) B200_CUDA(cudaMalloc(&ring[dev], 256 * sizeof(unsigned int)));
+                p.work = ring[dev] + (slot[dev]++ & 255u);
+                B200_CUDA(cudaMemsetAsync(p.work, 0, sizeof(unsigned int), s));
+            }
         }
         const int64_t need = (p.n_chunks + 7) / 8;
         const int64_t cap = (int64_t)sm_count() * (CPL == 1 ? B200REC_FAST_MINB : 2);
