@@ -397,6 +397,9 @@ def main():
     ap.add_argument("--no-secondary", dest="no_secondary", action="store_true")
     ap.add_argument("--wire", default="fp32", choices=["fp32", "bf16"],
                     help="N>1 user_sharded: dtype of the all-reduced item-delta buffer")
+    ap.add_argument("--exchange", default="diff", choices=["diff", "buffer"],
+                    help="N>1 user_sharded: 'diff' = kernel updates the item replica in place and the difference is "
+                         "all-reduced (default); 'buffer' = kernel accumulates item deltas in a separate dense buffer")
     ap.add_argument("--small", action="store_true", help="tiny shapes for a quick functional run (NOT a bench value)")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -147,6 +147,10 @@ int b200rec_add_bf16(float *W, const void *delta_bf16, int64_t n, void *stream);
 /* dense SGD / Adam sweeps: torch.optim.SGD(lr) and torch.optim.Adam(lr, betas,
  * eps, weight_decay=0) as constructed at models/MF.py:30 - every element moves. */
 int b200rec_sgd_dense(float *param, const float *grad, int64_t n, float lr, void *stream);
+/* "update in place, exchange the difference" (user-sharded multi-GPU layout; no reference counterpart):
+ *   delta_diff:  d_wire = d_own = W - snapshot      delta_apply:  W += d_sum - d_own      (n a multiple of 4) */
+int b200rec_delta_diff(const float *W, const float *snapshot, float *d_wire, float *d_own, int64_t n, void *stream);
+int b200rec_delta_apply(float *W, const float *d_sum, const float *d_own, int64_t n, void *stream);
 int b200rec_adam_dense(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
                        int64_t n, float lr, float beta1, float beta2, float eps, int step,
                        void *stream);

@@ -59,6 +59,8 @@ _PROTOS = {
     "b200rec_rows_add": (_I, [_P, _I, _P, _I, _P, _I, _F, _P]),
     "b200rec_add_bf16": (_I, [_P, _P, _L, _P]),
     "b200rec_sgd_dense": (_I, [_P, _P, _L, _F, _P]),
+    "b200rec_delta_diff": (_I, [_P, _P, _P, _P, _L, _P]),
+    "b200rec_delta_apply": (_I, [_P, _P, _P, _L, _P]),
     "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
     "b200rec_adam_rows": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _F, _F, _F, _F, _I, _P]),
     "b200rec_score_topk_workspace": (_L, [_I, _I, _I, _I, _I]),

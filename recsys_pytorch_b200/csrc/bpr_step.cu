@@ -902,6 +902,54 @@ extern "C" int b200rec_sgd_dense(float *param, const float *grad, int64_t n, flo
     return B200REC_OK;
 }
 
+// ---- "update in place, exchange the difference" (user-sharded multi-GPU layout) ---------------------------------
+// d_own = d_wire = W - snapshot  (what this rank's step did to its replica; two copies: one is all-reduced in place,
+// the other is subtracted again when the sum comes back)
+__global__ void __launch_bounds__(256) delta_diff_kernel(const float4 *__restrict__ W, const float4 *__restrict__ snap,
+                                                         float4 *__restrict__ d_wire, float4 *__restrict__ d_own,
+                                                         int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 w = W[i], s = snap[i];
+        const float4 d = make_float4(w.x - s.x, w.y - s.y, w.z - s.z, w.w - s.w);
+        d_wire[i] = d;
+        d_own[i] = d;
+    }
+}
+// W += d_sum - d_own  (the other ranks' contribution of that step)
+__global__ void __launch_bounds__(256) delta_apply_kernel(float4 *__restrict__ W, const float4 *__restrict__ d_sum,
+                                                          const float4 *__restrict__ d_own, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 w = W[i];
+        const float4 a = d_sum[i], b = d_own[i];
+        w.x += a.x - b.x; w.y += a.y - b.y; w.z += a.z - b.z; w.w += a.w - b.w;
+        W[i] = w;
+    }
+}
+
+extern "C" int b200rec_delta_diff(const float *W, const float *snapshot, float *d_wire, float *d_own, int64_t n,
+                                  void *stream) {
+    B200_REQUIRE(W && snapshot && d_wire && d_own, B200REC_EINVAL, "delta_diff: null argument");
+    B200_REQUIRE(n % 4 == 0, B200REC_EINVAL, "delta_diff: n must be a multiple of 4 (padded tables)");
+    if (n <= 0) return B200REC_OK;
+    const int64_t n4 = n / 4, blocks = (n4 + 255) / 256, cap = (int64_t)sm_count() * 16;
+    delta_diff_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(W), reinterpret_cast<const float4 *>(snapshot),
+        reinterpret_cast<float4 *>(d_wire), reinterpret_cast<float4 *>(d_own), n4);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+extern "C" int b200rec_delta_apply(float *W, const float *d_sum, const float *d_own, int64_t n, void *stream) {
+    B200_REQUIRE(W && d_sum && d_own, B200REC_EINVAL, "delta_apply: null argument");
+    B200_REQUIRE(n % 4 == 0, B200REC_EINVAL, "delta_apply: n must be a multiple of 4 (padded tables)");
+    if (n <= 0) return B200REC_OK;
+    const int64_t n4 = n / 4, blocks = (n4 + 255) / 256, cap = (int64_t)sm_count() * 16;
+    delta_apply_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4 *>(W), reinterpret_cast<const float4 *>(d_sum), reinterpret_cast<const float4 *>(d_own), n4);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
 extern "C" int b200rec_adam_dense(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n,
                                   float lr, float beta1, float beta2, float eps, int step, void *stream) {
     B200_REQUIRE(param && grad && exp_avg && exp_avg_sq, B200REC_EINVAL, "adam_dense: null argument");

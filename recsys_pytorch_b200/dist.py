@@ -211,6 +211,47 @@ class UserShardedBPR:
         ov["pending"] = cur
         ov["n"] += 1
 
+    # ---- update in place, exchange the difference ------------------------------------------------------
+    def step_diff(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True):
+        """Same overlapped schedule, but the fused kernel updates this rank's item replica IN PLACE (the single-GPU
+        fast path: a separate 51 MB delta buffer next to V does not fit L2 together with 1 GB of streaming user rows and
+        costs the kernel +25 %), and what crosses NVLink is the difference it made:
+            snapshot = V;  kernel(V);  d = V - snapshot;  all_reduce(d) on the side stream;
+            one step later  V += sum(d) - d_own          (the other ranks' contribution).
+        The arithmetic is the same sum of per-triple deltas, but a replica adds its own deltas triple by triple and the
+        others' as one dense sum, so replicas agree to fp32 rounding (not bit for bit); `resync()` makes them identical
+        again (broadcast of rank 0's table), `flush()` applies the last pending difference."""
+        if not hasattr(self, "_df"):
+            z = lambda: torch.zeros_like(self.V)
+            self._df = dict(snap=torch.empty_like(self.V), wire=[z(), z()], own=[z(), z()],
+                            comm=torch.cuda.Stream(device=self.device), ev_done=[torch.cuda.Event(), torch.cuda.Event()],
+                            ev_k=torch.cuda.Event(), n=0, pending=None)
+        df = self._df
+        cur = df["n"] & 1
+        main = torch.cuda.current_stream(self.device)
+        df["snap"].copy_(self.V)
+        engine.bpr_step(self.U, self.V, self.d, users_local, csr=self.train, lr=self.lr, reg=self.reg,
+                        sink=SINK_UPDATE, flags=(self.flags & ~(F_ITEM_DELTA | F_ITEM_DELTA_BF16)) |
+                        (F_USERS_UNIQUE if users_unique else 0), seed=self.seed,
+                        step=step_key * self.world + self.rank, loss_sum=loss_sum, inv_batch=1.0 / float(global_batch))
+        engine.delta_diff(self.V, df["snap"], df["wire"][cur], df["own"][cur])
+        df["ev_k"].record(main)
+        with torch.cuda.stream(df["comm"]):
+            df["comm"].wait_event(df["ev_k"])
+            allreduce_sum(df["wire"][cur])
+            df["ev_done"][cur].record(df["comm"])
+        if df["pending"] is not None:
+            main.wait_event(df["ev_done"][df["pending"]])
+            engine.delta_apply(self.V, df["wire"][df["pending"]], df["own"][df["pending"]])
+        df["pending"] = cur
+        df["n"] += 1
+
+    def resync(self):
+        """Make the item replicas bit-identical again (step_diff lets them differ by fp32 rounding)."""
+        self.flush()
+        if dist.is_initialized() and self.world > 1:
+            dist.broadcast(self.V, src=0)
+
     def evaluate(self, eval_users_local, truth_local, ks, protocol="holdout"):
         """Evaluation: the item table is already replicated, every rank scores its own users (local row
         ids of this rank's shard; `truth_local` rows are local too); metric sums are all-reduced."""
@@ -223,6 +264,11 @@ class UserShardedBPR:
             torch.cuda.current_stream(self.device).wait_event(ov["ev_done"][ov["pending"]])
             self.apply_item_delta(ov["bufs"][ov["pending"]])
             ov["pending"] = None
+        df = getattr(self, "_df", None)
+        if df and df["pending"] is not None:
+            torch.cuda.current_stream(self.device).wait_event(df["ev_done"][df["pending"]])
+            engine.delta_apply(self.V, df["wire"][df["pending"]], df["own"][df["pending"]])
+            df["pending"] = None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -266,15 +312,26 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
         B_glob = B_local * world
 
         sync_mode = os.environ.get("B200REC_DIST_SYNC", "0") == "1"
+        exchange = getattr(args, "exchange", "diff")
+        if tr.wire_bf16 and exchange == "diff":
+            exchange = "buffer"
 
         def step(s):
             if sync_mode:
                 tr.step(perms[s % 2], s + 1, B_glob, loss_sum=loss)
+            elif exchange == "diff":
+                tr.step_diff(perms[s % 2], s + 1, B_glob, loss_sum=loss)
             else:
                 tr.step_overlapped(perms[s % 2], s + 1, B_glob, loss_sum=loss)
-        coll = ("all_reduce(sum) of the dense [I, ld] %s item-delta buffer (%d MiB) per step, on a side stream, "
-                "overlapped with the next step's kernel (item rows one step stale)"
-                % ("bf16" if tr.wire_bf16 else "fp32", tr.dV.numel() * tr.dV.element_size() >> 20))
+        if exchange == "diff" and not sync_mode:
+            coll = ("item replica updated in place by the fused kernel; all_reduce(sum) of the dense [I, ld] fp32 "
+                    "difference V - snapshot (%d MiB) per step on a side stream, overlapped with the next step's kernel; "
+                    "V += sum - own one step later (item rows one step stale, replicas equal to fp32 rounding)"
+                    % (tr.V.numel() * 4 >> 20))
+        else:
+            coll = ("all_reduce(sum) of the dense [I, ld] %s item-delta buffer (%d MiB) per step, on a side stream, "
+                    "overlapped with the next step's kernel (item rows one step stale)"
+                    % ("bf16" if tr.wire_bf16 else "fp32", tr.dV.numel() * tr.dV.element_size() >> 20))
 
     for s in range(args.warmup):
         step(s)
@@ -305,6 +362,8 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
         loss.zero_()
         if layout == "item_sharded":
             tr.step(u, 1000 + s, loss_sum=loss)
+        elif exchange == "diff" and not sync_mode:
+            tr.step_diff(u, 1000 + s, B_glob, loss_sum=loss)
         else:
             tr.step_overlapped(u, 1000 + s, B_glob, loss_sum=loss)
         return float(loss.item())

@@ -126,6 +126,16 @@ def add_bf16(param, delta_bf16):
     check(_lib.lib().b200rec_add_bf16(ptr(param), ptr(delta_bf16), param.numel(), current_stream()))
 
 
+def delta_diff(W, snapshot, d_wire, d_own):
+    """d_wire = d_own = W - snapshot (dense, same shape)."""
+    check(_lib.lib().b200rec_delta_diff(ptr(W), ptr(snapshot), ptr(d_wire), ptr(d_own), W.numel(), current_stream()))
+
+
+def delta_apply(W, d_sum, d_own):
+    """W += d_sum - d_own."""
+    check(_lib.lib().b200rec_delta_apply(ptr(W), ptr(d_sum), ptr(d_own), W.numel(), current_stream()))
+
+
 def sgd_dense(param, grad, lr):
     check(_lib.lib().b200rec_sgd_dense(ptr(param), ptr(grad), param.numel(), float(lr), current_stream()))
 

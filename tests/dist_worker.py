@@ -44,6 +44,26 @@ def main():
     chk = tu.V.double().sum().reshape(1)
     dist.all_gather(both, chk)
     assert all(torch.equal(b, both[0]) for b in both), "item replicas diverged (overlapped steps)"
+    # "update in place, exchange the difference": same SGD sums as the delta-buffer schedule up to fp32 rounding
+    ta = UserShardedBPR(nu, ni, d, trl, rank, world, dev, lr=1.0, reg=0.001, init_std=0.1, seed=9)
+    tb = UserShardedBPR(nu, ni, d, trl, rank, world, dev, lr=1.0, reg=0.001, init_std=0.1, seed=9)
+    gg = torch.Generator(device=dev); gg.manual_seed(5 + rank)
+    for s in range(6):
+        users = torch.randperm(uhi - ulo, device=dev, generator=gg)[:4096].to(torch.int32)
+        ta.step_overlapped(users, 200 + s, 4096 * world)
+        tb.step_diff(users, 200 + s, 4096 * world)
+    ta.flush(); tb.flush()
+    torch.cuda.synchronize()
+    assert torch.allclose(ta.V, tb.V, rtol=1e-4, atol=1e-6), float((ta.V - tb.V).abs().max())
+    assert torch.allclose(ta.U, tb.U, rtol=1e-4, atol=1e-6)
+    mx = tb.V.abs().max()
+    peers = [torch.zeros_like(tb.V) for _ in range(world)]
+    dist.all_gather(peers, tb.V)
+    assert all(float((q - peers[0]).abs().max()) <= 1e-5 * float(mx) for q in peers), "replicas drifted beyond rounding"
+    tb.resync()
+    chk = tb.V.double().sum().reshape(1)
+    dist.all_gather(both, chk)
+    assert all(torch.equal(b, both[0]) for b in both), "resync did not make the replicas identical"
     # evaluation: item-sharded = one all-gather of the item shards + user slices; user-sharded = local users
     from recsys_pytorch_b200 import engine
     from recsys_pytorch_b200.dist import allgather_rows, evaluate_user_shard

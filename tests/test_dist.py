@@ -174,6 +174,26 @@ def test_user_sharded_equals_single_device_oracle(dev):
 
 
 @pytest.mark.gpu
+def test_step_diff_world1_equals_delta_buffer_step(dev):
+    """step_diff (kernel updates the replica in place, V - snapshot is exchanged) against the delta-buffer step on
+    one rank: identical SGD sums, different summation order."""
+    from recsys_pytorch_b200.dist import UserShardedBPR
+    rng = np.random.default_rng(11)
+    nu, ni, d, B = 3000, 500, 128, 1024
+    _, csr = _csr(rng, nu, ni, 2, 20, dev)
+    a = UserShardedBPR(nu, ni, d, csr, 0, 1, dev, lr=2.0, reg=0.01, init_std=0.1, seed=4)
+    b = UserShardedBPR(nu, ni, d, csr, 0, 1, dev, lr=2.0, reg=0.01, init_std=0.1, seed=4)
+    for s in range(4):
+        users = torch.from_numpy(rng.permutation(nu)[:B].astype(np.int32)).to(dev)
+        a.step(users, s + 1, B)
+        b.step_diff(users, s + 1, B)
+    b.flush()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(b.V.cpu().numpy(), a.V.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(b.U.cpu().numpy(), a.U.cpu().numpy(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_sharded_evaluation_matches_evaluator(dev):
     """SURVEY 8(e) scoring: users are independent units - the per-shard metric sums add up to the Evaluator's means."""
     from recsys_pytorch_b200 import engine

@@ -39,6 +39,8 @@ for s in range(n_steps):
         allreduce_sum(buf)
         ev[s]["a1"].record(comm)
         done[cur].record(comm)
+    if os.environ.get("SYNC", "0") == "1":
+        main.wait_event(done[cur])            # no overlap: the next kernel waits for this step's all-reduce
     if pending is not None:
         main.wait_event(done[pending])
         ev[s]["p0"].record(main)
