@@ -397,9 +397,10 @@ def main():
     ap.add_argument("--no-secondary", dest="no_secondary", action="store_true")
     ap.add_argument("--wire", default="fp32", choices=["fp32", "bf16"],
                     help="N>1 user_sharded: dtype of the all-reduced item-delta buffer")
-    ap.add_argument("--exchange", default="diff", choices=["diff", "buffer"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "diff", "buffer"],
                     help="N>1 user_sharded: 'diff' = kernel updates the item replica in place and the difference is "
-                         "all-reduced (default); 'buffer' = kernel accumulates item deltas in a separate dense buffer")
+                         "all-reduced; 'buffer' = kernel accumulates item deltas in a separate dense buffer; 'auto' = "
+                         "diff at N=2 (measured 3.44 vs 3.18 G triples/s), buffer at N>=4 (6.20 vs 5.23 G at N=4)")
     ap.add_argument("--small", action="store_true", help="tiny shapes for a quick functional run (NOT a bench value)")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

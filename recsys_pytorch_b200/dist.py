@@ -312,7 +312,9 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
         B_glob = B_local * world
 
         sync_mode = os.environ.get("B200REC_DIST_SYNC", "0") == "1"
-        exchange = getattr(args, "exchange", "diff")
+        exchange = getattr(args, "exchange", "auto")
+        if exchange == "auto":      # measured: diff wins at N=2, the delta buffer at N=4 (profiles/r01_run30/31)
+            exchange = "diff" if world <= 2 else "buffer"
         if tr.wire_bf16 and exchange == "diff":
             exchange = "buffer"
 
@@ -398,6 +400,7 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
                "config": {"workload": "BPRMF synthetic %dx%d d=%d, %s over %d GPUs" % (nu, ni, d, layout, world),
                           "batch_triples": B_glob, "per_gpu_triples": B_local, "optimizer": "sgd+l2",
                           "parallelism": "%s%d" % (layout, world), "collective": coll, "gather": args.gather,
+                          "exchange": (exchange if layout == "user_sharded" else None),
                           "l2_policy": "inputs larger than L2"},
                "clocks": clk,
                "e2e": {"value": B_glob * args.steps / (ms_e2e * 1e-3), "unit": "triples/s",
