@@ -491,3 +491,28 @@ def test_item_delta_bf16_sink_and_apply(dev, d):
     np.testing.assert_array_equal(V.cpu().numpy(), _dev_table(V0, dev).cpu().numpy() + got)
     with pytest.raises(_lib.B200RecError):                                 # refines F_ITEM_DELTA only
         engine.bpr_step(U, V, d, tu, ti, tj, lr=0.1, sink=SINK_UPDATE, flags=F_ITEM_DELTA_BF16, gV=dV)
+
+
+def test_dataset_device_split_on_cuda(dev, tmp_path):
+    """the vectorised split runs on the device and obeys the reference's split law; the resulting
+    matrices feed the engine as DeviceCSRs."""
+    import math
+    from recsys_pytorch_b200.dataset import UIRTDataset, split_by_user_device
+    rng = np.random.default_rng(9)
+    nu = 500
+    deg = rng.integers(10, 80, nu)
+    u = np.repeat(np.arange(nu), deg)
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    held = split_by_user_device(torch.from_numpy(u).to(dev), torch.zeros(len(u), device=dev), 0.2, True, g)
+    np.testing.assert_array_equal(np.bincount(u[held.cpu().numpy()], minlength=nu), np.ceil(0.2 * deg).astype(np.int64))
+    lines = []
+    for uu in range(40):
+        for it in rng.choice(300, int(deg[uu]), replace=False):
+            lines.append(f"{uu + 5},{it + 1000},4,{rng.integers(0, 10**6)}")
+    p = tmp_path / "toy.csv"; p.write_text("\n".join(lines) + "\n")
+    ds = UIRTDataset(str(p), separator=",", min_item_per_user=10, split="device", device=dev, seed=4)
+    tr = ds.device_csr("train_data", dev)
+    assert tr.shape == (ds.num_users, ds.num_items) and tr.nnz == ds.train_data.nnz
+    for row in range(ds.num_users):
+        k_test = math.ceil(0.1 * deg[row])
+        assert ds.test_target[row].nnz == k_test and ds.valid_target[row].nnz == math.ceil(0.2 * (deg[row] - k_test))
