@@ -8,7 +8,7 @@ this package is the host-side mirror of the reference's Python interface.
 from . import _lib  # noqa: F401
 from ._lib import B200RecError, LIB_PATH  # noqa: F401
 
-__all__ = ["MF", "B200MF", "BaseModel", "PairwiseGenerator", "Evaluator", "engine", "B200RecError"]
+__all__ = ["MF", "B200MF", "BaseModel", "LightGCN", "PairwiseGenerator", "Evaluator", "UIRTDataset", "engine", "B200RecError"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require torch.cuda
@@ -24,7 +24,10 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name in ("Evaluator", "predict_topk_func", "eval_func_router", "Statistics"):
         from . import evaluation
         return getattr(evaluation, name)
-    if name in ("engine", "synthetic", "dist", "evaluation", "generators", "mf", "lightgcn"):
+    if name == "UIRTDataset":
+        from .dataset import UIRTDataset
+        return UIRTDataset
+    if name in ("engine", "synthetic", "dist", "evaluation", "generators", "mf", "lightgcn", "dataset"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)
