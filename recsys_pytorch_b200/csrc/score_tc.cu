@@ -233,10 +233,10 @@ struct TcParams {
     uint64_t *cand;                  // [n_rows, kCand]  (ordered approx score << 32 | sorted item position)
     int32_t *cand_cnt;               // [n_rows]  (-1 = overflow: re-do with the exact kernel)
     float *dump;                     // bring-up: dense [n_rows_pad, n_tiles*kBN] approx scores (sorted order), else NULL
-    int ablate;                      // diagnostics (B200REC_TC_ABLATE): 1 no appends, 2 no filter, 4 no TMEM loads, 8 no TMA
+    int ablate;                      // diagnostics (B200REC_TC_ABLATE, ping-pong kernel): 1 no appends, 2 no filter, 4 no TMEM loads, 8 no TMA, 128 no bootstrap
     float *dbg_row;                  // diagnostics: per row [appends, final count, tau, cu]; or NULL
     unsigned long long *dbg_warp;    // diagnostics: per (block, epilogue warp) [total, wait, raise cycles, raises]; or NULL
-    unsigned long long *dbg;         // diagnostics: [0] appends, [1] raises, [2] warp-chunks with a hit, [3] warp-chunks; or NULL
+    unsigned long long *dbg;         // diagnostics: [0] appends, [1] raises, [4] wait / [5] raise / [7] total cycles (sums), [8..11] maxima; or NULL
 };
 
 // asynchronous 64-column load (no wait) and the wait that also pins the destination registers: the
@@ -398,8 +398,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, const int row0, c
     }
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * TILE;   // + stage offset (N=128 kernel)
     const int abl = DIAG ? p.ablate : 0;
-    unsigned long long d_app = 0, d_raise = 0, d_hit = 0, d_chunks = 0;
-    long long d_wait = 0, d_rcyc = 0, d_acyc = 0;
+    unsigned long long d_app = 0, d_raise = 0;
+    long long d_wait = 0, d_rcyc = 0;
     const long long c_start = DIAG ? clock64() : 0;
     uint32_t ra[64], rb[64];
     // one 64-column chunk: FMNMX3 max tree against the row threshold.  Survivors of a hit group are appended
@@ -517,9 +517,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, const int row0, c
     if (DIAG && p.dbg) {
         atomicAdd(p.dbg + 0, d_app);
         if (lane == 0) {
-            atomicAdd(p.dbg + 1, d_raise); atomicAdd(p.dbg + 2, d_hit); atomicAdd(p.dbg + 3, d_chunks);
+            atomicAdd(p.dbg + 1, d_raise);
             atomicAdd(p.dbg + 4, (unsigned long long)d_wait); atomicAdd(p.dbg + 5, (unsigned long long)d_rcyc);
-            atomicAdd(p.dbg + 6, (unsigned long long)d_acyc);
             atomicAdd(p.dbg + 7, (unsigned long long)(clock64() - c_start));
             if (p.dbg_warp) {
                 unsigned long long *w = p.dbg_warp + ((size_t)blockIdx.x * kEpiWarps + ew) * 4;
