@@ -120,3 +120,25 @@ def test_tc_large_catalogue_properties(dev):
     sample = users[::16].contiguous()
     ie, se = engine.score_topk(U, V, d, sample, mask, k, algo=SCORE_EXACT)
     assert torch.equal(it[::16], ie) and torch.equal(st[::16], se)
+
+
+def test_tc_more_users_than_one_launch_holds(dev):
+    """The TC path works through the users in chunks of 148*256*2 = 75 776 rows (cfg5 has 10M): the second chunk
+    re-uses the candidate lists, filters and the fp16 user tile of the first."""
+    rng = np.random.default_rng(77)
+    nu, ni, d, k = 75_776 + 300, 2_000, 32, 10
+    U, V = _tables(rng, nu, ni, d, dev, 0.3)
+    deg = rng.integers(0, 12, nu)
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum(deg)
+    cols = np.empty(int(indptr[-1]), np.int32)
+    for u in range(nu):                                     # sorted unique columns per row
+        cols[indptr[u]:indptr[u + 1]] = np.sort(rng.choice(ni, deg[u], replace=False))
+    mask = engine.DeviceCSR(torch.from_numpy(indptr).to(dev), torch.from_numpy(cols).to(dev), (nu, ni))
+    users = torch.from_numpy(rng.permutation(nu).astype(np.int32)).to(dev)
+    it, st = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_TC)
+    tail = torch.arange(75_776 - 200, nu, device=dev)       # rows on both sides of the chunk boundary
+    ie, se = engine.score_topk(U, V, d, users[tail].contiguous(), mask, k, algo=SCORE_EXACT)
+    assert torch.equal(it[tail], ie) and torch.equal(st[tail], se)
+    head = torch.arange(0, 500, device=dev)
+    ie, se = engine.score_topk(U, V, d, users[head].contiguous(), mask, k, algo=SCORE_EXACT)
+    assert torch.equal(it[head], ie) and torch.equal(st[head], se)
