@@ -123,3 +123,67 @@ class PairwiseGenerator:
                 bp = torch.tensor(bp, dtype=torch.long, device=self.device)
                 bn = torch.tensor(bn, dtype=torch.long, device=self.device)
             yield bu, bp, bn
+
+
+class PointwiseGenerator:
+    """Host mirror of `data/generators.py::PointwiseGenerator` (:43-136) - the batch source of the reference's
+    POINTWISE MF mode (models/MF.py:49-52).  Same constructor keywords and iteration
+    contract: `(users, items, ratings)` (int64, int64, float32 tensors on `device`) when `return_rating`, else
+    `(users, items)`.  Reproduces the reference draw for draw (same np.random call sequence), including its quirk:
+    `sample_negatives` ignores the batch it is handed and draws `num_negatives` unobserved items for EVERY user of the
+    matrix, so each batch carries `num_users * num_negatives` extra zero-rated rows (generators.py:79-101,121-126).
+    Host side only (numpy): the fused device step for this mode is the next kernel to write."""
+
+    def __init__(self, input_matrix, return_rating=True, as_numpy=False, negative_sample=True, num_negatives=1,
+                 batch_size=32, shuffle=True, device=None):
+        self.input_matrix = input_matrix.tocsr()
+        self.return_rating, self.as_numpy = return_rating, as_numpy
+        self.negative_sample, self.num_negatives = negative_sample, num_negatives
+        self.batch_size, self.shuffle = int(batch_size), shuffle
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        m = self.input_matrix
+        self.users = np.repeat(np.arange(m.shape[0]), np.diff(m.indptr))        # :58-70 without the per-user loop
+        self.items = m.indices.astype(np.int64).copy()
+        self.ratings = m.data.astype(np.float64).copy() if return_rating else np.array([])
+        self._num_data = len(self.users)
+
+    def sample_negatives(self, users=None):
+        """generators.py:79-101: one exact-uniform draw over the non-positives per user, for ALL users."""
+        m = self.input_matrix
+        num_users, num_items = m.shape
+        out_u, out_i = [], []
+        for u in range(num_users):
+            prob = np.ones(num_items)
+            prob[m.indices[m.indptr[u]:m.indptr[u + 1]]] = 0.0
+            prob = prob / sum(prob)                      # python sum, as generators.py:90 (bit-identical p vector)
+            neg = np.random.choice(num_items, size=self.num_negatives, replace=False, p=prob)
+            out_u += [u] * len(neg)
+            out_i += neg.tolist()
+        out_u, out_i = np.array(out_u), np.array(out_i)
+        return out_u, out_i, np.zeros_like(out_u)
+
+    def __len__(self):
+        return int(np.ceil(self._num_data / self.batch_size))
+
+    def __iter__(self):
+        perm = np.random.permutation(self._num_data) if self.shuffle else np.arange(self._num_data)
+        for st in range(0, self._num_data, self.batch_size):
+            idx = perm[st:min(st + self.batch_size, self._num_data)]
+            bu, bi = self.users[idx], self.items[idx]
+            if not self.return_rating:
+                if self.as_numpy:
+                    yield bu, bi
+                else:
+                    yield (torch.tensor(bu, dtype=torch.long, device=self.device),
+                           torch.tensor(bi, dtype=torch.long, device=self.device))
+                continue
+            br = self.ratings[idx]
+            if self.negative_sample and self.num_negatives > 0:
+                nu_, ni_, nr_ = self.sample_negatives(bu)
+                bu, bi, br = np.concatenate((bu, nu_)), np.concatenate((bi, ni_)), np.concatenate((br, nr_))
+            if self.as_numpy:
+                yield bu, bi, br
+            else:
+                yield (torch.tensor(bu, dtype=torch.long, device=self.device),
+                       torch.tensor(bi, dtype=torch.long, device=self.device),
+                       torch.tensor(br, dtype=torch.float32, device=self.device))

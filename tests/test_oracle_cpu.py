@@ -220,3 +220,43 @@ def test_oracle_sparse_adam(golden):
             np.testing.assert_allclose(U, t["U"][s], rtol=1e-4, atol=2e-6)
             np.testing.assert_allclose(V, t["V"][s], rtol=1e-4, atol=2e-6)
             s += 1
+
+
+# ---- pointwise MF mode: oracle + host generator pinned to the reference ----
+@pytest.mark.parametrize("lf", ["ce", "mse"])
+def test_oracle_pointwise_loss_grads_and_adam(golden, lf):
+    g = golden["tiny_pointwise"]
+    sc = float(g[f"{lf}_scale"])
+    t = golden["tiny_bpr"]
+    U, V = (t["U0"] * sc).astype(np.float32), (t["V0"] * sc).astype(np.float32)
+    u, i, r = g["users"][0], g["items"][0], g["ratings"][0]
+    loss, x = O.pointwise_loss(U, V, u, i, r, lf)
+    np.testing.assert_allclose(x, g[f"{lf}_scores"], rtol=2e-6, atol=2e-6)
+    assert abs(float(loss) - float(g[f"{lf}_loss"])) <= 2e-6 * max(1.0, abs(float(g[f"{lf}_loss"])))
+    dU, dV, _, _ = O.pointwise_grads(U, V, u, i, r, lf)
+    np.testing.assert_allclose(dU, g[f"{lf}_dU"], rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(dV, g[f"{lf}_dV"], rtol=2e-5, atol=2e-7)
+    opt = O.DenseAdam([U.shape, V.shape])                      # the reference's optimiser as-is (MF.py:30)
+    for b in range(3):
+        dU, dV, _, _ = O.pointwise_grads(U, V, g["users"][b], g["items"][b], g["ratings"][b], lf)
+        U, V = opt.step([U, V], [dU, dV])
+    np.testing.assert_allclose(U, g[f"{lf}_adam_U"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(V, g[f"{lf}_adam_V"], rtol=1e-4, atol=2e-6)
+
+
+def test_pointwise_generator_mirror_reproduces_reference_batches(golden):
+    import scipy.sparse as sp
+    from recsys_pytorch_b200.generators import PointwiseGenerator
+    g = golden["tiny_pointwise"]
+    R = sp.csr_matrix((np.ones(len(g["R_indices"])), g["R_indices"], g["R_indptr"]), shape=tuple(g["R_shape"]))
+    np.random.seed(99)
+    gen = PointwiseGenerator(R, return_rating=True, num_negatives=1, batch_size=32, shuffle=True, as_numpy=True)
+    assert len(gen) == int(g["gen_num_batches"])
+    bu, bi, br, lens = [], [], [], []
+    for _ in range(2):
+        for (a, b, c) in gen:
+            bu.append(a); bi.append(b); br.append(c); lens.append(len(a))
+    np.testing.assert_array_equal(lens, g["gen_lens"])
+    np.testing.assert_array_equal(np.concatenate(bu), g["gen_users"])
+    np.testing.assert_array_equal(np.concatenate(bi), g["gen_items"])
+    np.testing.assert_array_equal(np.concatenate(br).astype(np.float32), g["gen_ratings"])
