@@ -125,6 +125,18 @@ typedef struct b200rec_bpr_args {
  * autograd's "all gradients from pre-step weights" semantics exactly. */
 int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream);
 
+/* Pointwise MF step (models/MF.py:63-68 with the pointwise branch MF.py:101-102):
+ *   x_b = U[users[b]] . V[items[b]];  loss_kind 0: F.binary_cross_entropy_with_logits(x, ratings) ('ce', MF.py:21),
+ *   loss_kind 1: F.mse_loss(x, ratings), both reduction='mean' (scale inv_batch, 0 = 1/B).
+ * sink = B200REC_SINK_UPDATE (rows updated in place with -lr * (grad + reg/B * row), vector atomics),
+ *        B200REC_SINK_GRAD (raw gradient rows accumulated into dense gU/gV, for the reference's dense Adam) or
+ *        B200REC_SINK_NONE (loss only).  loss_sum (device double, may be NULL) receives the SUM of per-sample losses.
+ * STATUS: written against oracle/bpr_oracle.py::pointwise_loss/_grads (pinned to the reference's outputs in
+ * tests/golden/tiny_pointwise.npz); its device test (tests/test_gpu_pointwise.py) has not run on hardware yet. */
+int b200rec_pointwise_step(float *U, float *V, int ld, int d, const int32_t *users, const int32_t *items,
+                           const float *ratings, int B, int loss_kind, float lr, float reg, int sink,
+                           float *gU, float *gV, double *loss_sum, float inv_batch, void *stream);
+
 /* data/generators.py:168-201 on the device, sampling only: for each users[t] draw
  * (pos, neg) with the same counter RNG the fused step uses for (seed, step, t).
  * out_pos[t] = out_neg[t] = -1 for users without positives. */

@@ -54,6 +54,7 @@ _PROTOS = {
     "b200rec_evaluate_loo": (_I, [_I, _P, _I, _P, _I, _P, _P]),
     "b200rec_mf_forward": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "b200rec_bpr_step": (_I, [C.POINTER(BprArgs), _P]),
+    "b200rec_pointwise_step": (_I, [_P, _P, _I, _I, _P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _F, _P]),
     "b200rec_sample_triples": (_I, [_P, _I, _P, _P, _I, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "b200rec_bpr_apply": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _P]),
     "b200rec_rows_add": (_I, [_P, _I, _P, _I, _P, _I, _F, _P]),

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (B200RecError, BprArgs, F_TMA_GATHER, F_USERS_UNIQUE, SCORE_EXACT, SCORE_TC, SINK_GRAD,
                    SINK_STAGE, SINK_UPDATE, check, current_stream, ptr, require_cuda)
 
-__all__ = ["DeviceCSR", "padded_dim", "alloc_table", "mf_forward", "bpr_step", "bpr_apply", "sample_triples",
+__all__ = ["pointwise_step", "DeviceCSR", "padded_dim", "alloc_table", "mf_forward", "bpr_step", "bpr_apply", "sample_triples",
            "sgd_dense", "adam_dense", "score_topk", "predict_dense", "topk_rows", "holdout_metrics", "loo_metrics",
            "column_means", "spmm_csr", "spmm_plan", "SpmmPlan"]
 
@@ -98,6 +98,21 @@ def bpr_step(U, V, d, users, pos=None, neg=None, csr: DeviceCSR | None = None, l
     a.udelta = ptr(require_cuda(udelta, "udelta", torch.float32)) if udelta is not None else None
     a.inv_batch = float(inv_batch)
     check(_lib.lib().b200rec_bpr_step(C.byref(a), current_stream()))
+
+
+def pointwise_step(U, V, d, users, items, ratings, loss_func="ce", lr=0.0, reg=0.0, sink=SINK_UPDATE, gU=None, gV=None,
+                   loss_sum=None, inv_batch=0.0):
+    """models/MF.py:63-68 in pointwise mode (MF.py:101-102) as one fused kernel (see b200rec_pointwise_step).
+    Not yet validated on hardware."""
+    require_cuda(U, "U", torch.float32); require_cuda(V, "V", torch.float32)
+    ratings = require_cuda(ratings, "ratings", torch.float32)
+    check(_lib.lib().b200rec_pointwise_step(
+        ptr(U), ptr(V), U.shape[1], d, ptr(_i32(users, "users")), ptr(_i32(items, "items")), ptr(ratings),
+        users.numel(), 1 if loss_func == "mse" else 0, float(lr), float(reg), int(sink),
+        ptr(require_cuda(gU, "gU", torch.float32)) if gU is not None else None,
+        ptr(require_cuda(gV, "gV", torch.float32)) if gV is not None else None,
+        ptr(require_cuda(loss_sum, "loss_sum", torch.float64)) if loss_sum is not None else None,
+        float(inv_batch), current_stream()))
 
 
 def bpr_apply(U, V, users, pos, neg, stage):

@@ -182,6 +182,11 @@ def test_cabi_argument_errors_without_gpu(built_lib):
     assert b"NULL" in built_lib.b200rec_last_error()
     sc = np.zeros((2, 8), np.float32); out = np.zeros((2, 4), np.int32)
     assert built_lib.b200rec_top_k_array_index(sc.ctypes.data, 8, 2, 9, out.ctypes.data) == _lib.EINVAL   # k > cols
+    assert built_lib.b200rec_pointwise_step(None, None, 8, 8, None, None, None, 4, 0, 0.1, 0.0, 0, None, None, None, 0.0,
+                                            None) == _lib.EINVAL
+    assert built_lib.b200rec_spmm_csr_split(None, None, None, 4, None, 8, 8, None, 8, None, 8, 1.0, 0, 256, None, None, 0,
+                                            None, None, 0, None, None) == _lib.EINVAL
+    assert built_lib.b200rec_delta_diff(None, None, None, None, 8, None) == _lib.EINVAL
     import torch
     if not torch.cuda.is_available():
         rc = built_lib.b200rec_top_k_array_index(sc.ctypes.data, 8, 2, 4, out.ctypes.data)
