@@ -792,6 +792,85 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
     }
 }
 
+// Re-rank, staged variant (B200REC_RERANK=2; NOT the default: written after the round's GPU minutes were spent, it
+// has not run on hardware yet).  The default kernel lets every lane walk its own candidate's V row straight from L2
+// (ncu run 24: 30 % of the stalls sit on those loads inside the FMA chain); here the warp first copies the rows of up to
+// RC candidates into shared memory with coalesced 16-byte loads that are all in flight at once, then RC lanes run the
+// SAME k-ordered fp32 FMA chain out of shared memory (row stride d_pad + 4 floats: conflict-free float4 reads).
+constexpr int kRerankRC = 8;
+__global__ void __launch_bounds__(256) rerank_staged_kernel(const float *__restrict__ U, const float *__restrict__ V, int ld,
+                                                            int d, const int32_t *__restrict__ users, int n_rows, int k,
+                                                            const int64_t *__restrict__ mask_indptr,
+                                                            const int32_t *__restrict__ mask_indices,
+                                                            const int32_t *__restrict__ item_of_pos,
+                                                            const uint64_t *__restrict__ cand,
+                                                            const int32_t *__restrict__ cand_cnt, int32_t *__restrict__ out_idx,
+                                                            float *__restrict__ out_score, int32_t *__restrict__ redo_rows,
+                                                            int32_t *__restrict__ redo_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int dp = (d + 3) & ~3;                       // d rounded up to a float4; ld >= dp (tables are padded with zeros)
+    const int vstride = dp + 4;
+    uint64_t *rk = reinterpret_cast<uint64_t *>(smem_raw) + (size_t)wid * k;
+    float *us = reinterpret_cast<float *>(smem_raw + (size_t)8 * k * 8) + (size_t)wid * dp;
+    float *vs = reinterpret_cast<float *>(smem_raw + (size_t)8 * k * 8 + (size_t)8 * dp * 4) + (size_t)wid * kRerankRC * vstride;
+    for (int row = blockIdx.x * 8 + wid; row < n_rows; row += gridDim.x * 8) {
+        const int n = cand_cnt[row];
+        if (n < 0) {
+            if (lane == 0) redo_rows[atomicAdd(redo_count, 1)] = row;
+            continue;
+        }
+        const int u = users[row];
+        for (int c = lane * 4; c < dp; c += 128) *reinterpret_cast<float4 *>(us + c) = ld4(U + (int64_t)u * ld + c);
+        for (int pp = lane; pp < k; pp += 32) rk[pp] = make_key(-INFINITY, 0x7FFFFFFF);
+        __syncwarp();
+        const int32_t *mrow = nullptr;
+        int mdeg = 0;
+        if (mask_indptr) { mrow = mask_indices + mask_indptr[u]; mdeg = (int)(mask_indptr[u + 1] - mask_indptr[u]); }
+        for (int c0 = 0; c0 < n; c0 += kRerankRC) {
+            int item = 0;
+            bool ok = lane < kRerankRC && c0 + lane < n;
+            if (ok) {
+                item = item_of_pos[(uint32_t)(cand[(size_t)row * kCand + c0 + lane] & 0x7FFFFFFFu)];
+                int l = 0, r = mdeg;  // masked? (models/MF.py:130)
+                while (l < r) { const int m = (l + r) >> 1; if (mrow[m] < item) l = m + 1; else r = m; }
+                if (l < mdeg && mrow[l] == item) ok = false;
+            }
+            const unsigned okm = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+            for (int j = 0; j < kRerankRC; ++j) {      // coalesced staging of the surviving rows, all loads independent
+                const int it_j = __shfl_sync(0xffffffffu, item, j);
+                if ((okm >> j) & 1u)
+                    for (int c = lane * 4; c < dp; c += 128)
+                        *reinterpret_cast<float4 *>(vs + j * vstride + c) = ldg4(V + (int64_t)it_j * ld + c);
+            }
+            __syncwarp();
+            uint64_t key = 0;
+            if (ok) {
+                const float *pv = vs + lane * vstride;
+                float acc = 0.f;
+                int kk = 0;
+                for (; kk + 4 <= d; kk += 4) {          // ascending k: the oracle's FMA order
+                    const float4 x = *reinterpret_cast<const float4 *>(us + kk);
+                    const float4 y = *reinterpret_cast<const float4 *>(pv + kk);
+                    acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+                    acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+                }
+                for (; kk < d; ++kk) acc = fmaf(us[kk], pv[kk], acc);
+                key = make_key(acc, item);
+            }
+            topk_list_offer(rk, k, key, ok, lane);
+            __syncwarp();
+        }
+        __syncwarp();
+        for (int pp = lane; pp < k; pp += 32) {
+            out_idx[(int64_t)row * k + pp] = key_id(rk[pp]);
+            if (out_score) out_score[(int64_t)row * k + pp] = key_score(rk[pp]);
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void gather_ids_kernel(const int32_t *users, const int32_t *rows, int n, int32_t *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = users[rows[i]];
@@ -1121,8 +1200,21 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         }
         cudaEvent_t er0 = nullptr, er1 = nullptr;
         if (diag) { cudaEventCreate(&er0); cudaEventCreate(&er1); cudaEventRecord(er0, s); }
-        rerank_kernel<<<rgrid, 256, rsmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, order, cand, cnt,
-                                                oi + (size_t)r0 * k, os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
+        const bool staged = getenv("B200REC_RERANK") && atoi(getenv("B200REC_RERANK")) == 2 && (ld & 3) == 0;
+        if (staged) {   // experimental (see rerank_staged_kernel); the default stays the validated kernel
+            const size_t dp = (size_t)((d + 3) & ~3);
+            const size_t ssmem = (size_t)8 * k * 8 + 8 * dp * 4 + (size_t)8 * kRerankRC * (dp + 4) * 4;
+            B200_CUDA(cudaFuncSetAttribute(rerank_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+            int occ = 0, sgrid = (nr + 7) / 8;
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rerank_staged_kernel, 256, ssmem));
+            if (occ < 1) occ = 1;
+            if (sgrid > sms * occ) sgrid = sms * occ;
+            rerank_staged_kernel<<<sgrid, 256, ssmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, order, cand, cnt,
+                                                          oi + (size_t)r0 * k, os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
+        } else {
+            rerank_kernel<<<rgrid, 256, rsmem, s>>>(U, V, ld, d, users + r0, nr, k, mi, mx, order, cand, cnt,
+                                                    oi + (size_t)r0 * k, os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
+        }
         B200_LAUNCH_CHECK();
         if (diag) {
             cudaEventRecord(er1, s); cudaEventSynchronize(er1);
