@@ -167,6 +167,65 @@ int b200rec_adam_dense(float *param, const float *grad, float *exp_avg, float *e
                        int64_t n, float lr, float beta1, float beta2, float eps, int step,
                        void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * multi-GPU: item table sharded by item-id range (north_star), user table sharded by user-id range, user rows
+ * exchanged through NVSwitch peer memory INSIDE the fused step (csrc/p2p.cu).  The reference is single-device; the
+ * per-step semantics are those of b200rec_bpr_step.  One process per GPU; pointers of other ranks are peer-mapped
+ * (b200rec_peer_import) or, for single-process emulation in the tests, plain local pointers.
+ * ------------------------------------------------------------------------- */
+#define B200REC_MAX_RANKS 16
+#define B200REC_PEER_HANDLE_BYTES 64
+
+typedef struct b200rec_p2p_route_args {
+    const int32_t *users;      /* [B] LOCAL row ids of this rank's batch users                                  */
+    const int32_t *pos, *neg;  /* [B] GLOBAL item ids, or NULL -> sampled on device (neg from owner(pos)'s range) */
+    int32_t B;
+    const int64_t *csr_indptr; /* CSR shard: rows = this rank's users (local ids), columns = GLOBAL item ids     */
+    const int32_t *csr_indices;
+    uint64_t seed, step;
+    int32_t world, rank;
+    int32_t item_bounds[B200REC_MAX_RANKS + 1]; /* rank r holds items [item_bounds[r], item_bounds[r+1])         */
+    /* outbox in this rank's exported memory: triples for owner d at out_*[d*cap + k], k < out_cnt[d]            */
+    int32_t *out_u, *out_i, *out_j, *out_cnt;
+    int32_t cap;               /* >= B                                                                           */
+    int32_t *dbg_pos, *dbg_neg;/* optional [B]: the (pos, neg) drawn for users[t], -1 = skipped                  */
+} b200rec_p2p_route_args;
+
+/* sample + bucket this rank's batch by owner(pos) into its outbox (local kernel; zeroes out_cnt first) */
+int b200rec_p2p_route(const b200rec_p2p_route_args *args, void *stream);
+
+typedef struct b200rec_p2p_step_args {
+    int32_t world, rank, ld, d;
+    float *U_peer[B200REC_MAX_RANKS];  /* user-table shard base of every rank ([rank] = this rank's own)         */
+    float *V_peer[B200REC_MAX_RANKS];  /* item-table shard base of every rank                                    */
+    int32_t item_bounds[B200REC_MAX_RANKS + 1];
+    /* for every source rank s: the outbox segment s routed to THIS rank (already offset by rank*cap) + its count */
+    const int32_t *in_u[B200REC_MAX_RANKS], *in_i[B200REC_MAX_RANKS], *in_j[B200REC_MAX_RANKS];
+    const int32_t *in_cnt[B200REC_MAX_RANKS];
+    float lr, reg, inv_batch;  /* inv_batch = 1 / GLOBAL batch                                                   */
+    int32_t flags;             /* B200REC_F_USERS_UNIQUE: user rows written back with plain stores               */
+    double *loss_sum;          /* optional local device scalar                                                   */
+    int32_t *n_processed;      /* optional local device int: triples this rank processed                         */
+} b200rec_p2p_step_args;
+
+/* fused step over the triples routed to this rank: user row <- home rank (peer load), item rows local (peer only
+ * when a given negative lives elsewhere), item updates by vector atomics, user row -> home rank (peer store). */
+int b200rec_p2p_step(const b200rec_p2p_step_args *args, void *stream);
+
+/* peer memory: cudaMalloc'd (IPC-exportable) allocation, 64-byte handle, import on another process of the box */
+int b200rec_peer_alloc(int64_t bytes, void **dev_ptr);
+int b200rec_peer_free(void *dev_ptr);
+int b200rec_peer_export(void *dev_ptr, void *handle64);
+int b200rec_peer_import(const void *handle64, void **dev_ptr);
+int b200rec_peer_close(void *dev_ptr);
+/* dst[0..bytes) = src[0..bytes) on `stream`; either side may be a peer-mapped pointer (UVA device-to-device copy) */
+int b200rec_peer_copy(void *dst, const void *src, int64_t bytes, void *stream);
+
+/* L2 residency control for a reused table (no reference counterpart; the item table of the BPR step): reserves up
+ * to `bytes` of persisting L2 and installs an access-policy window [base, base+bytes) on `stream`; bytes == 0
+ * removes it.  Affects kernels launched on `stream` afterwards. */
+int b200rec_l2_persist(const void *base, int64_t bytes, float hit_ratio, void *stream);
+
 /* Row-wise (lazy) Adam = torch.optim.SparseAdam semantics: only the rows listed in
  * ids[0..n) move.  `grad` holds the per-row gradient sums produced by b200rec_bpr_step(SINK_GRAD) and is zeroed
  * again row by row; `stamp` (int32 per table row, zero-initialised once) de-duplicates ids within a step; ids < 0

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200rec.so")
+# B200REC_LIB: profiling builds only (tools/build_ablate.sh); the product library is always the in-tree one
+LIB_PATH = os.environ.get("B200REC_LIB") or os.path.join(_HERE, "libb200rec.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SINK_UPDATE, SINK_STAGE, SINK_GRAD, SINK_NONE = 0, 1, 2, 3
@@ -44,6 +45,37 @@ class BprArgs(C.Structure):
     ]
 
 
+MAX_RANKS, PEER_HANDLE_BYTES = 16, 64
+
+
+class P2PRouteArgs(C.Structure):
+    """struct b200rec_p2p_route_args (include/b200rec.h)."""
+    _fields_ = [
+        ("users", C.c_void_p), ("pos", C.c_void_p), ("neg", C.c_void_p), ("B", C.c_int32),
+        ("csr_indptr", C.c_void_p), ("csr_indices", C.c_void_p),
+        ("seed", C.c_uint64), ("step", C.c_uint64),
+        ("world", C.c_int32), ("rank", C.c_int32),
+        ("item_bounds", C.c_int32 * (MAX_RANKS + 1)),
+        ("out_u", C.c_void_p), ("out_i", C.c_void_p), ("out_j", C.c_void_p), ("out_cnt", C.c_void_p),
+        ("cap", C.c_int32),
+        ("dbg_pos", C.c_void_p), ("dbg_neg", C.c_void_p),
+    ]
+
+
+class P2PStepArgs(C.Structure):
+    """struct b200rec_p2p_step_args (include/b200rec.h)."""
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("ld", C.c_int32), ("d", C.c_int32),
+        ("U_peer", C.c_void_p * MAX_RANKS), ("V_peer", C.c_void_p * MAX_RANKS),
+        ("item_bounds", C.c_int32 * (MAX_RANKS + 1)),
+        ("in_u", C.c_void_p * MAX_RANKS), ("in_i", C.c_void_p * MAX_RANKS), ("in_j", C.c_void_p * MAX_RANKS),
+        ("in_cnt", C.c_void_p * MAX_RANKS),
+        ("lr", C.c_float), ("reg", C.c_float), ("inv_batch", C.c_float),
+        ("flags", C.c_int32),
+        ("loss_sum", C.c_void_p), ("n_processed", C.c_void_p),
+    ]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _PROTOS = {
     "b200rec_last_error": (C.c_char_p, []),
@@ -63,6 +95,15 @@ _PROTOS = {
     "b200rec_delta_diff": (_I, [_P, _P, _P, _P, _L, _P]),
     "b200rec_delta_apply": (_I, [_P, _P, _P, _L, _P]),
     "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
+    "b200rec_p2p_route": (_I, [C.POINTER(P2PRouteArgs), _P]),
+    "b200rec_p2p_step": (_I, [C.POINTER(P2PStepArgs), _P]),
+    "b200rec_peer_alloc": (_I, [_L, C.POINTER(C.c_void_p)]),
+    "b200rec_peer_free": (_I, [_P]),
+    "b200rec_peer_export": (_I, [_P, _P]),
+    "b200rec_peer_import": (_I, [_P, C.POINTER(C.c_void_p)]),
+    "b200rec_peer_close": (_I, [_P]),
+    "b200rec_peer_copy": (_I, [_P, _P, _L, _P]),
+    "b200rec_l2_persist": (_I, [_P, _L, _F, _P]),
     "b200rec_adam_rows": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _F, _F, _F, _F, _I, _P]),
     "b200rec_score_topk_workspace": (_L, [_I, _I, _I, _I, _I]),
     "b200rec_score_topk": (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P, _I, _P, _P, _P, _L, _I, _P]),

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "sampler.cuh"
 
 namespace b200 {
 
@@ -46,48 +47,6 @@ __device__ __forceinline__ float bpr_grad(float x, float invB) {
 
 __device__ __forceinline__ float softplus_neg(float x) {  // -log(sigmoid(x)) = log(1+exp(-x)), stable
     return x > 0.f ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
-}
-
-// lane-parallel triple fetch / on-device sampling (data/generators.py:168-201 semantics:
-// positive uniform in the user's CSR row, negative uniform over non-positives)
-__device__ __forceinline__ void fetch_triple(const b200rec_bpr_args &a, int64_t t, bool &valid, int &u, int &i,
-                                             int &j) {
-    u = i = j = 0;
-    if (!valid) return;
-    u = a.users[t];
-    const bool sample_pos = (a.pos == nullptr), sample_neg = (a.neg == nullptr);
-    if (!sample_pos) i = a.pos[t];
-    if (!sample_neg) j = a.neg[t];
-    if (sample_pos || sample_neg) {
-        const int64_t lo = a.csr_indptr[u], hi = a.csr_indptr[u + 1];
-        const uint32_t deg = (uint32_t)(hi - lo);
-        if (deg == 0 && sample_pos) {
-            valid = false;  // generators.py:186-189: a user without positives emits no triple
-        } else {
-            const int32_t *row = a.csr_indices + lo;
-            if (sample_pos) i = row[(uint32_t)(((uint64_t)rng_u32(a.seed, a.step, (uint64_t)t, 0) * deg) >> 32)];
-            // item-sharded layout: only the rank owning the positive processes the triple,
-            // and it draws the negative from its own id range
-            const bool sharded = a.item_hi > a.item_lo;
-            const uint32_t n_lo = sharded ? (uint32_t)a.item_lo : 0u;
-            const uint32_t n_cnt = sharded ? (uint32_t)(a.item_hi - a.item_lo) : (uint32_t)a.num_items;
-            if (sharded && (i < a.item_lo || i >= a.item_hi)) valid = false;
-            if (sample_neg && valid) {
-                for (uint32_t tries = 0; tries < 64; ++tries) {
-                    j = (int)(n_lo + (uint32_t)(((uint64_t)rng_u32(a.seed, a.step, (uint64_t)t, 1 + tries) *
-                                                 (uint64_t)n_cnt) >> 32));
-                    uint32_t l = 0, r = deg;  // lower_bound in the sorted row
-                    while (l < r) {
-                        uint32_t m = (l + r) >> 1;
-                        if (row[m] < j) l = m + 1; else r = m;
-                    }
-                    if (!(l < deg && row[l] == j)) break;
-                }
-            }
-        }
-        if (a.out_pos) a.out_pos[t] = valid ? i : -1;
-        if (a.out_neg) a.out_neg[t] = valid ? j : -1;
-    }
 }
 
 // four floats -> four bf16 (round to nearest), added atomically as two bf16x2 words (REDG.E.ADD.BF16x4)
@@ -380,6 +339,15 @@ struct RowSet {
 #ifndef B200REC_FAST_MINB
 #define B200REC_FAST_MINB 3
 #endif
+// Profiling-only build (tools/build_ablate.sh, -DB200REC_ABLATE): B200REC_ABL=<bits> switches parts of the fast
+// kernel off to measure what each costs (results are then WRONG on purpose).  Never compiled into libb200rec.so.
+//   1 item REDs become plain stores   2 no item writes   4 no user write   8 no neg row (load+write)   16 no pos row
+#ifdef B200REC_ABLATE
+__constant__ int c_abl;
+#define ABL(bit) (c_abl & (bit))
+#else
+#define ABL(bit) 0
+#endif
 // IDELTA: the two item-row updates go to the dense fp32 item-delta buffer gV (user-sharded multi-GPU layout: one
 // all-reduce of gV per step) instead of V itself.
 template <int CPL, bool UNIQ, bool LOSS, bool IDELTA = false>
@@ -433,7 +401,16 @@ __global__ void __launch_bounds__(256, CPL == 1 ? B200REC_FAST_MINB : 2) bpr_ste
                     const float *pu = U + (int64_t)r.tu * LD + lane * 4;
                     const float *pi = V + (int64_t)r.ti * LD + lane * 4;
                     const float *pj = V + (int64_t)r.tj * LD + lane * 4;
+#ifdef B200REC_ABLATE
+                    if (ABL(8 | 16)) {
 #pragma unroll
+                        for (int k = 0; k < CPL; ++k) {
+                            r.u[k] = ld4(pu + 128 * k);
+                            r.i[k] = ABL(16) ? make_float4(0.1f, 0.1f, 0.1f, 0.1f) : ld4(pi + 128 * k);
+                            r.j[k] = ABL(8) ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(pj + 128 * k);
+                        }
+                    } else
+#endif
                     if (hints) {
 #pragma unroll
                         for (int k = 0; k < CPL; ++k) {
@@ -478,7 +455,20 @@ __global__ void __launch_bounds__(256, CPL == 1 ? B200REC_FAST_MINB : 2) bpr_ste
                         else red4_hint(pu + 128 * k, du, pol_u);
                         red4_hint(pi + 128 * k, di, pol_v);
                         red4_hint(pj + 128 * k, dj, pol_v);
-                    } else {
+                    }
+#ifdef B200REC_ABLATE
+                    else if (c_abl) {
+                        if (!ABL(4)) {
+                            if (UNIQ) st4(pu + 128 * k, make_float4(r.u[k].x + du.x, r.u[k].y + du.y, r.u[k].z + du.z, r.u[k].w + du.w));
+                            else red4(pu + 128 * k, du);
+                        }
+                        if (!ABL(2)) {
+                            if (ABL(1)) { if (!ABL(16)) st4(pi + 128 * k, di); if (!ABL(8)) st4(pj + 128 * k, dj); }
+                            else { if (!ABL(16)) red4(pi + 128 * k, di); if (!ABL(8)) red4(pj + 128 * k, dj); }
+                        }
+                    }
+#endif
+                    else {
                         if (UNIQ) st4(pu + 128 * k, make_float4(r.u[k].x + du.x, r.u[k].y + du.y, r.u[k].z + du.z, r.u[k].w + du.w));
                         else red4(pu + 128 * k, du);
                         red4(pi + 128 * k, di);
@@ -501,6 +491,120 @@ __global__ void __launch_bounds__(256, CPL == 1 ? B200REC_FAST_MINB : 2) bpr_ste
     }
     if (LOSS) {
         // every lane accumulated the same per-triple value
+        if (lane == 0 && loss_local != 0.f) atomicAdd(p.a.loss_sum, (double)loss_local);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Group fast path: a row is held by a sub-warp group of G lanes (32/G float4 per lane and row), so a warp works on
+// 32/G triples at once.  Why (profiles/r02_bpr_ablation.md): a random 512-byte row gather alone reaches 6.6 TB/s on
+// this part, yet the warp-per-row kernel above needs 0.27 ms just to READ the 1M user rows of a step (1.9 TB/s) - it
+// is bound by its own dependent chain (one triple per warp at a time: 5 shuffle stages + exp + rcp between the loads
+// of consecutive triples), not by memory.  With G = 8 every lane issues 12 independent 16-byte loads per triple
+// group, the reduction is 3 shuffle stages, and the scalar part (sigmoid, loss) is paid once per 4 triples.
+// PF = register sets loaded ahead of the one being computed.
+// ---------------------------------------------------------------------------
+template <int CPL>
+struct GroupSet {
+    float4 u[CPL], i[CPL], j[CPL];
+};
+
+template <int G, int F4, int PF, bool UNIQ, bool LOSS, bool IDELTA>
+__global__ void __launch_bounds__(256) bpr_step_group_kernel(const BprParams p) {
+    constexpr int CPL = F4 / G, TPW = 32 / G, ITERS = 32 / TPW;
+    constexpr int64_t LD = F4 * 4;
+    float *__restrict__ const U = p.a.U;
+    float *__restrict__ const V = p.a.V;
+    float *__restrict__ const VD = IDELTA ? p.a.gV : p.a.V;
+    const int lane = threadIdx.x & 31, sl = lane % G, sg = lane / G;
+    const float c_g = p.a.lr * p.invB;             // delta = c_g*(1-s) * other  + c_r * self
+    const float c_r = -p.a.lr * p.a.reg * p.invB;
+    const int B = p.a.B;
+    const int64_t n_chunks = p.n_chunks;
+    b200rec_bpr_args a = p.a;
+    float loss_local = 0.f;
+    unsigned int *const work = p.work;
+    int64_t c = 0, c_next = 0;
+    if (lane == 0) c = (int64_t)atomicAdd(work, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    for (; c < n_chunks; c = c_next) {
+        if (lane == 0) c_next = (int64_t)atomicAdd(work, 1u);
+        const int64_t t_lane = c * 32 + lane;
+        bool valid = t_lane < B;
+        int u, i, j;
+        fetch_triple(a, t_lane, valid, u, i, j);
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+
+        GroupSet<CPL> set[PF + 1];
+        auto load = [&](GroupSet<CPL> &r, int it) {
+            const int src = it * TPW + sg;
+            const int tu = __shfl_sync(0xffffffffu, u, src);
+            const int ti = __shfl_sync(0xffffffffu, i, src);
+            const int tj = __shfl_sync(0xffffffffu, j, src);
+            if ((vmask >> src) & 1u) {
+                const float *pu = U + (int64_t)tu * LD + sl * 4;
+                const float *pi = V + (int64_t)ti * LD + sl * 4;
+                const float *pj = V + (int64_t)tj * LD + sl * 4;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) r.u[k] = ld4(pu + k * G * 4);
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) r.i[k] = ld4(pi + k * G * 4);
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) r.j[k] = ld4(pj + k * G * 4);
+            }
+        };
+        auto compute = [&](GroupSet<CPL> &r, int it) {
+            const int src = it * TPW + sg;
+            const int tu = __shfl_sync(0xffffffffu, u, src);
+            const int ti = __shfl_sync(0xffffffffu, i, src);
+            const int tj = __shfl_sync(0xffffffffu, j, src);
+            const bool ok = (vmask >> src) & 1u;
+            float part = 0.f;
+            if (ok) {
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    // r.i becomes the difference row (v_i - v_j); r.j keeps v_j (v_i = diff + v_j is not needed: the
+                    // L2 term of the positive row uses the loaded value kept in `vi` below)
+                    part = fmaf(r.u[k].x, r.i[k].x - r.j[k].x, part); part = fmaf(r.u[k].y, r.i[k].y - r.j[k].y, part);
+                    part = fmaf(r.u[k].z, r.i[k].z - r.j[k].z, part); part = fmaf(r.u[k].w, r.i[k].w - r.j[k].w, part);
+                }
+            }
+            const float x = group_sum<G>(part);
+            if (ok) {
+                const float s = __frcp_rn(1.f + __expf(-x));       // sigmoid(x); 1 - s saturates like the reference's fp32
+                const float a1 = c_g * (1.f - s);                   // = -lr * g
+                if (LOSS && sl == 0) loss_local += (x < -15.f) ? -x : -__logf(s);
+                float *pu = U + (int64_t)tu * LD + sl * 4;
+                float *pi = VD + (int64_t)ti * LD + sl * 4;
+                float *pj = VD + (int64_t)tj * LD + sl * 4;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const float4 ru = r.u[k], ri = r.i[k], rj = r.j[k];
+                    float4 du, di, dj;
+                    du.x = fmaf(a1, ri.x - rj.x, c_r * ru.x); du.y = fmaf(a1, ri.y - rj.y, c_r * ru.y);
+                    du.z = fmaf(a1, ri.z - rj.z, c_r * ru.z); du.w = fmaf(a1, ri.w - rj.w, c_r * ru.w);
+                    di.x = fmaf(a1, ru.x, c_r * ri.x); di.y = fmaf(a1, ru.y, c_r * ri.y);
+                    di.z = fmaf(a1, ru.z, c_r * ri.z); di.w = fmaf(a1, ru.w, c_r * ri.w);
+                    dj.x = fmaf(-a1, ru.x, c_r * rj.x); dj.y = fmaf(-a1, ru.y, c_r * rj.y);
+                    dj.z = fmaf(-a1, ru.z, c_r * rj.z); dj.w = fmaf(-a1, ru.w, c_r * rj.w);
+                    if (UNIQ) st4(pu + k * G * 4, make_float4(ru.x + du.x, ru.y + du.y, ru.z + du.z, ru.w + du.w));
+                    else red4(pu + k * G * 4, du);
+                    red4(pi + k * G * 4, di);
+                    red4(pj + k * G * 4, dj);
+                }
+            }
+        };
+#pragma unroll
+        for (int k = 0; k < PF; ++k) load(set[k], k);
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            if (it + PF < ITERS) load(set[(it + PF) % (PF + 1)], it + PF);
+            compute(set[it % (PF + 1)], it);
+        }
+        c_next = __shfl_sync(0xffffffffu, c_next, 0);
+    }
+    if (LOSS) {
+        loss_local = group_sum<32>(loss_local);
         if (lane == 0 && loss_local != 0.f) atomicAdd(p.a.loss_sum, (double)loss_local);
     }
 }
@@ -828,6 +932,44 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
                 if (!ring[dev]) B200_CUDA(cudaMalloc(&ring[dev], 256 * sizeof(unsigned int)));
                 p.work = ring[dev] + (slot[dev]++ & 255u);
                 B200_CUDA(cudaMemsetAsync(p.work, 0, sizeof(unsigned int), s));
+            }
+        }
+#ifdef B200REC_ABLATE
+        {
+            const int abl = getenv("B200REC_ABL") ? atoi(getenv("B200REC_ABL")) : 0;
+            B200_CUDA(cudaMemcpyToSymbolAsync(c_abl, &abl, sizeof(int), 0, cudaMemcpyHostToDevice, s));
+        }
+#endif
+        // group kernel (default for ld = 128; B200REC_STEP_VARIANT="G,PF" selects another instantiation, "0,0" the
+        // warp-per-row kernel below)
+        {
+            const char *var = getenv("B200REC_STEP_VARIANT");
+            int vg = 8, vpf = 0;      // measured best at cfg2 (profiles/r02_bpr_ablation.md); "0,0" = warp-per-row kernel
+            if (var && sscanf(var, "%d,%d", &vg, &vpf) != 2) { vg = 8; vpf = 0; }
+            if (vg > 0 && p.work && CPL == 1 && !(a.flags & B200REC_F_L2_HINTS)) {
+                p.chunk = 32;
+                p.n_chunks = ((int64_t)a.B + 31) / 32;
+#define B200_GROUP(GG, PP)                                                                                   \
+    if (vg == GG && vpf == PP) {                                                                             \
+        auto launch = [&](auto kern) -> int {                                                                \
+            int occ = 0;                                                                                     \
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));                    \
+            if (occ < 1) occ = 1;                                                                            \
+            const int64_t need_g = (p.n_chunks + 7) / 8, cap_g = (int64_t)sm_count() * occ;                  \
+            kern<<<(int)(need_g < cap_g ? need_g : cap_g), 256, 0, s>>>(p);                                  \
+            return B200REC_OK;                                                                               \
+        };                                                                                                   \
+        int rc_g;                                                                                            \
+        if (uniq) { if (loss) { if (idelta) rc_g = launch(bpr_step_group_kernel<GG, 32, PP, true, true, true>); else rc_g = launch(bpr_step_group_kernel<GG, 32, PP, true, true, false>); } \
+                    else { if (idelta) rc_g = launch(bpr_step_group_kernel<GG, 32, PP, true, false, true>); else rc_g = launch(bpr_step_group_kernel<GG, 32, PP, true, false, false>); } } \
+        else { if (loss) { if (idelta) rc_g = launch(bpr_step_group_kernel<GG, 32, PP, false, true, true>); else rc_g = launch(bpr_step_group_kernel<GG, 32, PP, false, true, false>); } \
+               else { if (idelta) rc_g = launch(bpr_step_group_kernel<GG, 32, PP, false, false, true>); else rc_g = launch(bpr_step_group_kernel<GG, 32, PP, false, false, false>); } } \
+        if (rc_g) return rc_g;                                                                               \
+        B200_LAUNCH_CHECK();                                                                                 \
+        return B200REC_OK;                                                                                   \
+    }
+                B200_GROUP(8, 0) B200_GROUP(8, 1) B200_GROUP(16, 1)
+#undef B200_GROUP
             }
         }
         const int64_t need = (p.n_chunks + 7) / 8;

@@ -60,6 +60,18 @@ struct DevBuf {  // RAII device scratch for the host-buffer drop-ins
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+struct StreamPair {  // RAII: the two copy/compute streams of the chunked host drop-in (freed on every return path)
+    cudaStream_t st[2] = {nullptr, nullptr};
+    ~StreamPair() { for (int b = 0; b < 2; ++b) if (st[b]) cudaStreamDestroy(st[b]); }
+    int create() {
+        for (int b = 0; b < 2; ++b) {
+            cudaError_t e = cudaStreamCreate(&st[b]);
+            if (e != cudaSuccess) { set_error("cudaStreamCreate -> %s", cudaGetErrorString(e)); st[b] = nullptr; return B200REC_ECUDA; }
+        }
+        return B200REC_OK;
+    }
+};
+
 }  // namespace b200
 
 using namespace b200;
@@ -90,6 +102,37 @@ extern "C" int b200rec_score_topk(const float *U, const float *V, int ld, int d,
                             nullptr, (cudaStream_t)stream);
 }
 
+// Reserve part of L2 for a reused table (the item table of the BPR step: 51 MB at cfg2, read twice and
+// vector-reduced twice per triple) while 1 GB of single-use user rows stream past it: sets the device's persisting-L2
+// carve-out and an access-policy window on `stream` (kernels launched on it afterwards).  bytes == 0 clears it.
+extern "C" int b200rec_l2_persist(const void *base, int64_t bytes, float hit_ratio, void *stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    int dev = 0, max_persist = 0, max_window = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    B200_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (bytes <= 0 || base == nullptr) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        B200_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        B200_CUDA(cudaCtxResetPersistingL2Cache());
+        return B200REC_OK;
+    }
+    B200_REQUIRE(max_persist > 0, B200REC_EUNSUPPORTED, "l2_persist: device has no persisting L2");
+    size_t carve = (size_t)bytes < (size_t)max_persist ? (size_t)bytes : (size_t)max_persist;
+    B200_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    size_t win = (size_t)bytes < (size_t)max_window ? (size_t)bytes : (size_t)max_window;
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = hit_ratio * (win > carve ? (float)carve / (float)win : 1.f);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    B200_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return B200REC_OK;
+}
+
 // ---- func.h:22-31 --------------------------------------------------------
 extern "C" int b200rec_top_k_array_index(const float *scores_pt, int columns_num, int rows_num, int max_k,
                                          int *rankings_pt) {
@@ -105,9 +148,9 @@ extern "C" int b200rec_top_k_array_index(const float *scores_pt, int columns_num
     int chunk_rows = (int)((256ull << 20) / row_bytes);
     if (chunk_rows < 1) chunk_rows = 1;
     if (chunk_rows > rows_num) chunk_rows = rows_num;
-    cudaStream_t st[2];
-    B200_CUDA(cudaStreamCreate(&st[0]));
-    B200_CUDA(cudaStreamCreate(&st[1]));
+    StreamPair sp;
+    if ((rc = sp.create())) return rc;
+    cudaStream_t *st = sp.st;
     DevBuf sc[2], ix[2];
     for (int b = 0; b < 2; ++b) {
         if ((rc = sc[b].alloc((size_t)chunk_rows * row_bytes))) return rc;
@@ -125,8 +168,6 @@ extern "C" int b200rec_top_k_array_index(const float *scores_pt, int columns_num
     }
     B200_CUDA(cudaStreamSynchronize(st[0]));
     B200_CUDA(cudaStreamSynchronize(st[1]));
-    cudaStreamDestroy(st[0]);
-    cudaStreamDestroy(st[1]);
     return B200REC_OK;
 }
 

@@ -151,6 +151,15 @@ def delta_apply(W, d_sum, d_own):
     check(_lib.lib().b200rec_delta_apply(ptr(W), ptr(d_sum), ptr(d_own), W.numel(), current_stream()))
 
 
+def l2_persist(table, hit_ratio=1.0):
+    """Keep `table` resident in L2 for kernels launched on the current stream (None clears the window)."""
+    if table is None:
+        check(_lib.lib().b200rec_l2_persist(None, 0, 0.0, current_stream()))
+    else:
+        check(_lib.lib().b200rec_l2_persist(ptr(table), table.numel() * table.element_size(), float(hit_ratio),
+                                            current_stream()))
+
+
 def sgd_dense(param, grad, lr):
     check(_lib.lib().b200rec_sgd_dense(ptr(param), ptr(grad), param.numel(), float(lr), current_stream()))
 

@@ -1,7 +1,5 @@
 """`-m gpu`: the fused pointwise-MF step (csrc/pointwise_step.cu) against the oracle and the
-reference's golden vectors.  The kernel was written after this round's GPU budget was spent: it compiles for sm_100a and
-its oracle is pinned on the CPU, but it has NOT run on hardware yet - hence the separate process and the non-strict xfail
-(an XPASS in the log is its first device validation)."""
+reference's golden vectors (first validated on a B200 by the round-1 driver run; runs in its own process)."""
 import os
 import subprocess
 import sys
@@ -12,7 +10,6 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.xfail(strict=False, reason="csrc/pointwise_step.cu has not run on hardware yet (written with no GPU minutes left)")
 def test_pointwise_step_matches_oracle_and_reference_golden():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "pointwise_worker.py")], capture_output=True,
                          text=True, timeout=300)

@@ -1,0 +1,201 @@
+"""The P2P-fused multi-GPU layout (recsys_pytorch_b200/p2p.py, csrc/p2p.cu): item AND user tables sharded by id range,
+user rows exchanged through peer memory inside the fused step.  The reference has no distributed code; the oracle is
+the single-device numpy step (oracle/bpr_oracle.py::sgd_step) on the triples the ranks actually used.  W ranks are
+emulated in one process on one GPU (every "peer" pointer is a local pointer) - the kernels and the routing logic are
+exactly the ones the multi-process run uses; the real CUDA-IPC path is covered by the 2-GPU torchrun test."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bpr_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ CPU: bounds logic ---------------------------------
+def test_bounds_and_owner_cpu():
+    from recsys_pytorch_b200.p2p import balanced_item_bounds, owner_from_bounds, uniform_bounds
+    assert uniform_bounds(10, 3) == [0, 3, 6, 10]
+    rng = np.random.default_rng(0)
+    for n, w in ((8, 8), (100, 3), (5000, 8), (100_000, 8)):
+        counts = 1e6 / rng.permutation(np.arange(1, n + 1)).astype(np.float64)   # Zipf(1) popularity, ids shuffled
+        b = balanced_item_bounds(torch.from_numpy(counts), w)
+        assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+        assert all(b[r] < b[r + 1] for r in range(w))                 # no empty shard
+        own = owner_from_bounds(np.arange(n), b)
+        for r in range(w):
+            assert (own[b[r]:b[r + 1]] == r).all()
+        if n >= 5000:
+            mass = np.array([counts[b[r]:b[r + 1]].sum() for r in range(w)]) / counts.sum()
+            assert mass.max() < 1.0 / w + counts.max() / counts.sum() + 1e-3   # at most its share + the head item
+    z = balanced_item_bounds(torch.zeros(16), 4)                      # degenerate histogram -> uniform
+    assert z == [0, 4, 8, 12, 16]
+
+
+def test_sampler_mirror_with_bounds_cpu():
+    indptr = np.array([0, 3, 5]); indices = np.array([1, 4, 7, 0, 9])
+    b = [0, 5, 10]
+    for t in range(50):
+        p, n = O.sample_triple(3, 1, t, t % 2, indptr, indices, 10, item_bounds=b)
+        lo, hi = (0, 5) if p < 5 else (5, 10)
+        assert lo <= n < hi and n not in indices[indptr[t % 2]:indptr[t % 2 + 1]]
+    full = np.array([0, 10]); allitems = np.arange(10)               # a user who has everything: no negative exists
+    assert O.sample_triple(3, 1, 0, 0, full, allitems, 10)[1] == -1
+
+
+# ------------------------------------------------------------------ GPU: emulated ranks -------------------------------
+def _make(dev, W, nu, ni, d, seed, bounds=None, init=0.3, deg=12):
+    from recsys_pytorch_b200 import engine
+    from recsys_pytorch_b200.p2p import P2PShardedBPR, uniform_bounds
+    rng = np.random.default_rng(seed)
+    U0 = (rng.standard_normal((nu, d)) * init).astype(np.float32)
+    V0 = (rng.standard_normal((ni, d)) * init).astype(np.float32)
+    rows = [np.sort(rng.choice(ni, size=rng.integers(1, deg), replace=False)).astype(np.int32) for _ in range(nu)]
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.concatenate(rows)
+    ib = bounds if bounds is not None else uniform_bounds(ni, W)
+    ub = uniform_bounds(nu, W)
+    ranks = []
+    for r in range(W):
+        lo, hi = ub[r], ub[r + 1]
+        ip = torch.from_numpy(indptr[lo:hi + 1] - indptr[lo]).to(dev)
+        ix = torch.from_numpy(indices[indptr[lo]:indptr[hi]]).to(dev)
+        obj = P2PShardedBPR(nu, ni, d, engine.DeviceCSR(ip, ix, (hi - lo, ni)), r, W, dev, ib, ub, lr=0.9, reg=0.01,
+                            init_std=0.0, seed=11, max_batch=hi - lo)
+        obj.U[:, :d] = torch.from_numpy(U0[lo:hi]).to(dev)
+        obj.V[:, :d] = torch.from_numpy(V0[ib[r]:ib[r + 1]]).to(dev)
+        ranks.append(obj)
+    P2PShardedBPR.connect_local(ranks)
+    return ranks, U0, V0, indptr, indices, ib, ub
+
+
+def _tables(ranks, d):
+    U = np.concatenate([r.U.cpu().numpy()[:, :d] for r in ranks])
+    V = np.concatenate([r.V.cpu().numpy()[:, :d] for r in ranks])
+    return U, V
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("d", [128, 50, 200])
+def test_p2p_given_triples_cross_shard_equals_single_device(dev, W, d):
+    """Fixed-triple parity mode (SURVEY 8(e) bullet 2): arbitrary (u, i, j) with i and j on DIFFERENT shards; no id is
+    shared between triples, so the Hogwild step is the exact step: tables == oracle at rtol 2e-5."""
+    nu, ni = 1536, 4000
+    bounds = None if W == 1 else sorted({0, ni} | set(np.random.default_rng(W).choice(np.arange(1, ni), W - 1, replace=False).tolist()))
+    ranks, U0, V0, _, _, ib, ub = _make(dev, W, nu, ni, d, seed=W * 100 + d, bounds=bounds)
+    rng = np.random.default_rng(5)
+    items = rng.permutation(ni)
+    gu, gi, gj = [], [], []
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    k = 0
+    for r in ranks:
+        n_loc = r.uhi - r.ulo
+        B = n_loc * 3 // 4
+        ul = rng.permutation(n_loc)[:B].astype(np.int32)
+        pi, pj = items[k:k + B].astype(np.int32), items[k + B:k + 2 * B].astype(np.int32); k += 2 * B
+        gu.append(ul + r.ulo); gi.append(pi); gj.append(pj)
+        r.route(torch.from_numpy(ul).to(dev), 1, pos=torch.from_numpy(pi).to(dev), neg=torch.from_numpy(pj).to(dev))
+    gu, gi, gj = np.concatenate(gu), np.concatenate(gi), np.concatenate(gj)
+    Bg = len(gu)
+    n_proc = 0
+    for r in ranks:
+        r.compute(Bg, loss_sum=loss)
+        n_proc += int(r.n_processed.item())
+    assert n_proc == Bg
+    Ur, Vr, lref = O.sgd_step(U0, V0, gu, gi, gj, 0.9, 0.01)
+    U, V = _tables(ranks, d)
+    np.testing.assert_allclose(U, Ur, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(V, Vr, rtol=2e-5, atol=2e-6)
+    assert abs(loss.item() / Bg - float(lref)) < 2e-5 * max(1.0, float(lref))
+    for r in ranks:
+        assert float(r.U[:, d:].abs().sum()) == 0.0 and float(r.V[:, d:].abs().sum()) == 0.0
+        r.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W", [1, 2, 4, 8])
+def test_p2p_sampled_step_routing_and_oracle(dev, W):
+    """On-device sampling + routing: the triples drawn are bit-identical to the host mirror, every triple lands in the
+    outbox segment of owner(pos) exactly once with its negative inside that owner's range, and two Hogwild steps stay
+    within the second-order bound of the exact oracle step on those triples."""
+    from recsys_pytorch_b200.p2p import owner_from_bounds
+    nu, ni, d = 2048, 1500, 128
+    ranks, U0, V0, indptr, indices, ib, ub = _make(dev, W, nu, ni, d, seed=W, init=0.3)
+    for r in ranks:
+        r.lr, r.reg = 8.0, 0.0
+    rng = np.random.default_rng(1)
+    Uc, Vc = U0, V0
+    for step in (1, 2):
+        gu, gi, gj = [], [], []
+        for r in ranks:
+            n_loc = r.uhi - r.ulo
+            B = n_loc - 7
+            ul = torch.from_numpy(rng.permutation(n_loc)[:B].astype(np.int32)).to(dev)
+            dp, dn = torch.empty_like(ul), torch.empty_like(ul)
+            r.route(ul, step, dbg_pos=dp, dbg_neg=dn)
+            ulh, dph, dnh = ul.cpu().numpy(), dp.cpu().numpy(), dn.cpu().numpy()
+            ob = r.ob[r._n & 1]
+            cnt = ob["cnt"].cpu().numpy()[:W]
+            own = owner_from_bounds(dph, ib)
+            assert (dph >= 0).all() and (dnh >= 0).all()
+            assert (cnt == np.bincount(own, minlength=W)).all()
+            for dst in range(W):                                      # segment content == the triples owned by dst
+                seg = np.stack([ob[k_].cpu().numpy()[dst, :cnt[dst]] for k_ in ("u", "i", "j")], 1)
+                exp = np.stack([ulh[own == dst], dph[own == dst], dnh[own == dst]], 1)
+                assert (seg[np.lexsort(seg.T[::-1])] == exp[np.lexsort(exp.T[::-1])]).all()
+            assert (owner_from_bounds(dnh, ib) == own).all()           # negative co-located with the positive
+            for t in range(0, B, 97):                                 # host mirror of the counter-RNG draws
+                p_, n_ = O.sample_triple(11, step * W + r.rank, t, int(ulh[t]) + r.ulo, indptr, indices, ni, item_bounds=ib)
+                assert (p_, n_) == (int(dph[t]), int(dnh[t]))
+            gu.append(ulh + r.ulo); gi.append(dph); gj.append(dnh)
+        gu, gi, gj = np.concatenate(gu), np.concatenate(gi), np.concatenate(gj)
+        for t in range(len(gu)):                                      # a negative is never one of the user's positives
+            if t % 13 == 0:
+                assert gj[t] not in indices[indptr[gu[t]]:indptr[gu[t] + 1]]
+        for r in ranks:
+            r.compute(len(gu))
+        Ur, Vr, _ = O.sgd_step(Uc, Vc, gu, gi, gj, 8.0, 0.0)
+        U, V = _tables(ranks, d)
+        stepsz = max(np.abs(Ur - Uc).max(), np.abs(Vr - Vc).max())
+        dev_ = max(np.abs(U - Ur).max(), np.abs(V - Vr).max())
+        assert stepsz > 2e-3 and dev_ < 0.05 * stepsz, (stepsz, dev_)
+        Uc, Vc = U, V                                                 # next step starts from the device state
+    for r in ranks:
+        r.close()
+
+
+@pytest.mark.gpu
+def test_p2p_gather_items_and_sharded_evaluation_equals_single(dev):
+    """Evaluation in the layout: gathered item table == concatenation of the shards; per-rank scoring of its own users
+    gives the same top-k as one device holding everything."""
+    from recsys_pytorch_b200 import engine
+    from recsys_pytorch_b200._lib import SCORE_EXACT
+    W, nu, ni, d = 4, 1024, 3000, 64
+    ranks, U0, V0, indptr, indices, ib, ub = _make(dev, W, nu, ni, d, seed=9)
+    full = ranks[1].gather_items()
+    assert np.array_equal(full.cpu().numpy()[:, :d], V0)
+    Ug = engine.alloc_table(nu, d, dev, std=0.0); Ug[:, :d] = torch.from_numpy(U0).to(dev)
+    mask = engine.DeviceCSR(torch.from_numpy(indptr).to(dev), torch.from_numpy(indices).to(dev), (nu, ni))
+    ref, _ = engine.score_topk(Ug, full, d, torch.arange(nu, dtype=torch.int32, device=dev), mask, 10, algo=SCORE_EXACT)
+    for r in ranks:
+        got, _ = engine.score_topk(r.U, full, d, torch.arange(r.uhi - r.ulo, dtype=torch.int32, device=dev), r.train, 10,
+                                   algo=SCORE_EXACT)
+        assert torch.equal(got, ref[r.ulo:r.uhi])
+        r.close()
+
+
+@pytest.mark.gpu
+def test_p2p_two_gpus_real_ipc():
+    """Real thing: 2 processes, 2 GPUs, CUDA IPC peer mappings, NCCL barrier (tests/p2p_worker.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29600 + os.getpid() % 300
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "tests", "p2p_worker.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "P2P_WORKER_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
