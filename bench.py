@@ -34,6 +34,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 CFG = dict(num_users=1_000_000, num_items=100_000, d=128, batch=1_000_000, seed=2020, lr=0.05 * 1_000_000, reg=1e-4,
+           lr_per_triple=0.05,                            # lr / batch: what one triple moves its rows by (same for every N)
            init_std=0.01, eval_users=37_888, eval_k=10)   # 148 SMs x 256 rows: one full wave of the scoring kernel
 FALLBACK_HBM_GBS = 6650.0
 
@@ -182,6 +183,10 @@ def run_b200(args):
     hbm_gbs, bf16_tf, peak_src = measured_peaks()
 
     if world > 1:
+        c["small"] = bool(args.small)
+        if args.layout == "p2p":
+            from recsys_pytorch_b200 import p2p
+            return p2p.bench_p2p(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs, peak_src)
         from recsys_pytorch_b200 import dist as bdist
         return bdist.bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs, peak_src)
 
@@ -391,16 +396,23 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gather", default="ldg", choices=["ldg", "async", "tma", "generic"])
     ap.add_argument("--score-algo", dest="score_algo", default="tc", choices=["exact", "tc"])
-    ap.add_argument("--layout", default="user_sharded", choices=["item_sharded", "user_sharded"],
-                    help="N>1: user_sharded (default; also measures the north_star item_sharded layout and reports it "
-                         "under 'north_star_item_sharded') or item_sharded only")
+    ap.add_argument("--layout", default="p2p", choices=["p2p", "item_sharded", "user_sharded"],
+                    help="N>1: p2p (default: item AND user tables sharded by id range, user rows through NVSwitch peer "
+                         "memory inside the fused step; N=8 is BASELINE configs[2] 10Mx1M), item_sharded (north_star as "
+                         "written: replicated user table + NCCL all-reduce of the user-delta buffer) or user_sharded "
+                         "(replicated item table + all-reduce of the dense item delta)")
     ap.add_argument("--no-secondary", dest="no_secondary", action="store_true")
+    ap.add_argument("--head", type=int, default=None,
+                    help="N>1 p2p: number of most-popular items replicated on every rank (default 16384; 0 = pure range "
+                         "sharding of the whole catalogue)")
     ap.add_argument("--wire", default="fp32", choices=["fp32", "bf16"],
                     help="N>1 user_sharded: dtype of the all-reduced item-delta buffer")
     ap.add_argument("--exchange", default="auto", choices=["auto", "diff", "buffer"],
                     help="N>1 user_sharded: 'diff' = kernel updates the item replica in place and the difference is "
                          "all-reduced; 'buffer' = kernel accumulates item deltas in a separate dense buffer; 'auto' = "
                          "diff at N=2 (measured 3.44 vs 3.18 G triples/s), buffer at N>=4 (6.20 vs 5.23 G at N=4)")
+    ap.add_argument("--head-reduce", dest="head_reduce", default="mean", choices=["mean", "sum"],
+                    help="N>1 p2p with a replicated head: how the per-rank differences of the head rows are combined")
     ap.add_argument("--small", action="store_true", help="tiny shapes for a quick functional run (NOT a bench value)")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

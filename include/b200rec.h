@@ -163,6 +163,10 @@ int b200rec_sgd_dense(float *param, const float *grad, int64_t n, float lr, void
  *   delta_diff:  d_wire = d_own = W - snapshot      delta_apply:  W += d_sum - d_own      (n a multiple of 4) */
 int b200rec_delta_diff(const float *W, const float *snapshot, float *d_wire, float *d_own, int64_t n, void *stream);
 int b200rec_delta_apply(float *W, const float *d_sum, const float *d_own, int64_t n, void *stream);
+/* W = snapshot + scale * d_sum (n a multiple of 4): combines all-reduced per-rank differences of a replicated table */
+int b200rec_snap_apply(float *W, const float *snapshot, const float *d_sum, float scale, int64_t n, void *stream);
+/* W += delta; delta = 0 (n a multiple of 4): applies an all-reduced delta buffer and clears it in one pass */
+int b200rec_add_clear(float *W, float *delta, int64_t n, void *stream);
 int b200rec_adam_dense(float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
                        int64_t n, float lr, float beta1, float beta2, float eps, int step,
                        void *stream);
@@ -185,6 +189,9 @@ typedef struct b200rec_p2p_route_args {
     uint64_t seed, step;
     int32_t world, rank;
     int32_t item_bounds[B200REC_MAX_RANKS + 1]; /* rank r holds items [item_bounds[r], item_bounds[r+1])         */
+    int32_t head;              /* items [0, head) are REPLICATED on every rank (item_bounds[0] == head): a triple whose
+                                  positive is a head item stays on the routing rank; negatives are drawn from
+                                  head U owner's range.  0 = pure range sharding                                 */
     /* outbox in this rank's exported memory: triples for owner d at out_*[d*cap + k], k < out_cnt[d]            */
     int32_t *out_u, *out_i, *out_j, *out_cnt;
     int32_t cap;               /* >= B                                                                           */
@@ -199,6 +206,11 @@ typedef struct b200rec_p2p_step_args {
     float *U_peer[B200REC_MAX_RANKS];  /* user-table shard base of every rank ([rank] = this rank's own)         */
     float *V_peer[B200REC_MAX_RANKS];  /* item-table shard base of every rank                                    */
     int32_t item_bounds[B200REC_MAX_RANKS + 1];
+    int32_t head;                      /* replicated head rows [0, head): read from Vh, updates reduced into dVh  */
+    float *Vh, *dVh;                   /* [head, ld] local replica and where its updates go: dVh == Vh updates the
+                                          replica in place (Hogwild inside the rank; the caller exchanges the
+                                          difference to a snapshot between steps), a separate zeroed buffer keeps Vh
+                                          at its pre-step value; NULL when head == 0                              */
     /* for every source rank s: the outbox segment s routed to THIS rank (already offset by rank*cap) + its count */
     const int32_t *in_u[B200REC_MAX_RANKS], *in_i[B200REC_MAX_RANKS], *in_j[B200REC_MAX_RANKS];
     const int32_t *in_cnt[B200REC_MAX_RANKS];

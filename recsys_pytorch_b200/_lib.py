@@ -55,7 +55,7 @@ class P2PRouteArgs(C.Structure):
         ("csr_indptr", C.c_void_p), ("csr_indices", C.c_void_p),
         ("seed", C.c_uint64), ("step", C.c_uint64),
         ("world", C.c_int32), ("rank", C.c_int32),
-        ("item_bounds", C.c_int32 * (MAX_RANKS + 1)),
+        ("item_bounds", C.c_int32 * (MAX_RANKS + 1)), ("head", C.c_int32),
         ("out_u", C.c_void_p), ("out_i", C.c_void_p), ("out_j", C.c_void_p), ("out_cnt", C.c_void_p),
         ("cap", C.c_int32),
         ("dbg_pos", C.c_void_p), ("dbg_neg", C.c_void_p),
@@ -67,7 +67,8 @@ class P2PStepArgs(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("rank", C.c_int32), ("ld", C.c_int32), ("d", C.c_int32),
         ("U_peer", C.c_void_p * MAX_RANKS), ("V_peer", C.c_void_p * MAX_RANKS),
-        ("item_bounds", C.c_int32 * (MAX_RANKS + 1)),
+        ("item_bounds", C.c_int32 * (MAX_RANKS + 1)), ("head", C.c_int32),
+        ("Vh", C.c_void_p), ("dVh", C.c_void_p),
         ("in_u", C.c_void_p * MAX_RANKS), ("in_i", C.c_void_p * MAX_RANKS), ("in_j", C.c_void_p * MAX_RANKS),
         ("in_cnt", C.c_void_p * MAX_RANKS),
         ("lr", C.c_float), ("reg", C.c_float), ("inv_batch", C.c_float),
@@ -92,6 +93,8 @@ _PROTOS = {
     "b200rec_rows_add": (_I, [_P, _I, _P, _I, _P, _I, _F, _P]),
     "b200rec_add_bf16": (_I, [_P, _P, _L, _P]),
     "b200rec_sgd_dense": (_I, [_P, _P, _L, _F, _P]),
+    "b200rec_snap_apply": (_I, [_P, _P, _P, _F, _L, _P]),
+    "b200rec_add_clear": (_I, [_P, _P, _L, _P]),
     "b200rec_delta_diff": (_I, [_P, _P, _P, _P, _L, _P]),
     "b200rec_delta_apply": (_I, [_P, _P, _P, _L, _P]),
     "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),

@@ -1068,6 +1068,49 @@ __global__ void __launch_bounds__(256) delta_apply_kernel(float4 *__restrict__ W
     }
 }
 
+// W += d; d = 0   (replicated head rows of the P2P layout: apply the all-reduced delta and clear the buffer in one pass)
+__global__ void __launch_bounds__(256) add_clear_kernel(float4 *__restrict__ W, float4 *__restrict__ d, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 w = W[i];
+        const float4 a = d[i];
+        w.x += a.x; w.y += a.y; w.z += a.z; w.w += a.w;
+        W[i] = w;
+        d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// W = snapshot + scale * d   (replicated head rows: combine the all-reduced per-rank differences; scale = 1 is the
+// data-parallel sum, scale = 1/ranks the per-step parameter average)
+__global__ void __launch_bounds__(256) snap_apply_kernel(float4 *__restrict__ W, const float4 *__restrict__ snap,
+                                                         const float4 *__restrict__ d, float scale, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 s = snap[i], a = d[i];
+        W[i] = make_float4(fmaf(scale, a.x, s.x), fmaf(scale, a.y, s.y), fmaf(scale, a.z, s.z), fmaf(scale, a.w, s.w));
+    }
+}
+
+extern "C" int b200rec_snap_apply(float *W, const float *snapshot, const float *d_sum, float scale, int64_t n, void *stream) {
+    B200_REQUIRE(W && snapshot && d_sum, B200REC_EINVAL, "snap_apply: null argument");
+    B200_REQUIRE(n % 4 == 0, B200REC_EINVAL, "snap_apply: n must be a multiple of 4 (padded tables)");
+    if (n <= 0) return B200REC_OK;
+    const int64_t n4 = n / 4, blocks = (n4 + 255) / 256, cap = (int64_t)sm_count() * 16;
+    snap_apply_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4 *>(W), reinterpret_cast<const float4 *>(snapshot), reinterpret_cast<const float4 *>(d_sum), scale, n4);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
+extern "C" int b200rec_add_clear(float *W, float *delta, int64_t n, void *stream) {
+    B200_REQUIRE(W && delta, B200REC_EINVAL, "add_clear: null argument");
+    B200_REQUIRE(n % 4 == 0, B200REC_EINVAL, "add_clear: n must be a multiple of 4 (padded tables)");
+    if (n <= 0) return B200REC_OK;
+    const int64_t n4 = n / 4, blocks = (n4 + 255) / 256, cap = (int64_t)sm_count() * 16;
+    add_clear_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4 *>(W), reinterpret_cast<float4 *>(delta), n4);
+    B200_LAUNCH_CHECK();
+    return B200REC_OK;
+}
+
 extern "C" int b200rec_delta_diff(const float *W, const float *snapshot, float *d_wire, float *d_own, int64_t n,
                                   void *stream) {
     B200_REQUIRE(W && snapshot && d_wire && d_own, B200REC_EINVAL, "delta_diff: null argument");

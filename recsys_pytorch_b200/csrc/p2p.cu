@@ -20,6 +20,7 @@
 // Fixed-triple parity mode (SURVEY 8(e) bullet 2): with given (pos, neg) the negative may live on another shard; the
 // step kernel then resolves V[j] through the peer table too (peer load + peer vector atomic), so ANY triple list gives
 // the single-device result up to fp32 summation order.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "sampler.cuh"
@@ -65,14 +66,14 @@ __global__ void __launch_bounds__(kRouteThreads) p2p_route_kernel(const b200rec_
                     if (deg == 0 && !a.pos) valid = false;
                     if (valid && !a.pos) i[k] = sample_pos(row, deg, a.seed, a.step, (uint64_t)t);
                     if (valid && !a.neg) {
-                        const int o = owner_of(a.item_bounds, W, i[k]);
+                        const int o = i[k] < a.head ? a.rank : owner_of(a.item_bounds, W, i[k]);
                         const uint32_t n_lo = (uint32_t)a.item_bounds[o];
-                        valid = sample_neg(row, deg, n_lo, (uint32_t)a.item_bounds[o + 1] - n_lo, a.seed, a.step,
-                                           (uint64_t)t, j[k]);
+                        valid = sample_neg2(row, deg, (uint32_t)a.head, n_lo, (uint32_t)a.item_bounds[o + 1] - n_lo,
+                                            a.seed, a.step, (uint64_t)t, j[k]);
                     }
                 }
                 if (valid) {
-                    dst[k] = owner_of(a.item_bounds, W, i[k]);
+                    dst[k] = i[k] < a.head ? a.rank : owner_of(a.item_bounds, W, i[k]);
                     slot[k] = atomicAdd(&hist[dst[k]], 1);
                 }
                 if (a.dbg_pos) a.dbg_pos[t] = valid ? i[k] : -1;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kRouteThreads) p2p_route_kernel(const b200rec_
 template <int CPL>
 struct P2PRows {
     float4 u[CPL], i[CPL], j[CPL];
-    float *pu, *pi, *pj;
+    int tu, ti, tj;
 };
 
 struct P2PParams {
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
     __shared__ float *s_V[B200REC_MAX_RANKS];
     __shared__ const int32_t *s_iu[B200REC_MAX_RANKS], *s_ii[B200REC_MAX_RANKS], *s_ij[B200REC_MAX_RANKS];
     __shared__ int s_bounds[B200REC_MAX_RANKS + 1];
+    __shared__ int s_rr;
     const b200rec_p2p_step_args &a = p.a;
     const int W = a.world, me = a.rank;
     const int lane = threadIdx.x & 31;
@@ -130,8 +132,14 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
     if (threadIdx.x <= W) s_bounds[threadIdx.x] = a.item_bounds[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += (s_cnt[k] + 31) >> 5; }
+        // chunk order: round-robin over the sources while every source still has chunks (a rank then pulls from all
+        // homes at once - uniform all-to-all traffic on the switch - and its local triples overlap the NVLink round
+        // trips of the remote ones), then the leftovers source by source
+        int mn = 0x7fffffff;
+        for (int k = 0; k < W; ++k) mn = min(mn, (s_cnt[k] + 31) >> 5);
+        s_rr = mn;
+        int acc = mn * W;
+        for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += ((s_cnt[k] + 31) >> 5) - mn; }
         s_pref[W] = acc;
         if (blockIdx.x == 0 && a.n_processed) {
             int tot = 0;
@@ -144,6 +152,8 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
     const int ld = a.ld, d4 = a.ld >> 2;
     const int item_lo = s_bounds[me], item_hi = s_bounds[me + 1];
     float *const Vloc = s_V[me];
+    const int head = a.head;
+    float *const Vh = a.Vh, *const dVh = a.dVh;
     const float c_g = a.lr * a.inv_batch;                 // delta = c_g*(1-s) * other + c_r * self
     const float c_r = -a.lr * a.reg * a.inv_batch;
     float loss_local = 0.f;
@@ -154,16 +164,19 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
     c = __shfl_sync(0xffffffffu, c, 0);
     for (; c < n_chunks; c = c_next) {
         if (lane == 0) c_next = (int)atomicAdd(work, 1u);   // latency hides behind this chunk's rows
-        int k = 0;
-        while (c >= s_pref[k + 1]) ++k;
-        const int off = (c - s_pref[k]) << 5;
+        int k, off;
+        if (c < s_rr * W) { k = c % W; off = (c / W) << 5; }
+        else { k = 0; while (c >= s_pref[k + 1]) ++k; off = (s_rr + c - s_pref[k]) << 5; }
         const int n_here = min(32, s_cnt[k] - off);
         int u = 0, i = 0, j = 0;
         if (lane < n_here) { u = s_iu[k][off + lane]; i = s_ii[k][off + lane]; j = s_ij[k][off + lane]; }
         float *const Uhome = s_U[s_src[k]];
 
         P2PRows<CPL> r0, r1, r2;
-        auto vptr = [&](int id) -> float * {
+        // where an item row is READ (head replica / own shard / a peer's shard) and where its update GOES (the head's
+        // delta buffer, or the row itself)
+        auto vptr = [&](int id, bool write) -> float * {
+            if (id < head) return (write ? dVh : Vh) + (int64_t)id * ld;
             if (id >= item_lo && id < item_hi) return Vloc + (int64_t)(id - item_lo) * ld;
             int o = 0;
             for (int q = 1; q < W; ++q) o += (id >= s_bounds[q]);
@@ -171,15 +184,15 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
         };
         auto load = [&](P2PRows<CPL> &r, int it) {
             if (it < n_here) {
-                const int tu = __shfl_sync(0xffffffffu, u, it);
-                const int ti = __shfl_sync(0xffffffffu, i, it);
-                const int tj = __shfl_sync(0xffffffffu, j, it);
-                r.pu = Uhome + (int64_t)tu * ld + lane * 4;
-                r.pi = vptr(ti) + lane * 4;
-                r.pj = vptr(tj) + lane * 4;
+                r.tu = __shfl_sync(0xffffffffu, u, it);
+                r.ti = __shfl_sync(0xffffffffu, i, it);
+                r.tj = __shfl_sync(0xffffffffu, j, it);
+                const float *pu = Uhome + (int64_t)r.tu * ld + lane * 4;
+                const float *pi = vptr(r.ti, false) + lane * 4;
+                const float *pj = vptr(r.tj, false) + lane * 4;
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
-                    if (lane + 32 * q < d4) { r.u[q] = ld4(r.pu + 128 * q); r.i[q] = ld4(r.pi + 128 * q); r.j[q] = ld4(r.pj + 128 * q); }
+                    if (lane + 32 * q < d4) { r.u[q] = ld4(pu + 128 * q); r.i[q] = ld4(pi + 128 * q); r.j[q] = ld4(pj + 128 * q); }
                     else r.u[q] = r.i[q] = r.j[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
@@ -200,6 +213,9 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
                 const float s = __frcp_rn(1.f + __expf(-x));       // sigmoid(x); 1 - s saturates like the reference's fp32
                 const float a1 = c_g * (1.f - s);                   // = -lr * g
                 if (LOSS) loss_local += (x < -15.f) ? -x : -__logf(s);
+                float *pu = Uhome + (int64_t)r.tu * ld + lane * 4;
+                float *pi = vptr(r.ti, true) + lane * 4;
+                float *pj = vptr(r.tj, true) + lane * 4;
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
                     if (lane + 32 * q < d4) {
@@ -210,10 +226,10 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
                         di.z = fmaf(a1, r.u[q].z, c_r * r.i[q].z); di.w = fmaf(a1, r.u[q].w, c_r * r.i[q].w);
                         dj.x = fmaf(-a1, r.u[q].x, c_r * r.j[q].x); dj.y = fmaf(-a1, r.u[q].y, c_r * r.j[q].y);
                         dj.z = fmaf(-a1, r.u[q].z, c_r * r.j[q].z); dj.w = fmaf(-a1, r.u[q].w, c_r * r.j[q].w);
-                        if (UNIQ) st4(r.pu + 128 * q, make_float4(r.u[q].x + du.x, r.u[q].y + du.y, r.u[q].z + du.z, r.u[q].w + du.w));
-                        else red4(r.pu + 128 * q, du);
-                        red4(r.pi + 128 * q, di);
-                        red4(r.pj + 128 * q, dj);
+                        if (UNIQ) st4(pu + 128 * q, make_float4(r.u[q].x + du.x, r.u[q].y + du.y, r.u[q].z + du.z, r.u[q].w + du.w));
+                        else red4(pu + 128 * q, du);
+                        red4(pi + 128 * q, di);
+                        red4(pj + 128 * q, dj);
                     }
                 }
             }
@@ -234,6 +250,140 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
         if (lane == 0 && loss_local != 0.f) atomicAdd(a.loss_sum, (double)loss_local);
     }
     __threadfence_system();   // peer stores of this thread are performed before the kernel (and the next barrier) ends
+}
+
+// Same step with a row held by a sub-warp group of G lanes (ld = 128 floats: 32/G float4 per lane), 32/G triples per warp
+// at a time: more independent loads in flight per lane (what hides the ~2 us NVLink round trip of a remote user row),
+// a 3-stage instead of a 5-stage reduction, and the scalar part paid once per 32/G triples (cf. bpr_step_group_kernel).
+template <int G, bool UNIQ, bool LOSS>
+__global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_constant__ P2PParams p) {
+    constexpr int F4 = 32, CPL = F4 / G, TPW = 32 / G, ITERS = 32 / TPW, LD = F4 * 4;
+    __shared__ int s_cnt[B200REC_MAX_RANKS];
+    __shared__ int s_pref[B200REC_MAX_RANKS + 1];
+    __shared__ int s_src[B200REC_MAX_RANKS];
+    __shared__ float *s_U[B200REC_MAX_RANKS];
+    __shared__ float *s_V[B200REC_MAX_RANKS];
+    __shared__ const int32_t *s_iu[B200REC_MAX_RANKS], *s_ii[B200REC_MAX_RANKS], *s_ij[B200REC_MAX_RANKS];
+    __shared__ int s_bounds[B200REC_MAX_RANKS + 1];
+    __shared__ int s_rr;
+    const b200rec_p2p_step_args &a = p.a;
+    const int W = a.world, me = a.rank;
+    const int lane = threadIdx.x & 31, sl = lane % G, sg = lane / G;
+    if (threadIdx.x < W) {
+        const int k = threadIdx.x, s = (me + 1 + k) % W;
+        s_src[k] = s;
+        s_cnt[k] = *a.in_cnt[s];
+        s_iu[k] = a.in_u[s]; s_ii[k] = a.in_i[s]; s_ij[k] = a.in_j[s];
+    }
+    if (threadIdx.x < B200REC_MAX_RANKS) { s_U[threadIdx.x] = a.U_peer[threadIdx.x]; s_V[threadIdx.x] = a.V_peer[threadIdx.x]; }
+    if (threadIdx.x <= W) s_bounds[threadIdx.x] = a.item_bounds[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // chunk order: round-robin over the sources while every source still has chunks (a rank then pulls from all
+        // homes at once - uniform all-to-all traffic on the switch - and its local triples overlap the NVLink round
+        // trips of the remote ones), then the leftovers source by source
+        int mn = 0x7fffffff;
+        for (int k = 0; k < W; ++k) mn = min(mn, (s_cnt[k] + 31) >> 5);
+        s_rr = mn;
+        int acc = mn * W;
+        for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += ((s_cnt[k] + 31) >> 5) - mn; }
+        s_pref[W] = acc;
+        if (blockIdx.x == 0 && a.n_processed) {
+            int tot = 0;
+            for (int k = 0; k < W; ++k) tot += s_cnt[k];
+            *a.n_processed = tot;
+        }
+    }
+    __syncthreads();
+    const int n_chunks = s_pref[W];
+    const int item_lo = s_bounds[me], item_hi = s_bounds[me + 1];
+    float *const Vloc = s_V[me];
+    const int head = a.head;
+    float *const Vh = a.Vh, *const dVh = a.dVh;
+    const float c_g = a.lr * a.inv_batch;
+    const float c_r = -a.lr * a.reg * a.inv_batch;
+    float loss_local = 0.f;
+    unsigned int *const work = p.work;
+    int c = 0, c_next = 0;
+    if (lane == 0) c = (int)atomicAdd(work, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    for (; c < n_chunks; c = c_next) {
+        if (lane == 0) c_next = (int)atomicAdd(work, 1u);
+        int k, off;
+        if (c < s_rr * W) { k = c % W; off = (c / W) << 5; }
+        else { k = 0; while (c >= s_pref[k + 1]) ++k; off = (s_rr + c - s_pref[k]) << 5; }
+        const int n_here = min(32, s_cnt[k] - off);
+        int u = 0, i = 0, j = 0;
+        if (lane < n_here) { u = s_iu[k][off + lane]; i = s_ii[k][off + lane]; j = s_ij[k][off + lane]; }
+        float *const Uhome = s_U[s_src[k]];
+        auto vptr = [&](int id, bool write) -> float * {
+            if (id < head) return (write ? dVh : Vh) + (int64_t)id * LD;
+            if (id >= item_lo && id < item_hi) return Vloc + (int64_t)(id - item_lo) * LD;
+            int o = 0;
+            for (int q = 1; q < W; ++q) o += (id >= s_bounds[q]);
+            return s_V[o] + (int64_t)(id - s_bounds[o]) * LD;
+        };
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            if (it * TPW >= n_here) break;                       // warp-uniform
+            const int src = it * TPW + sg;
+            const int tu = __shfl_sync(0xffffffffu, u, src);
+            const int ti = __shfl_sync(0xffffffffu, i, src);
+            const int tj = __shfl_sync(0xffffffffu, j, src);
+            const bool ok = src < n_here;
+            float4 ru[CPL], ri[CPL], rj[CPL];
+            float part = 0.f;
+            if (ok) {
+                const float *pu = Uhome + (int64_t)tu * LD + sl * 4;
+                const float *pi = vptr(ti, false) + sl * 4;
+                const float *pj = vptr(tj, false) + sl * 4;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) ru[q] = ld4(pu + q * G * 4);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) ri[q] = ld4(pi + q * G * 4);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) rj[q] = ld4(pj + q * G * 4);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    part = fmaf(ru[q].x, ri[q].x - rj[q].x, part); part = fmaf(ru[q].y, ri[q].y - rj[q].y, part);
+                    part = fmaf(ru[q].z, ri[q].z - rj[q].z, part); part = fmaf(ru[q].w, ri[q].w - rj[q].w, part);
+                }
+            }
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (ok) {
+                const float x = part;
+                const float s = __frcp_rn(1.f + __expf(-x));
+                const float a1 = c_g * (1.f - s);
+                if (LOSS && sl == 0) loss_local += (x < -15.f) ? -x : -__logf(s);
+                float *pu = Uhome + (int64_t)tu * LD + sl * 4;
+                float *pi = vptr(ti, true) + sl * 4;
+                float *pj = vptr(tj, true) + sl * 4;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const float4 vu = ru[q], vi = ri[q], vj = rj[q];
+                    float4 du, di, dj;
+                    du.x = fmaf(a1, vi.x - vj.x, c_r * vu.x); du.y = fmaf(a1, vi.y - vj.y, c_r * vu.y);
+                    du.z = fmaf(a1, vi.z - vj.z, c_r * vu.z); du.w = fmaf(a1, vi.w - vj.w, c_r * vu.w);
+                    di.x = fmaf(a1, vu.x, c_r * vi.x); di.y = fmaf(a1, vu.y, c_r * vi.y);
+                    di.z = fmaf(a1, vu.z, c_r * vi.z); di.w = fmaf(a1, vu.w, c_r * vi.w);
+                    dj.x = fmaf(-a1, vu.x, c_r * vj.x); dj.y = fmaf(-a1, vu.y, c_r * vj.y);
+                    dj.z = fmaf(-a1, vu.z, c_r * vj.z); dj.w = fmaf(-a1, vu.w, c_r * vj.w);
+                    if (UNIQ) st4(pu + q * G * 4, make_float4(vu.x + du.x, vu.y + du.y, vu.z + du.z, vu.w + du.w));
+                    else red4(pu + q * G * 4, du);
+                    red4(pi + q * G * 4, di);
+                    red4(pj + q * G * 4, dj);
+                }
+            }
+        }
+        c_next = __shfl_sync(0xffffffffu, c_next, 0);
+    }
+    if (LOSS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) loss_local += __shfl_xor_sync(0xffffffffu, loss_local, o);
+        if (lane == 0 && loss_local != 0.f) atomicAdd(a.loss_sum, (double)loss_local);
+    }
+    __threadfence_system();
 }
 
 static int next_work_counter(cudaStream_t s, unsigned int **out) {
@@ -262,11 +412,12 @@ extern "C" int b200rec_p2p_route(const b200rec_p2p_route_args *args, void *strea
     B200_REQUIRE(a.B == 0 || a.users, B200REC_EINVAL, "p2p_route: users is NULL");
     B200_REQUIRE((a.pos && a.neg) || (a.csr_indptr && a.csr_indices), B200REC_EINVAL,
                  "p2p_route: on-device sampling needs the CSR shard");
+    B200_REQUIRE(a.head >= 0 && a.item_bounds[0] == a.head, B200REC_EINVAL,
+                 "p2p_route: item_bounds must start at head (%d), got %d", a.head, a.item_bounds[0]);
     for (int r = 0; r < a.world; ++r)
-        B200_REQUIRE(a.item_bounds[r] <= a.item_bounds[r + 1] && a.item_bounds[0] == 0, B200REC_EINVAL,
-                     "p2p_route: item_bounds must start at 0 and be non-decreasing");
+        B200_REQUIRE(a.item_bounds[r] <= a.item_bounds[r + 1], B200REC_EINVAL, "p2p_route: item_bounds must be non-decreasing");
     for (int r = 0; r < a.world && !a.neg; ++r)
-        B200_REQUIRE(a.item_bounds[r] < a.item_bounds[r + 1], B200REC_EINVAL,
+        B200_REQUIRE(a.head > 0 || a.item_bounds[r] < a.item_bounds[r + 1], B200REC_EINVAL,
                      "p2p_route: an empty item shard cannot supply negatives");
     cudaStream_t s = (cudaStream_t)stream;
     B200_CUDA(cudaMemsetAsync(a.out_cnt, 0, sizeof(int32_t) * a.world, s));
@@ -286,6 +437,8 @@ extern "C" int b200rec_p2p_step(const b200rec_p2p_step_args *args, void *stream)
     B200_REQUIRE(a.d >= 1 && a.ld >= a.d && (a.ld % 4) == 0 && a.ld <= 512, B200REC_EINVAL,
                  "p2p_step: need 1 <= d <= ld <= 512, ld %% 4 == 0 (d=%d ld=%d)", a.d, a.ld);
     B200_REQUIRE(a.inv_batch > 0.f, B200REC_EINVAL, "p2p_step: inv_batch (1 / global batch) is required");
+    B200_REQUIRE(a.head >= 0 && a.item_bounds[0] == a.head && (a.head == 0 || (a.Vh && a.dVh)), B200REC_EINVAL,
+                 "p2p_step: head rows need Vh and dVh, and item_bounds[0] == head");
     for (int r = 0; r < a.world; ++r) {
         B200_REQUIRE(a.U_peer[r] && a.V_peer[r] && a.in_u[r] && a.in_i[r] && a.in_j[r] && a.in_cnt[r], B200REC_EINVAL,
                      "p2p_step: peer table entry %d is NULL", r);
@@ -300,6 +453,28 @@ extern "C" int b200rec_p2p_step(const b200rec_p2p_step_args *args, void *stream)
     if (rc) return rc;
     const int cpl = (a.ld / 4 + 31) / 32;
     const bool uniq = (a.flags & B200REC_F_USERS_UNIQUE) != 0, loss = a.loss_sum != nullptr;
+    {   // ld == 128: group kernel (B200REC_P2P_VARIANT=0 selects the warp-per-row kernel)
+        const char *var = getenv("B200REC_P2P_VARIANT");
+        const int vg = var ? atoi(var) : 16;
+        if (a.ld == 128 && vg > 0) {
+            auto launch = [&](auto kern) -> int {
+                int occ = 0;
+                B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+                if (occ < 1) occ = 1;
+                kern<<<sm_count() * occ, 256, 0, s>>>(p);
+                return B200REC_OK;
+            };
+            int rc_g;
+#define B200_P2PG(GG)                                                                                            \
+    if (uniq) { rc_g = loss ? launch(p2p_step_group_kernel<GG, true, true>) : launch(p2p_step_group_kernel<GG, true, false>); } \
+    else { rc_g = loss ? launch(p2p_step_group_kernel<GG, false, true>) : launch(p2p_step_group_kernel<GG, false, false>); }
+            if (vg == 16) { B200_P2PG(16) } else { B200_P2PG(8) }
+#undef B200_P2PG
+            if (rc_g) return rc_g;
+            B200_LAUNCH_CHECK();
+            return B200REC_OK;
+        }
+    }
     const int grid = sm_count() * (cpl == 1 ? 3 : (cpl == 2 ? 2 : 1));
 #define B200_P2P(C)                                                                     \
     {                                                                                   \

@@ -29,6 +29,23 @@ __device__ __forceinline__ bool sample_neg(const int32_t *row, uint32_t deg, uin
     return false;
 }
 
+// same over the union [0, cnt0) U [lo1, lo1 + cnt1): the replicated head of the catalogue plus one tail shard
+// (csrc/p2p.cu).  cnt0 == 0 makes exactly the draws of sample_neg(row, deg, lo1, cnt1, ...).
+__device__ __forceinline__ bool sample_neg2(const int32_t *row, uint32_t deg, uint32_t cnt0, uint32_t lo1, uint32_t cnt1,
+                                            uint64_t seed, uint64_t step, uint64_t t, int &j) {
+    for (uint32_t tries = 0; tries < kNegTries; ++tries) {
+        const uint32_t r = (uint32_t)(((uint64_t)rng_u32(seed, step, t, 1 + tries) * (uint64_t)(cnt0 + cnt1)) >> 32);
+        j = (int)(r < cnt0 ? r : lo1 + (r - cnt0));
+        uint32_t l = 0, h = deg;
+        while (l < h) {
+            const uint32_t m = (l + h) >> 1;
+            if (row[m] < j) l = m + 1; else h = m;
+        }
+        if (!(l < deg && row[l] == j)) return true;
+    }
+    return false;
+}
+
 // lane-parallel triple fetch / sampling for the single-table kernels
 __device__ __forceinline__ void fetch_triple(const b200rec_bpr_args &a, int64_t t, bool &valid, int &u, int &i,
                                              int &j) {

@@ -141,6 +141,16 @@ def add_bf16(param, delta_bf16):
     check(_lib.lib().b200rec_add_bf16(ptr(param), ptr(delta_bf16), param.numel(), current_stream()))
 
 
+def snap_apply(W, snapshot, d_sum, scale=1.0):
+    """W = snapshot + scale * d_sum (dense, same shape)."""
+    check(_lib.lib().b200rec_snap_apply(ptr(W), ptr(snapshot), ptr(d_sum), float(scale), W.numel(), current_stream()))
+
+
+def add_clear(W, delta):
+    """W += delta; delta = 0 (dense, same shape)."""
+    check(_lib.lib().b200rec_add_clear(ptr(W), ptr(delta), W.numel(), current_stream()))
+
+
 def delta_diff(W, snapshot, d_wire, d_own):
     """d_wire = d_own = W - snapshot (dense, same shape)."""
     check(_lib.lib().b200rec_delta_diff(ptr(W), ptr(snapshot), ptr(d_wire), ptr(d_own), W.numel(), current_stream()))

@@ -95,11 +95,14 @@ def uniform_bounds(n: int, world: int):
     return [(n * r) // world for r in range(world + 1)]
 
 
-def balanced_item_bounds(item_counts, world: int):
+def balanced_item_bounds(item_counts, world: int, head: int = 0):
     """Contiguous item-id ranges of (nearly) equal POSITIVE MASS: the owner of a triple is the shard of its positive
     item, and under a Zipf catalogue equal-width ranges leave the rank holding the head items with up to ~1.5x the
     work.  `item_counts` = global number of train interactions per item (1-D tensor / array).  Every shard keeps at
-    least one item; bounds are identical on every rank because the histogram is."""
+    least one item; bounds are identical on every rank because the histogram is.  `head` > 0: the first `head` ids are
+    replicated everywhere and only [head, n) is split (bounds[0] == head)."""
+    if head:
+        return [head + b for b in balanced_item_bounds(torch.as_tensor(item_counts)[head:], world)]
     c = torch.as_tensor(item_counts).double().cpu()
     n = int(c.numel())
     assert n >= world
@@ -117,8 +120,35 @@ def balanced_item_bounds(item_counts, world: int):
 
 
 def owner_from_bounds(ids, bounds):
-    """Rank owning each id (numpy)."""
+    """Rank owning each (tail) id (numpy)."""
     return np.searchsorted(np.asarray(bounds[1:-1]), np.asarray(ids), side="right")
+
+
+def relabel_by_popularity(csrs, item_counts, head, seed=0):
+    """Renumber the catalogue so that the `head` most popular items are the ids [0, head) - in RANDOM order inside the
+    head, and the tail keeps its original relative order.  (Measured, profiles/r02_p2p_notes.md: laying the rows out in
+    popularity ORDER makes the step kernel 35 % slower - the few dozen hottest rows then sit next to each other and their
+    vector atomics pile onto the same L2 slices; scattered over the head they do not.)  Returns (relabelled DeviceCSRs
+    with re-sorted rows, new_id_of_old int64 tensor, counts in the new order).  Pure data preparation, once per dataset;
+    every rank computes the same permutation (same histogram, same seed)."""
+    counts = torch.as_tensor(item_counts)
+    dev0 = counts.device
+    order = torch.argsort(counts, descending=True, stable=True)
+    g = torch.Generator(device="cpu"); g.manual_seed(int(seed))
+    head_items = order[:head][torch.randperm(int(head), generator=g).to(dev0)] if head else order[:0]
+    tail_items, _ = torch.sort(order[head:])
+    new_order = torch.cat([head_items, tail_items])
+    new_id = torch.empty_like(new_order)
+    new_id[new_order] = torch.arange(new_order.numel(), device=dev0)
+    out = []
+    for csr in csrs:
+        dev = csr.indices.device
+        nid = new_id.to(dev)
+        rows = torch.repeat_interleave(torch.arange(csr.shape[0], device=dev), csr.indptr[1:] - csr.indptr[:-1])
+        key = rows * csr.shape[1] + nid[csr.indices.long()]
+        key, _ = torch.sort(key)
+        out.append(engine.DeviceCSR(csr.indptr, (key - rows * csr.shape[1]).to(torch.int32).contiguous(), csr.shape))
+    return out, new_id, counts[new_order]
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -130,15 +160,27 @@ class P2PShardedBPR:
     emulation of W ranks on one GPU: build W objects and call `P2PShardedBPR.connect_local(objs)`."""
 
     def __init__(self, num_users, num_items, d, train_local, rank, world, device, item_bounds, user_bounds=None,
-                 lr=0.05, reg=0.0, init_std=0.01, seed=2020, max_batch=None):
+                 lr=0.05, reg=0.0, init_std=0.01, seed=2020, max_batch=None, head=0, head_reduce="sum"):
+        """`head` > 0: the items [0, head) (the most popular ones after `relabel_by_popularity`) are REPLICATED on every
+        rank; `item_bounds` then splits [head, num_items) only.  A triple whose positive is a head item is processed on
+        its user's home rank without any NVLink traffic.  Every rank updates its replica IN PLACE during the step
+        (Hogwild inside the rank, like the single-GPU kernel); between steps the per-rank differences to the pre-step
+        snapshot are all-reduced (the same collective doubles as the step barrier) and every replica becomes
+            snapshot + sum_r diff_r        head_reduce='sum'   exact data-parallel SGD (what the parity tests check)
+            snapshot + mean_r diff_r       head_reduce='mean'  per-step parameter averaging (local SGD)
+        'mean' is what large batches need: a hot row receives ~1e5 updates per rank and step, each rank's in-place
+        trajectory saturates on its own, and ADDING W saturated displacements overshoots W-fold (observed: NaN at 8
+        ranks, 8M-triple steps); averaging them does not.  Under a Zipf catalogue the head holds most positives, so
+        most user rows never travel."""
         assert 1 <= world <= MAX_RANKS, "at most %d ranks" % MAX_RANKS
+        self.head = int(head)
         self.num_users, self.num_items, self.d = int(num_users), int(num_items), int(d)
         self.rank, self.world, self.device = int(rank), int(world), torch.device(device)
         self.lr, self.reg, self.seed = float(lr), float(reg), int(seed)
         self.train = train_local
         self.item_bounds = [int(b) for b in item_bounds]
         self.user_bounds = [int(b) for b in (user_bounds if user_bounds is not None else uniform_bounds(num_users, world))]
-        assert len(self.item_bounds) == world + 1 and self.item_bounds[0] == 0 and self.item_bounds[-1] == num_items
+        assert len(self.item_bounds) == world + 1 and self.item_bounds[0] == self.head and self.item_bounds[-1] == num_items
         assert len(self.user_bounds) == world + 1 and self.user_bounds[-1] == num_users
         self.ulo, self.uhi = self.user_bounds[rank], self.user_bounds[rank + 1]
         self.ilo, self.ihi = self.item_bounds[rank], self.item_bounds[rank + 1]
@@ -163,12 +205,25 @@ class P2PShardedBPR:
         if init_std > 0:
             self.U[:, :d].normal_(0.0, init_std, generator=gu)
             self.V[:, :d].normal_(0.0, init_std, generator=gu)
+        # replicated head rows: identical init on every rank (seed only), delta buffer zero
+        self.Vh = self.dVh = None
+        self.head_reduce = str(head_reduce)
+        assert self.head_reduce in ("sum", "mean")
+        if self.head:
+            gh = torch.Generator(device=self.device); gh.manual_seed(seed * 104729 + 7)
+            self.Vh = engine.alloc_table(self.head, d, self.device, init_std, gh)
+            self._snap = torch.empty_like(self.Vh)
+            self._diff = torch.empty_like(self.Vh)
+            self._head_dirty = False
         self._bar = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.n_processed = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._step_args = None
         self._n = 0
         self._peer_base = None
         self._emulated = False
+        self._side = torch.cuda.Stream(device=self.device)
+        self._ev_sync, self._ev_route = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_sync.record(torch.cuda.current_stream(self.device))
 
     # ---- wiring ------------------------------------------------------------------------------------
     def _meta(self):
@@ -183,6 +238,8 @@ class P2PShardedBPR:
             a.world, a.rank, a.ld, a.d = self.world, self.rank, self.ld, self.d
             for k, v in enumerate(self.item_bounds):
                 a.item_bounds[k] = v
+            a.head = self.head
+            a.Vh, a.dVh = (ptr(self.Vh), ptr(self.Vh)) if self.head else (None, None)     # replica updated in place
             for s in range(self.world):
                 m = metas[s]
                 assert m["cap"] >= 1
@@ -239,15 +296,38 @@ class P2PShardedBPR:
         a.world, a.rank = self.world, self.rank
         for k, v in enumerate(self.item_bounds):
             a.item_bounds[k] = v
+        a.head = self.head
         a.out_u, a.out_i, a.out_j, a.out_cnt, a.cap = ptr(ob["u"]), ptr(ob["i"]), ptr(ob["j"]), ptr(ob["cnt"]), self.cap
         a.dbg_pos = ptr(dbg_pos) if dbg_pos is not None else None
         a.dbg_neg = ptr(dbg_neg) if dbg_neg is not None else None
         check(_lib.lib().b200rec_p2p_route(C.byref(a), current_stream()))
 
     def barrier(self):
-        """Stream-ordered rendezvous of all ranks (a 4-byte all-reduce; nothing else crosses NCCL during training)."""
+        """Stream-ordered rendezvous of all ranks (a 4-byte all-reduce)."""
         if not self._emulated and self.world > 1 and dist.is_initialized():
             dist.all_reduce(self._bar)
+
+    def sync_head(self):
+        """All-reduce the head delta of the previous step and apply it to this replica (Vh += sum_r dVh_r); doubles as
+        the step barrier.  Without a head (or when no step is pending) it is the plain barrier."""
+        if not self.head or not self._head_dirty:
+            return self.barrier()
+        engine.delta_diff(self.Vh, self._snap, self._diff, self._diff)          # what this rank's step did to its replica
+        if not self._emulated and self.world > 1 and dist.is_initialized():
+            dist.all_reduce(self._diff)
+        engine.snap_apply(self.Vh, self._snap, self._diff, 1.0 if self.head_reduce == "sum" else 1.0 / self.world)
+        self._head_dirty = False
+
+    @staticmethod
+    def sync_head_local(ranks):
+        """Emulation of `sync_head` for sibling objects in one process."""
+        if not ranks[0].head or not ranks[0]._head_dirty:
+            return
+        tot = torch.stack([r.Vh - r._snap for r in ranks]).sum(0)
+        scale = 1.0 if ranks[0].head_reduce == "sum" else 1.0 / len(ranks)
+        for r in ranks:
+            engine.snap_apply(r.Vh, r._snap, tot, scale)
+            r._head_dirty = False
 
     def compute(self, global_batch, loss_sum=None, users_unique=True):
         """Fused step over the triples every rank routed to this one (buffer of the current step)."""
@@ -257,22 +337,51 @@ class P2PShardedBPR:
         a.flags = F_USERS_UNIQUE if users_unique else 0
         a.loss_sum = ptr(_lib.require_cuda(loss_sum, "loss_sum", torch.float64)) if loss_sum is not None else None
         a.n_processed = ptr(self.n_processed)
+        if self.head:
+            self._snap.copy_(self.Vh)
         check(_lib.lib().b200rec_p2p_step(C.byref(a), current_stream()))
         self._n += 1
+        if self.head:
+            self._head_dirty = True
 
     def step(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True, pos=None, neg=None):
-        """route -> barrier -> compute.  `users_local`: int32 local row ids of this rank's batch (unique)."""
-        self.route(users_local, step_key, pos, neg)
-        self.barrier()
+        """route -> sync_head (all-reduce of the previous step's head delta = the barrier) -> compute.
+        `users_local`: int32 local row ids of this rank's batch (unique).
+
+        The route kernel runs on a side stream (`self.side`): sampling does not read the tables, so the route of step
+        s overlaps the step kernel of step s-1 that is still executing on the main stream.  Its only dependency is the
+        sync point of step s-1 (every peer has finished reading the outbox buffer it is about to overwrite).  The same
+        triples, the same arithmetic - only the schedule differs from the serial order.  `users_local` (and pos/neg)
+        must be ready for the side stream: produce them on `self.side` or before a synchronisation."""
+        main = torch.cuda.current_stream(self.device)
+        if self._emulated or self._side is None:
+            self.route(users_local, step_key, pos, neg)
+        else:
+            self._side.wait_event(self._ev_sync)
+            with torch.cuda.stream(self._side):
+                self.route(users_local, step_key, pos, neg)
+                self._ev_route.record(self._side)
+            main.wait_event(self._ev_route)
+        self.sync_head()
+        if self._side is not None:
+            self._ev_sync.record(main)
         self.compute(global_batch, loss_sum, users_unique)
+
+    @property
+    def side(self):
+        """The stream the route kernel runs on (produce host-fed batches here)."""
+        return self._side if self._side is not None else torch.cuda.current_stream(self.device)
 
     # ---- evaluation ---------------------------------------------------------------------------------
     def gather_items(self):
         """Full [num_items, ld] item table on this rank: W device-to-device copies out of the peers' shards (the
         one-time exchange of an evaluation, SURVEY 8(e) 'Scoring'); bracketed by barriers so no rank is training."""
+        self.sync_head()
         self.barrier()
         full = torch.empty((self.num_items, self.ld), dtype=torch.float32, device=self.device)
         row = self.ld * 4
+        if self.head:
+            full[:self.head].copy_(self.Vh)
         for s in range(self.world):
             lo, hi = self.item_bounds[s], self.item_bounds[s + 1]
             if hi > lo:
@@ -295,3 +404,178 @@ class P2PShardedBPR:
                     _lib.lib().b200rec_peer_close(b)
         self._peer_base = None
         self.arena.free()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1), default layout
+# ---------------------------------------------------------------------------------------------------------------
+PER_GPU = dict(users=1_250_000, items=125_000)     # x8 = BASELINE configs[2]: 10M users x 1M items
+
+
+def default_head(num_items, world):
+    """Replicated head size: 16,384 rows (8 MB at d=128: a ~50 us all-reduce) hold ~70 % of the positives of a Zipf(1)
+    catalogue of 1M items; never more than an eighth of the catalogue; none on a single GPU."""
+    return 0 if world == 1 else int(min(16_384, num_items // 8))
+
+
+def build_rank(c, rank, world, dev, d=None, max_batch=None, lr=None, head=None, head_reduce="mean"):
+    """This rank's shard of the weak-scaling dataset: `PER_GPU` users and items per GPU (N = 8 is cfg3), one global Zipf
+    popularity order (item_seed), catalogue renumbered by popularity, balanced item bounds over the tail from the
+    all-reduced item histogram."""
+    from . import synthetic
+    import os
+    nu, ni = PER_GPU["users"] * world, int(os.environ.get("B200REC_PROBE_ITEMS", PER_GPU["items"])) * world
+    if c.get("small"):
+        nu, ni = 60_000 * world, 8_000 * world
+    ub = uniform_bounds(nu, world)
+    n_loc = ub[rank + 1] - ub[rank]
+    train, target = synthetic.make_interactions(n_loc, ni, seed=c["seed"] + 1 + rank, device=dev, item_seed=c["seed"])
+    hist = torch.bincount(train.indices.long(), minlength=ni).to(torch.int64)
+    if world > 1 and dist.is_initialized():
+        dist.all_reduce(hist)
+    head = default_head(ni, world) if head is None else int(head)
+    if head:
+        (train, target), _, hist = relabel_by_popularity([train, target], hist, head, seed=c["seed"])
+    ib = balanced_item_bounds(hist, world, head)
+    m = P2PShardedBPR(nu, ni, d or c["d"], train, rank, world, dev, ib, ub, lr=lr if lr is not None else c["lr"],
+                      reg=c["reg"], init_std=c["init_std"], seed=c["seed"], max_batch=max_batch or n_loc, head=head,
+                      head_reduce=head_reduce)
+    m.connect()
+    return m, train, target, hist
+
+
+def bench_p2p(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs, peak_src):
+    """Weak scaling, one fused P2P step per batch: every GPU brings 1.25M users, 125k items and 1M triples per step."""
+    import json
+    d, B_local = c["d"], c["batch"]
+    B_glob = B_local * world
+    lr = c["lr_per_triple"] * B_glob                      # the per-triple step does not depend on N (lr * 1/B_glob)
+    m, train, target, hist = build_rank(c, rank, world, dev, lr=lr, max_batch=B_local, head=getattr(args, "head", None),
+                                            head_reduce=getattr(args, "head_reduce", "mean"))
+    n_loc = m.uhi - m.ulo
+    head_mass = float(hist[:m.head].sum()) / float(hist.sum()) if m.head else 0.0
+    g = torch.Generator(device=dev); g.manual_seed(c["seed"] + rank)
+    perms = [torch.randperm(n_loc, device=dev, generator=g)[:B_local].to(torch.int32).contiguous() for _ in range(4)]
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    scratch = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step(s):
+        m.step(perms[s % 4], s + 1, B_glob, loss_sum=loss)
+
+    def step_idle(s):          # same kernels, same traffic, learning rate 0: the clock-sampling window only
+        keep = m.lr
+        m.lr = 0.0
+        try:
+            m.step(perms[s % 4], 100000 + s, B_glob, loss_sum=scratch)
+        finally:
+            m.lr = keep
+
+    for s in range(args.warmup):
+        step(s)
+    counted = [0, 0]
+
+    def step_counted(s):
+        if s == 0:
+            counted[0] = _lib.launch_count()
+        step(args.warmup + s)
+        if s == args.steps - 1:
+            counted[1] = _lib.launch_count()
+    reps = []
+    ms, clk = timed_under_load(step_counted, step_idle, args.steps, world, dev.index or 0, rank=rank, pre_steps=400,
+                               post_steps=120)
+    reps.append(ms)
+    for r in range(2):                                    # median of 3 timed repeats of the K steps
+        reps.append(timed_region(lambda s: step(args.warmup + args.steps * (r + 1) + s), args.steps, world))
+    ms = float(np.median(reps))
+    launches = counted[1] - counted[0]
+    # share of the triples each rank processed (load balance of the item bounds)
+    share = torch.zeros(world, dtype=torch.float64, device=dev)
+    share[rank] = float(m.n_processed.item())
+    dist.all_reduce(share)
+    share = (share / share.sum()).cpu().numpy()
+
+    tot_loss = loss.clone()
+    dist.all_reduce(tot_loss)
+    # ---- e2e: user ids arrive from pinned host memory every step, the step's loss is read back every step ----
+    host = [p.cpu().pin_memory() for p in perms]
+    dbuf = [torch.empty_like(perms[0]) for _ in range(2)]
+    hl = torch.zeros(1, dtype=torch.float64).pin_memory()
+
+    def step_e2e(s):
+        u = dbuf[s & 1]
+        with torch.cuda.stream(m.side):                       # the batch arrives on the stream that routes it
+            u.copy_(host[s % 4], non_blocking=True)
+        loss.zero_()
+        m.step(u, 5000 + s, B_glob, loss_sum=loss)
+        hl.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(hl[0])
+
+    for s in range(2):
+        step_e2e(s)
+    ms_e2e = timed_region(step_e2e, args.steps, world)
+
+    # ---- evaluation: one gather of the item shards, every rank scores its own users ----
+    n_ev = min(int(c["eval_users"]), n_loc)
+    ev_users = torch.arange(n_ev, dtype=torch.int32, device=dev)
+    m.evaluate(ev_users, target, [c["eval_k"]])
+    res = {}
+
+    def ev_step(s):
+        res["scores"], res["n"] = m.evaluate(ev_users, target, [c["eval_k"]])
+    ms_ev = timed_region(ev_step, 3, world) / 3
+    if rank == 0:
+        bpt = 24 * d + 8
+        per_gpu = bpt * B_local / (ms / args.steps * 1e-3) / 1e9
+        remote = (world - 1) / world * (1.0 - head_mass)                  # triples whose user row crosses NVLink
+        # per GPU per direction per step: the rows this rank pulls + the rows its peers write back into it
+        nvl_bytes = remote * B_local * (2 * 4 * m.ld + 12) + (2.0 * (world - 1) / world) * m.head * m.ld * 4
+        nvl_gbs = nvl_bytes / (ms / args.steps * 1e-3) / 1e9
+        out = {"metric": "BPR triples/sec (train)", "value": B_glob * args.steps / (ms * 1e-3), "unit": "triples/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "BPRMF synthetic %dx%d d=%d, item-sharded + user-sharded over %d GPUs, user rows "
+                                      "through NVSwitch peer memory inside the fused step%s"
+                                      % (m.num_users, m.num_items, d, world,
+                                         " (BASELINE configs[2])" if (m.num_users, m.num_items) == (10_000_000, 1_000_000) else ""),
+                          "batch_triples": B_glob, "per_gpu_triples": B_local, "optimizer": "sgd+l2",
+                          "lr_per_triple": c["lr_per_triple"], "reg": c["reg"], "parallelism": "p2p%d" % world,
+                          "collective": ("user rows: P2P loads/stores inside the step kernel; replicated head of the "
+                                         "catalogue (%d most popular items = %.1f %% of the positives), updated in place per "
+                                         "rank: one all-reduce of its [%d, %d] fp32 difference per step (%d MiB, combined "
+                                         "as the %s over ranks), which doubles as the step barrier"
+                                         % (m.head, 100 * head_mass, m.head, m.ld, m.head * m.ld * 4 >> 20, m.head_reduce)) if m.head else
+                                        "none on the data path: P2P loads/stores of user rows inside the step kernel; "
+                                        "one 4-byte all-reduce per step as the barrier",
+                          "head": m.head, "head_positive_mass": head_mass,
+                          "item_bounds": "contiguous ranges of equal positive mass", "l2_policy": "inputs larger than L2",
+                          "timing": "median of 3 repeats of the K steps", "repeats_ms": reps,
+                          "triple_share_per_rank": [round(float(x), 4) for x in share]},
+               "clocks": clk,
+               "e2e": {"value": B_glob * args.steps / (ms_e2e * 1e-3), "unit": "triples/s",
+                       "h2d_bytes_per_step": int(B_local * 4 * world), "d2h_bytes_per_step": 8 * world,
+                       "ms_per_step": ms_e2e / args.steps,
+                       "api": "recsys_pytorch_b200.p2p.P2PShardedBPR.step (user ids from pinned host memory, loss read "
+                              "back every step, per rank)"},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": hbm_gbs, "unit": "GB/s",
+                            "frac": per_gpu / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                            "note": "per-GPU algorithmic bytes (24d+8 per triple) of the fused step over the WHOLE step "
+                                    "time (route + barrier + step kernel)",
+                            "nvlink": {"bytes_per_gpu_per_direction_per_step": nvl_bytes, "achieved_gbs": nvl_gbs,
+                                       "model": "remote fraction x B_local x (row pulled + row written back by a peer + ids) "
+                                                "+ ring all-reduce of the head delta",
+                                       "peak_gbs": 770.0, "frac": nvl_gbs / 770.0,
+                                       "peak_source": "B200_PROFILING.md measured peer copy per direction"}},
+               "cpu_baseline": None,
+               "eval": {"scored_pairs_per_sec": float(res["n"]) * m.num_items / (ms_ev * 1e-3), "ms": ms_ev,
+                        "ndcg@%d" % c["eval_k"]: res["scores"]["NDCG@%d" % c["eval_k"]], "users": res["n"],
+                        "k": c["eval_k"], "algo": "tc", "flops_per_pair": 2 * d,
+                        "note": "whole evaluate() per rank: gather of the item shards through peer memory + scoring of "
+                                "the rank's own users + metrics + metric all-reduce; the dataset grows with N, so NDCG is "
+                                "not comparable across N (same-data parity across N: tests/test_p2p.py)"},
+               "final_loss": float(tot_loss.item()) / (B_glob * (args.steps * 3 + args.warmup))}
+        print(json.dumps(out))
+    dist.barrier()
+    m.close()
+    dist.destroy_process_group()

@@ -30,8 +30,10 @@ def _csr_from_keys(keys, num_users, num_items):
 
 
 def make_interactions(num_users, num_items, seed=2020, device="cuda", mu=3.5, sigma=0.8, dmin=10, dmax=1000,
-                      alpha=1.0, holdout_frac=0.2, chunk_users=2_000_000):
-    """Returns (train: DeviceCSR, target: DeviceCSR)."""
+                      alpha=1.0, holdout_frac=0.2, chunk_users=2_000_000, item_seed=None):
+    """Returns (train: DeviceCSR, target: DeviceCSR).  `item_seed` (multi-GPU shards of ONE dataset): the popularity
+    order of the catalogue comes from its own generator, so ranks that draw different users (`seed`) still agree on
+    which items are popular."""
     device = torch.device(device)
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -39,7 +41,12 @@ def make_interactions(num_users, num_items, seed=2020, device="cuda", mu=3.5, si
     ranks = torch.arange(1, num_items + 1, device=device, dtype=torch.float64)
     cdf = torch.cumsum(ranks.pow(-alpha), 0)
     cdf = (cdf / cdf[-1]).to(torch.float32)
-    item_perm = torch.randperm(num_items, generator=g, device=device)
+    if item_seed is None:
+        item_perm = torch.randperm(num_items, generator=g, device=device)
+    else:
+        gi = torch.Generator(device=device)
+        gi.manual_seed(item_seed)
+        item_perm = torch.randperm(num_items, generator=gi, device=device)
     tr_ptr, tr_idx, va_ptr, va_idx = [], [], [], []
     base_tr = base_va = 0
     for u0 in range(0, num_users, chunk_users):

@@ -28,14 +28,17 @@ def main():
     rows = [np.unique(rng.choice(ni, size=rng.integers(2, 20), p=pop)).astype(np.int32) for _ in range(nu)]
     indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
     indices = np.concatenate(rows)
-    ib = balanced_item_bounds(torch.from_numpy(np.bincount(indices, minlength=ni)), world)
+    head = 256                                             # replicated head rows [0, 256) + range-sharded tail
+    ib = balanced_item_bounds(torch.from_numpy(np.bincount(indices, minlength=ni)), world, head)
     ub = uniform_bounds(nu, world)
     lo, hi = ub[rank], ub[rank + 1]
     csr = engine.DeviceCSR(torch.from_numpy(indptr[lo:hi + 1] - indptr[lo]).to(dev),
                            torch.from_numpy(indices[indptr[lo]:indptr[hi]]).to(dev), (hi - lo, ni))
-    m = P2PShardedBPR(nu, ni, d, csr, rank, world, dev, ib, ub, lr=8.0, reg=0.0, init_std=0.0, seed=5, max_batch=hi - lo)
+    m = P2PShardedBPR(nu, ni, d, csr, rank, world, dev, ib, ub, lr=8.0, reg=0.0, init_std=0.0, seed=5, max_batch=hi - lo,
+                      head=head)
     m.U[:, :d] = torch.from_numpy(U0[lo:hi]).to(dev)
     m.V[:, :d] = torch.from_numpy(V0[ib[rank]:ib[rank + 1]]).to(dev)
+    m.Vh[:, :d] = torch.from_numpy(V0[:head]).to(dev)
     m.connect()
     Uc, Vc = U0, V0
     prng = np.random.default_rng(100 + rank)
@@ -45,19 +48,21 @@ def main():
         ul = torch.from_numpy(prng.permutation(hi - lo)[:B].astype(np.int32)).to(dev)
         dp, dn = torch.empty_like(ul), torch.empty_like(ul)
         m.route(ul, step, dbg_pos=dp, dbg_neg=dn)
-        m.barrier()
+        m.sync_head()
         m.compute(B * world, loss_sum=loss)
+        m.sync_head()                                      # apply this step's head delta so the tables can be compared
         m.barrier()
         torch.cuda.synchronize()
         mine = (ul.cpu().numpy() + lo, dp.cpu().numpy(), dn.cpu().numpy(), m.U.cpu().numpy()[:, :d], m.V.cpu().numpy()[:, :d],
-                int(m.n_processed.item()))
+                int(m.n_processed.item()), m.Vh.cpu().numpy()[:, :d])
         allm = [None] * world
         dist.all_gather_object(allm, mine)
         if rank == 0:
             gu, gi, gj = (np.concatenate([a[k] for a in allm]) for k in range(3))
             assert sum(a[5] for a in allm) == len(gu)
             Ur, Vr, _ = O.sgd_step(Uc, Vc, gu, gi, gj, 8.0, 0.0)
-            U = np.concatenate([a[3] for a in allm]); V = np.concatenate([a[4] for a in allm])
+            U = np.concatenate([a[3] for a in allm]); V = np.concatenate([allm[0][6]] + [a[4] for a in allm])
+            assert all(np.array_equal(a[6], allm[0][6]) for a in allm)          # head replicas identical
             stepsz = max(np.abs(Ur - Uc).max(), np.abs(Vr - Vc).max())
             dev_ = max(np.abs(U - Ur).max(), np.abs(V - Vr).max())
             assert stepsz > 2e-3 and dev_ < 0.05 * stepsz, (step, stepsz, dev_)
@@ -74,15 +79,16 @@ def main():
     pi = items[rank * 2 * B: rank * 2 * B + B].astype(np.int32); pj = items[rank * 2 * B + B: (rank + 1) * 2 * B].astype(np.int32)
     m.lr, m.reg = 0.9, 0.01
     m.route(ul, 9, pos=torch.from_numpy(pi).to(dev), neg=torch.from_numpy(pj).to(dev))
-    m.barrier(); m.compute(B * world); m.barrier()
+    m.sync_head(); m.compute(B * world); m.sync_head(); m.barrier()
     torch.cuda.synchronize()
     allm = [None] * world
-    dist.all_gather_object(allm, (ul.cpu().numpy() + lo, pi, pj, m.U.cpu().numpy()[:, :d], m.V.cpu().numpy()[:, :d]))
+    dist.all_gather_object(allm, (ul.cpu().numpy() + lo, pi, pj, m.U.cpu().numpy()[:, :d], m.V.cpu().numpy()[:, :d],
+                                  m.Vh.cpu().numpy()[:, :d]))
     if rank == 0:
         gu, gi, gj = (np.concatenate([a[k] for a in allm]) for k in range(3))
         Ur, Vr, _ = O.sgd_step(Uc, Vc, gu, gi, gj, 0.9, 0.01)
         np.testing.assert_allclose(np.concatenate([a[3] for a in allm]), Ur, rtol=2e-5, atol=2e-6)
-        np.testing.assert_allclose(np.concatenate([a[4] for a in allm]), Vr, rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(np.concatenate([allm[0][5]] + [a[4] for a in allm]), Vr, rtol=2e-5, atol=2e-6)
         print("P2P_WORKER_OK")
     dist.barrier()
     m.close()

@@ -48,7 +48,7 @@ def test_sampler_mirror_with_bounds_cpu():
 
 
 # ------------------------------------------------------------------ GPU: emulated ranks -------------------------------
-def _make(dev, W, nu, ni, d, seed, bounds=None, init=0.3, deg=12):
+def _make(dev, W, nu, ni, d, seed, bounds=None, init=0.3, deg=12, head=0):
     from recsys_pytorch_b200 import engine
     from recsys_pytorch_b200.p2p import P2PShardedBPR, uniform_bounds
     rng = np.random.default_rng(seed)
@@ -57,7 +57,7 @@ def _make(dev, W, nu, ni, d, seed, bounds=None, init=0.3, deg=12):
     rows = [np.sort(rng.choice(ni, size=rng.integers(1, deg), replace=False)).astype(np.int32) for _ in range(nu)]
     indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
     indices = np.concatenate(rows)
-    ib = bounds if bounds is not None else uniform_bounds(ni, W)
+    ib = bounds if bounds is not None else [head + b for b in uniform_bounds(ni - head, W)]
     ub = uniform_bounds(nu, W)
     ranks = []
     for r in range(W):
@@ -65,29 +65,37 @@ def _make(dev, W, nu, ni, d, seed, bounds=None, init=0.3, deg=12):
         ip = torch.from_numpy(indptr[lo:hi + 1] - indptr[lo]).to(dev)
         ix = torch.from_numpy(indices[indptr[lo]:indptr[hi]]).to(dev)
         obj = P2PShardedBPR(nu, ni, d, engine.DeviceCSR(ip, ix, (hi - lo, ni)), r, W, dev, ib, ub, lr=0.9, reg=0.01,
-                            init_std=0.0, seed=11, max_batch=hi - lo)
+                            init_std=0.0, seed=11, max_batch=hi - lo, head=head)
         obj.U[:, :d] = torch.from_numpy(U0[lo:hi]).to(dev)
         obj.V[:, :d] = torch.from_numpy(V0[ib[r]:ib[r + 1]]).to(dev)
+        if head:
+            obj.Vh[:, :d] = torch.from_numpy(V0[:head]).to(dev)
         ranks.append(obj)
     P2PShardedBPR.connect_local(ranks)
     return ranks, U0, V0, indptr, indices, ib, ub
 
 
 def _tables(ranks, d):
+    from recsys_pytorch_b200.p2p import P2PShardedBPR
+    P2PShardedBPR.sync_head_local(ranks)                      # emulated all-reduce of the head delta
     U = np.concatenate([r.U.cpu().numpy()[:, :d] for r in ranks])
-    V = np.concatenate([r.V.cpu().numpy()[:, :d] for r in ranks])
+    V = np.concatenate(([ranks[0].Vh.cpu().numpy()[:, :d]] if ranks[0].head else []) + [r.V.cpu().numpy()[:, :d] for r in ranks])
+    for r in ranks[1:]:
+        if r.head:
+            assert torch.equal(r.Vh, ranks[0].Vh)              # replicas are identical after the exchange
     return U, V
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("W", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("d", [128, 50, 200])
-def test_p2p_given_triples_cross_shard_equals_single_device(dev, W, d):
+@pytest.mark.parametrize("head", [0, 300])
+def test_p2p_given_triples_cross_shard_equals_single_device(dev, W, d, head):
     """Fixed-triple parity mode (SURVEY 8(e) bullet 2): arbitrary (u, i, j) with i and j on DIFFERENT shards; no id is
     shared between triples, so the Hogwild step is the exact step: tables == oracle at rtol 2e-5."""
     nu, ni = 1536, 4000
-    bounds = None if W == 1 else sorted({0, ni} | set(np.random.default_rng(W).choice(np.arange(1, ni), W - 1, replace=False).tolist()))
-    ranks, U0, V0, _, _, ib, ub = _make(dev, W, nu, ni, d, seed=W * 100 + d, bounds=bounds)
+    bounds = None if W == 1 else sorted({head, ni} | set(np.random.default_rng(W).choice(np.arange(head + 1, ni), W - 1, replace=False).tolist()))
+    ranks, U0, V0, _, _, ib, ub = _make(dev, W, nu, ni, d, seed=W * 100 + d, bounds=bounds, head=head)
     rng = np.random.default_rng(5)
     items = rng.permutation(ni)
     gu, gi, gj = [], [], []
@@ -119,13 +127,14 @@ def test_p2p_given_triples_cross_shard_equals_single_device(dev, W, d):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("W", [1, 2, 4, 8])
-def test_p2p_sampled_step_routing_and_oracle(dev, W):
+@pytest.mark.parametrize("head", [0, 200])
+def test_p2p_sampled_step_routing_and_oracle(dev, W, head):
     """On-device sampling + routing: the triples drawn are bit-identical to the host mirror, every triple lands in the
     outbox segment of owner(pos) exactly once with its negative inside that owner's range, and two Hogwild steps stay
     within the second-order bound of the exact oracle step on those triples."""
-    from recsys_pytorch_b200.p2p import owner_from_bounds
+    from recsys_pytorch_b200.p2p import P2PShardedBPR, owner_from_bounds
     nu, ni, d = 2048, 1500, 128
-    ranks, U0, V0, indptr, indices, ib, ub = _make(dev, W, nu, ni, d, seed=W, init=0.3)
+    ranks, U0, V0, indptr, indices, ib, ub = _make(dev, W, nu, ni, d, seed=W, init=0.3, head=head)
     for r in ranks:
         r.lr, r.reg = 8.0, 0.0
     rng = np.random.default_rng(1)
@@ -141,22 +150,24 @@ def test_p2p_sampled_step_routing_and_oracle(dev, W):
             ulh, dph, dnh = ul.cpu().numpy(), dp.cpu().numpy(), dn.cpu().numpy()
             ob = r.ob[r._n & 1]
             cnt = ob["cnt"].cpu().numpy()[:W]
-            own = owner_from_bounds(dph, ib)
+            own = np.where(dph < head, r.rank, owner_from_bounds(dph, ib))      # head positives stay at home
             assert (dph >= 0).all() and (dnh >= 0).all()
             assert (cnt == np.bincount(own, minlength=W)).all()
             for dst in range(W):                                      # segment content == the triples owned by dst
                 seg = np.stack([ob[k_].cpu().numpy()[dst, :cnt[dst]] for k_ in ("u", "i", "j")], 1)
                 exp = np.stack([ulh[own == dst], dph[own == dst], dnh[own == dst]], 1)
                 assert (seg[np.lexsort(seg.T[::-1])] == exp[np.lexsort(exp.T[::-1])]).all()
-            assert (owner_from_bounds(dnh, ib) == own).all()           # negative co-located with the positive
+            assert ((dnh < head) | (owner_from_bounds(dnh, ib) == own)).all()   # negative: head, or the processing rank's shard
             for t in range(0, B, 97):                                 # host mirror of the counter-RNG draws
-                p_, n_ = O.sample_triple(11, step * W + r.rank, t, int(ulh[t]) + r.ulo, indptr, indices, ni, item_bounds=ib)
+                p_, n_ = O.sample_triple(11, step * W + r.rank, t, int(ulh[t]) + r.ulo, indptr, indices, ni, item_bounds=ib,
+                                         head=head, rank=r.rank)
                 assert (p_, n_) == (int(dph[t]), int(dnh[t]))
             gu.append(ulh + r.ulo); gi.append(dph); gj.append(dnh)
         gu, gi, gj = np.concatenate(gu), np.concatenate(gi), np.concatenate(gj)
         for t in range(len(gu)):                                      # a negative is never one of the user's positives
             if t % 13 == 0:
                 assert gj[t] not in indices[indptr[gu[t]]:indptr[gu[t] + 1]]
+        P2PShardedBPR.sync_head_local(ranks)
         for r in ranks:
             r.compute(len(gu))
         Ur, Vr, _ = O.sgd_step(Uc, Vc, gu, gi, gj, 8.0, 0.0)
@@ -170,13 +181,36 @@ def test_p2p_sampled_step_routing_and_oracle(dev, W):
 
 
 @pytest.mark.gpu
+def test_p2p_head_mean_reduce_is_the_average_of_rank_trajectories(dev):
+    """head_reduce='mean' (per-step parameter averaging of the replicated head rows): after the exchange every replica
+    equals snapshot + mean over ranks of what each rank's own step did to its replica."""
+    from recsys_pytorch_b200.p2p import P2PShardedBPR
+    W, nu, ni, d, head = 4, 2048, 1500, 128, 200
+    ranks, U0, V0, indptr, indices, ib, ub = _make(dev, W, nu, ni, d, seed=3, head=head)
+    rng = np.random.default_rng(0)
+    for r in ranks:
+        r.head_reduce, r.lr, r.reg = "mean", 4.0, 0.0
+        r.route(torch.from_numpy(rng.permutation(r.uhi - r.ulo)[:400].astype(np.int32)).to(dev), 1)
+    for r in ranks:
+        r.compute(1600)
+    own = [(r.Vh - r._snap).clone() for r in ranks]
+    assert all(float(o.abs().max()) > 0 for o in own)
+    P2PShardedBPR.sync_head_local(ranks)
+    want = torch.from_numpy(V0[:head]).to(dev) + torch.stack(own).sum(0)[:, :d] / W
+    for r in ranks:
+        assert torch.equal(r.Vh, ranks[0].Vh)
+        torch.testing.assert_close(r.Vh[:, :d], want, rtol=1e-6, atol=1e-7)
+        r.close()
+
+
+@pytest.mark.gpu
 def test_p2p_gather_items_and_sharded_evaluation_equals_single(dev):
     """Evaluation in the layout: gathered item table == concatenation of the shards; per-rank scoring of its own users
     gives the same top-k as one device holding everything."""
     from recsys_pytorch_b200 import engine
     from recsys_pytorch_b200._lib import SCORE_EXACT
     W, nu, ni, d = 4, 1024, 3000, 64
-    ranks, U0, V0, indptr, indices, ib, ub = _make(dev, W, nu, ni, d, seed=9)
+    ranks, U0, V0, indptr, indices, ib, ub = _make(dev, W, nu, ni, d, seed=9, head=128)
     full = ranks[1].gather_items()
     assert np.array_equal(full.cpu().numpy()[:, :d], V0)
     Ug = engine.alloc_table(nu, d, dev, std=0.0); Ug[:, :d] = torch.from_numpy(U0).to(dev)

@@ -60,7 +60,15 @@ int main(int argc, char **argv) {
     const int64_t rows = argc > 1 ? atoll(argv[1]) : 1000000;
     const int n = argc > 2 ? atoi(argv[2]) : 1000000;
     float *T, *sink; int *ids;
-    CK(cudaMalloc(&T, rows * 512)); CK(cudaMemset(T, 0, rows * 512)); CK(cudaMalloc(&sink, 4));
+    const bool peer = argc > 3 && atoi(argv[3]) == 1;     // table on GPU 1, kernels on GPU 0: NVLink peer gather
+    if (peer) {
+        CK(cudaSetDevice(1)); CK(cudaMalloc(&T, rows * 512)); CK(cudaMemset(T, 0, rows * 512)); CK(cudaDeviceSynchronize());
+        CK(cudaSetDevice(0)); CK(cudaDeviceEnablePeerAccess(1, 0));
+        printf("PEER mode: table lives on GPU 1, gathered from GPU 0 over NVLink\n");
+    } else {
+        CK(cudaMalloc(&T, rows * 512)); CK(cudaMemset(T, 0, rows * 512));
+    }
+    CK(cudaMalloc(&sink, 4));
     std::vector<int> h(rows);
     for (int64_t i = 0; i < rows; ++i) h[i] = (int)i;
     std::mt19937 rng(1); std::shuffle(h.begin(), h.end(), rng);
@@ -74,6 +82,11 @@ int main(int argc, char **argv) {
     run<8, 2, W>(nm, T, ids, n, sink, 3); run<4, 1, W>(nm, T, ids, n, sink, 8); run<4, 2, W>(nm, T, ids, n, sink, 4);
     SWEEP(false, "read")
     SWEEP(true, "read+write")
+    if (peer) {   // deeper: more rows in flight per warp / more warps
+        run<32, 16, false>("read", T, ids, n, sink, 8); run<32, 8, false>("read", T, ids, n, sink, 6);
+        run<8, 4, false>("read", T, ids, n, sink, 8); run<8, 8, false>("read", T, ids, n, sink, 4);
+        run<32, 16, true>("read+write", T, ids, n, sink, 8); run<8, 4, true>("read+write", T, ids, n, sink, 8);
+    }
     // sorted ids (sequential rows): the streaming bound of the same kernel
     std::sort(h.begin(), h.begin() + n);
     CK(cudaMemcpy(ids, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
