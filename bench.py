@@ -181,6 +181,7 @@ def run_b200(args):
     if args.small:
         c.update(num_users=50_000, num_items=20_000, batch=50_000, eval_users=4096)
     hbm_gbs, bf16_tf, peak_src = measured_peaks()
+    args.bf16_tf = bf16_tf
 
     if world > 1:
         c["small"] = bool(args.small)
@@ -296,7 +297,26 @@ def run_b200(args):
                 "kernel": {"ldg": "bpr_step_fast_kernel<1,uniq,loss>", "async": "bpr_step_async_kernel<1,uniq,loss,8>",
                            "tma": "bpr_step_tma_kernel<32,1,UPDATE>", "generic": "bpr_step_ldg_kernel<32,1,UPDATE>"}[args.gather]}
 
-    cpu_base = cpu_baseline_leg(c, args) if not args.no_cpu else None
+    cpu_base = None
+    if not args.no_cpu:
+        # the (u,i,j) batches the device sampler itself draws, read back for the CPU arm
+        gpu_triples = {}
+        for bsz in (65_536 if not args.small else 8192, 256):
+            lst = []
+            for b in range(4):
+                u = perms[b % n_perm][:bsz].contiguous()
+                p_, n_ = engine.sample_triples(u, train, c["seed"], 9000 + b)
+                lst.append(tuple(t.cpu().long() for t in (u, p_, torch.clamp(n_, min=0))))
+            gpu_triples[bsz] = lst
+        cpu_base = cpu_baseline_leg(c, args, gpu_triples)
+    legs = {}
+    if not args.no_legs:
+        from recsys_pytorch_b200 import bench_legs
+        del model, ev
+        torch.cuda.empty_cache()
+        legs["lightgcn_cfg4"] = bench_legs.cfg4_leg(dev, hbm_gbs, peak_src, small=args.small)
+        torch.cuda.empty_cache()
+        legs["eval_cfg5"] = bench_legs.cfg5_leg(dev, 0, 1, bf16_tf, peak_src, small=args.small)
     out = {"metric": "BPR triples/sec (train)", "value": triples_per_s, "unit": "triples/s", "n_gpus": 1,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -306,6 +326,7 @@ def run_b200(args):
                       "l2_policy": "inputs larger than L2 (512 MB of user rows per step)", "nnz_train": train.nnz},
            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base,
            "eval": eval_leg, "final_loss": float(loss.item()) / (B * (args.steps + args.warmup))}
+    out.update(legs)
     print(json.dumps(out))
 
 
@@ -322,28 +343,72 @@ class _SubsetTarget:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference's torch CPU path restated (oracle/torch_port.py)
 # ------------------------------------------------------------------------------------------------
-def _cpu_workload(c, batch, n_batches, seed):
+def _host_threads():
+    """All host cores for the CPU arm - torchrun exports OMP_NUM_THREADS=1, which made round 1's N>1 reference
+    numbers 7.5x too slow."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
+def _cpu_csr(c, n_rows, seed):
+    """Synthetic interactions (same recipe as the GPU arm) for `n_rows` users, on the host."""
+    from recsys_pytorch_b200 import synthetic
+    tr, tg = synthetic.make_interactions_raw(n_rows, c["num_items"], seed=seed, device="cpu")
+    return ((tr[0].numpy(), tr[1].numpy()), (tg[0].numpy(), tg[1].numpy()))
+
+
+def _cpu_batches(c, csr, batch, n_batches, seed):
+    """(u, i, j) batches drawn by the HOST MIRROR of the device sampler (oracle.bpr_oracle.sample_triples_vec: the same
+    counter RNG, bit-identical to the kernel's draws for the same CSR, tests/test_gpu_parity.py): users are random rows
+    of the full-size table, their positives / negatives come from the CSR rows of a host-generated user sample."""
+    from oracle import bpr_oracle as O
+    indptr, indices = csr
+    n_rows = len(indptr) - 1
     rng = np.random.default_rng(seed)
     out = []
-    for _ in range(n_batches):
-        u = torch.from_numpy(rng.permutation(c["num_users"])[:batch].astype(np.int64))
-        i = torch.from_numpy(rng.integers(0, c["num_items"], batch).astype(np.int64))
-        j = torch.from_numpy(rng.integers(0, c["num_items"], batch).astype(np.int64))
-        out.append((u, i, j))
+    for b in range(n_batches):
+        rows = rng.permutation(n_rows)[:batch] if batch <= n_rows else rng.integers(0, n_rows, batch)
+        pos, neg = O.sample_triples_vec(c["seed"], b + 1, rows, indptr, indices, c["num_items"])
+        neg = np.where(neg < 0, 0, neg)
+        users = rng.permutation(c["num_users"])[:batch]
+        out.append(tuple(torch.from_numpy(np.ascontiguousarray(a, np.int64)) for a in (users, pos, neg)))
     return out
 
 
-def cpu_baseline_leg(c, args, steps=3, warmup=1, batch=65_536):
-    """Bounded sample on the host cores: a few 65,536-triple steps of the reference's own step
-    (dense autograd grads + dense Adam over all U+I rows, models/MF.py:64-68) at the same table sizes."""
+def _cpu_train_legs(c, batches_by_size, steps, warmup, table_sizes):
+    """reference step (MF.py:64-68) timed as-is (dense Adam) and with the parity optimiser (SGD swap), at
+    every batch size given.  Returns {leg: triples/s}."""
     from oracle import torch_port as TP
+    nu, ni = table_sizes
+    legs = {}
+    for opt in ("adam", "sgd"):
+        model = TP.RefMF(nu, ni, c["d"], init_std=c["init_std"], optimizer=opt, lr=1e-3 if opt == "adam" else 0.05)
+        for batch, batches in batches_by_size.items():
+            sec = TP.time_train(model, batches[:steps + warmup], warmup)
+            legs["%s_b%d" % (opt, batch)] = {"triples_per_s": batch / sec, "s_per_step": sec}
+        del model
+    return legs
+
+
+def cpu_baseline_leg(c, args, gpu_triples=None, steps=3, warmup=1):
+    """Bounded sample on the host cores: the reference's own step (dense autograd grads + dense Adam over all U+I
+    rows, models/MF.py:64-68) at the same table sizes, on the (u, i, j) batches the GPU engine itself sampled
+    (`gpu_triples`: {batch_size: [(u,i,j) int64 CPU tensors]})."""
     t_all = time.perf_counter()
-    model = TP.RefMF(c["num_users"], c["num_items"], c["d"], init_std=c["init_std"])
-    sec = TP.time_train(model, _cpu_workload(c, batch, steps + warmup, 1), warmup)
-    return {"value": batch / sec, "unit": "triples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d steps of %d triples (reference MF.py:64-68 restated on torch CPU: dense grads + dense Adam "
-                      "over %d rows); %.1f s total" % (steps, batch, c["num_users"] + c["num_items"],
-                                                       time.perf_counter() - t_all)}
+    cores = _host_threads()
+    legs = _cpu_train_legs(c, gpu_triples, steps, warmup, (c["num_users"], c["num_items"]))
+    head = legs["adam_b65536"] if "adam_b65536" in legs else next(iter(legs.values()))
+    return {"value": head["triples_per_s"], "unit": "triples/s", "cores": cores, "kind": "port", "legs": legs,
+            "sample": "%d timed steps per leg of the reference step (MF.py:64-68 restated on torch CPU: dense autograd "
+                      "grads + dense optimiser sweep over %d rows) on the very (u,i,j) batches the device sampler "
+                      "produced in this run; legs: Adam as-is and the SGD parity swap at B=256 and B=65,536; value = "
+                      "Adam at B=65,536; %.1f s total" % (steps, c["num_users"] + c["num_items"],
+                                                            time.perf_counter() - t_all)}
 
 
 def run_reference(args):
@@ -351,39 +416,40 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import torch_port as TP
+    cores = _host_threads()
     c = dict(CFG)
     if args.small:
         c.update(num_users=50_000, num_items=20_000, batch=50_000, eval_users=4096)
-    batch = 65_536 if not args.small else 8192
-    model = TP.RefMF(c["num_users"], c["num_items"], c["d"], init_std=c["init_std"])
-    wl = _cpu_workload(c, batch, args.steps + args.warmup, 1)
-    sec = TP.time_train(model, wl, args.warmup)
-    val = batch / sec
-    # evaluation leg: chunked restatement on 2 chunks of 1024 users
+    big = 65_536 if not args.small else 8192
+    (tr, tg) = _cpu_csr(c, 2 * big, seed=c["seed"])
+    n_b = args.steps + args.warmup
+    batches = {big: _cpu_batches(c, tr, big, n_b, 1), 256: _cpu_batches(c, tr, 256, n_b, 2)}
+    legs = _cpu_train_legs(c, batches, args.steps, args.warmup, (c["num_users"], c["num_items"]))
+    head = legs["adam_b%d" % big]
+    # evaluation leg: the chunked restatement (MF.py:109-112 + in-chunk -inf mask + func.h top-k + holdout.h) on 8
+    # chunks of 1024 users
     fns, kind = TP.native_eval_lib()
-    rng = np.random.default_rng(3)
-    deg = 40
-    mp = np.arange(c["num_users"] + 1, dtype=np.int64)[:2049] * deg
-    mi = np.sort(rng.integers(0, c["num_items"], (2048, deg)), 1).astype(np.int32).ravel()
-    tp = np.arange(2049, dtype=np.int64) * 8
-    ti = rng.integers(0, c["num_items"], 2048 * 8).astype(np.int32)
+    model = TP.RefMF(c["num_users"], c["num_items"], c["d"], init_std=c["init_std"])
+    n_chunks, cu = 8, 1024
     t0 = time.perf_counter(); pairs = 0
-    for ch in range(2):
-        users = np.arange(ch * 1024, (ch + 1) * 1024)
-        n, _ = TP.eval_chunk(model, users, mp, mi, tp, ti, c["eval_k"], fns)
+    for ch in range(n_chunks):
+        users = np.arange(ch * cu, (ch + 1) * cu)
+        n, _ = TP.eval_chunk(model, users, tr[0], tr[1], tg[0], tg[1], c["eval_k"], fns)
         pairs += n
     t_eval = time.perf_counter() - t0
-    cores = torch.get_num_threads()
-    sample = "%d steps x %d triples at %dx%d d=%d (dense autograd + dense Adam, MF.py:64-68)" % (
-        args.steps, batch, c["num_users"], c["num_items"], c["d"])
-    out = {"impl": "reference", "metric": "BPR triples/sec (train)", "value": val, "unit": "triples/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+    sample = ("%d timed steps x %d triples at %dx%d d=%d (dense autograd + dense Adam, MF.py:64-68) on batches drawn by "
+              "the host mirror of the device sampler; legs: Adam / SGD swap at B=256 and B=%d"
+              % (args.steps, big, c["num_users"], c["num_items"], c["d"], big))
+    out = {"impl": "reference", "metric": "BPR triples/sec (train)", "value": head["triples_per_s"], "unit": "triples/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["s_per_step"] * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "BPRMF synthetic %dx%d d=%d (BASELINE configs[1]), reference CPU path" %
-                      (c["num_users"], c["num_items"], c["d"]), "batch_triples": batch, "optimizer": "adam (MF.py:30)"},
-           "cpu_baseline": {"value": val, "unit": "triples/s", "cores": cores, "kind": "port", "sample": sample},
-           "e2e": {"value": val, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "eval": {"scored_pairs_per_sec": pairs / t_eval, "native": kind, "users": 2048, "k": c["eval_k"]},
+                      (c["num_users"], c["num_items"], c["d"]), "batch_triples": big, "optimizer": "adam (MF.py:30)"},
+           "cpu_baseline": {"value": head["triples_per_s"], "unit": "triples/s", "cores": cores, "kind": "port",
+                            "sample": sample, "legs": legs},
+           "e2e": {"value": head["triples_per_s"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "eval": {"scored_pairs_per_sec": pairs / t_eval, "native": kind, "users": n_chunks * cu, "chunks": n_chunks,
+                    "k": c["eval_k"]},
            "gpu_launches": 0}
     print(json.dumps(out))
 
@@ -402,19 +468,24 @@ def main():
                          "written: replicated user table + NCCL all-reduce of the user-delta buffer) or user_sharded "
                          "(replicated item table + all-reduce of the dense item delta)")
     ap.add_argument("--no-secondary", dest="no_secondary", action="store_true")
+    ap.add_argument("--shape", default="cfg3", choices=["cfg3", "cfg2"],
+                    help="N>1 item_sharded / user_sharded: cfg3 = 1.25M users + 125k items per GPU (N=8: 10M x 1M), "
+                         "cfg2 = N x 1M users over 100k items (round 1's scaling shape)")
     ap.add_argument("--head", type=int, default=None,
-                    help="N>1 p2p: number of most-popular items replicated on every rank (default 16384; 0 = pure range "
-                         "sharding of the whole catalogue)")
+                    help="N>1 p2p: number of most-popular items replicated on every rank (default 0 = pure range "
+                         "sharding of the whole catalogue; experimental, see p2p.default_head)")
     ap.add_argument("--wire", default="fp32", choices=["fp32", "bf16"],
                     help="N>1 user_sharded: dtype of the all-reduced item-delta buffer")
     ap.add_argument("--exchange", default="auto", choices=["auto", "diff", "buffer"],
                     help="N>1 user_sharded: 'diff' = kernel updates the item replica in place and the difference is "
                          "all-reduced; 'buffer' = kernel accumulates item deltas in a separate dense buffer; 'auto' = "
                          "diff at N=2 (measured 3.44 vs 3.18 G triples/s), buffer at N>=4 (6.20 vs 5.23 G at N=4)")
-    ap.add_argument("--head-reduce", dest="head_reduce", default="mean", choices=["mean", "sum"],
+    ap.add_argument("--head-reduce", dest="head_reduce", default="sum", choices=["mean", "sum"],
                     help="N>1 p2p with a replicated head: how the per-rank differences of the head rows are combined")
     ap.add_argument("--small", action="store_true", help="tiny shapes for a quick functional run (NOT a bench value)")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-legs", dest="no_legs", action="store_true",
+                    help="skip the secondary workloads (LightGCN cfg4 at N=1, scoring sweep cfg5 at every N)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -183,7 +183,8 @@ class UserShardedBPR:
         self.apply_item_delta(dV)
 
     # ---- same step with the collective hidden behind the next step's kernel --------------------------
-    def step_overlapped(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True):
+    def step_overlapped(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True, out_pos=None,
+                        out_neg=None):
         """The all-reduce of step s runs on a side stream while the fused kernel of step s+1 executes; the
         reduced item delta is applied one step late (item rows are one step stale - bounded-staleness SGD;
         `flush()` applies the last delta).  User rows are never stale."""
@@ -198,8 +199,8 @@ class UserShardedBPR:
         buf.zero_()
         engine.bpr_step(self.U, self.V, self.d, users_local, csr=self.train, lr=self.lr, reg=self.reg,
                         sink=SINK_UPDATE, flags=self.flags | (F_USERS_UNIQUE if users_unique else 0), seed=self.seed,
-                        step=step_key * self.world + self.rank, loss_sum=loss_sum, gV=buf,
-                        inv_batch=1.0 / float(global_batch))
+                        step=step_key * self.world + self.rank, loss_sum=loss_sum, gV=buf, out_pos=out_pos,
+                        out_neg=out_neg, inv_batch=1.0 / float(global_batch))
         ov["ev_k"].record(main)
         with torch.cuda.stream(ov["comm"]):
             ov["comm"].wait_event(ov["ev_k"])
@@ -212,7 +213,7 @@ class UserShardedBPR:
         ov["n"] += 1
 
     # ---- update in place, exchange the difference ------------------------------------------------------
-    def step_diff(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True):
+    def step_diff(self, users_local, step_key, global_batch, loss_sum=None, users_unique=True, out_pos=None, out_neg=None):
         """Same overlapped schedule, but the fused kernel updates this rank's item replica IN PLACE (the single-GPU
         fast path: a separate 51 MB delta buffer next to V does not fit L2 together with 1 GB of streaming user rows and
         costs the kernel +25 %), and what crosses NVLink is the difference it made:
@@ -233,7 +234,8 @@ class UserShardedBPR:
         engine.bpr_step(self.U, self.V, self.d, users_local, csr=self.train, lr=self.lr, reg=self.reg,
                         sink=SINK_UPDATE, flags=(self.flags & ~(F_ITEM_DELTA | F_ITEM_DELTA_BF16)) |
                         (F_USERS_UNIQUE if users_unique else 0), seed=self.seed,
-                        step=step_key * self.world + self.rank, loss_sum=loss_sum, inv_batch=1.0 / float(global_batch))
+                        step=step_key * self.world + self.rank, loss_sum=loss_sum, out_pos=out_pos, out_neg=out_neg,
+                        inv_batch=1.0 / float(global_batch))
         engine.delta_diff(self.V, df["snap"], df["wire"][cur], df["own"][cur])
         df["ev_k"].record(main)
         with torch.cuda.stream(df["comm"]):
@@ -275,14 +277,20 @@ class UserShardedBPR:
 # bench.py --gpus N (N > 1)
 # ------------------------------------------------------------------------------------------------
 def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs, peak_src):
-    """Weak scaling: per-GPU work is fixed (B_local = c['batch'] triples per rank per step); the
-    user population grows with N (N x num_users) while the item catalogue follows BASELINE
-    configs[2] proportionally (N x num_items, capped at 1M)."""
+    """The two NCCL-collective layouts (kept beside the default P2P layout of p2p.py for comparison).  Weak scaling:
+    per-GPU work is fixed (B_local = c['batch'] triples per rank per step).  --shape cfg3 (default): every GPU brings
+    1.25M users and 125k items (N = 8 is BASELINE configs[2], 10M x 1M); --shape cfg2: round 1's shape, N x 1M users
+    over a fixed 100k-item catalogue.  The per-triple step lr/B_glob is the same for every N."""
     from . import _lib, synthetic
+    from .p2p import PER_GPU
     d = c["d"]
     B_local = c["batch"]
-    # weak scaling: every GPU brings its own 1M users; the catalogue (100k items) does not grow
-    nu, ni = c["num_users"] * world, c["num_items"]
+    if getattr(args, "shape", "cfg3") == "cfg3" and not c.get("small"):
+        nu, ni = PER_GPU["users"] * world, PER_GPU["items"] * world
+    else:
+        nu, ni = c["num_users"] * world, c["num_items"]
+    c = dict(c)
+    c["lr"] = c["lr_per_triple"] * B_local * world          # r1 kept lr fixed while 1/B_glob shrank: user step ~ 1/N
     layout = args.layout
     loss = torch.zeros(1, dtype=torch.float64, device=dev)
     secondary = None
@@ -304,7 +312,8 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
         coll = "all_reduce(sum) of the [B, ld] fp32 user-delta buffer (%d MiB) per step" % (B_glob * wire >> 20)
     else:
         ulo, uhi = shard_range(nu, world, rank)
-        train, target = synthetic.make_interactions(uhi - ulo, ni, seed=c["seed"] + rank, device=dev)
+        train, target = synthetic.make_interactions(uhi - ulo, ni, seed=c["seed"] + 1 + rank, device=dev,
+                                                    item_seed=c["seed"])
         tr = UserShardedBPR(nu, ni, d, train, rank, world, dev, lr=c["lr"], reg=c["reg"], init_std=c["init_std"],
                             seed=c["seed"], gather=args.gather, wire_dtype=getattr(args, "wire", "fp32"))
         g = torch.Generator(device=dev); g.manual_seed(c["seed"] + rank)

@@ -209,7 +209,9 @@ class Evaluator:
         nk = len(self.top_k)
         sums = np.zeros(len(metrics) * nk, np.float64)
         hist = []
-        chunk = max(int(self.batch_size), 1) * 64           # users per fused launch
+        # users per fused call: 8 launches' worth of the tensor-core kernel (148 SMs x 256 rows x 2 waves = 75,776 rows per
+        # launch, csrc/score_tc.cu): whole waves, and the item-side pre-pass of a call is shared by all of them
+        chunk = 75_776 * 8
         for st in range(0, len(eval_users), chunk):
             u = users[st:st + chunk]
             idx, _ = model.predict_topk_device(u, self.eval_input, self.max_k)

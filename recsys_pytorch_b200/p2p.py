@@ -413,12 +413,15 @@ PER_GPU = dict(users=1_250_000, items=125_000)     # x8 = BASELINE configs[2]: 1
 
 
 def default_head(num_items, world):
-    """Replicated head size: 16,384 rows (8 MB at d=128: a ~50 us all-reduce) hold ~70 % of the positives of a Zipf(1)
-    catalogue of 1M items; never more than an eighth of the catalogue; none on a single GPU."""
-    return 0 if world == 1 else int(min(16_384, num_items // 8))
+    """Replicated head size used when none is given: 0 - pure range sharding.  A replicated head (e.g. 16,384 rows =
+    8 MB at d=128, ~70 % of the positives of a Zipf(1) catalogue of 1M items) removes most NVLink traffic, but its
+    synchronous exchange has no combiner that is right at every batch size: 'sum' overshoots once a hot row saturates
+    inside one rank's step (NaN at 8 ranks x 1M triples), 'mean' divides the head's learning rate by the number of ranks
+    when it does not (tests/test_p2p.py::test_p2p_same_data_ndcg_flat_across_world_sizes).  Opt-in: --head."""
+    return 0
 
 
-def build_rank(c, rank, world, dev, d=None, max_batch=None, lr=None, head=None, head_reduce="mean"):
+def build_rank(c, rank, world, dev, d=None, max_batch=None, lr=None, head=None, head_reduce="sum"):
     """This rank's shard of the weak-scaling dataset: `PER_GPU` users and items per GPU (N = 8 is cfg3), one global Zipf
     popularity order (item_seed), catalogue renumbered by popularity, balanced item bounds over the tail from the
     all-reduced item histogram."""
@@ -451,7 +454,7 @@ def bench_p2p(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs
     B_glob = B_local * world
     lr = c["lr_per_triple"] * B_glob                      # the per-triple step does not depend on N (lr * 1/B_glob)
     m, train, target, hist = build_rank(c, rank, world, dev, lr=lr, max_batch=B_local, head=getattr(args, "head", None),
-                                            head_reduce=getattr(args, "head_reduce", "mean"))
+                                            head_reduce=getattr(args, "head_reduce", "sum"))
     n_loc = m.uhi - m.ulo
     head_mass = float(hist[:m.head].sum()) / float(hist.sum()) if m.head else 0.0
     g = torch.Generator(device=dev); g.manual_seed(c["seed"] + rank)
@@ -524,6 +527,13 @@ def bench_p2p(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs
     def ev_step(s):
         res["scores"], res["n"] = m.evaluate(ev_users, target, [c["eval_k"]])
     ms_ev = timed_region(ev_step, 3, world) / 3
+    cfg5 = None
+    if not getattr(args, "no_legs", False):
+        from . import bench_legs
+        m.close(); del train, target
+        torch.cuda.empty_cache()
+        cfg5 = bench_legs.cfg5_leg(dev, rank, world, float(getattr(args, "bf16_tf", 1590.0)), peak_src,
+                                   small=bool(c.get("small")))
     if rank == 0:
         bpt = 24 * d + 8
         per_gpu = bpt * B_local / (ms / args.steps * 1e-3) / 1e9
@@ -575,7 +585,10 @@ def bench_p2p(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs
                                 "the rank's own users + metrics + metric all-reduce; the dataset grows with N, so NDCG is "
                                 "not comparable across N (same-data parity across N: tests/test_p2p.py)"},
                "final_loss": float(tot_loss.item()) / (B_glob * (args.steps * 3 + args.warmup))}
+        if cfg5 is not None:
+            out["eval_cfg5"] = cfg5
         print(json.dumps(out))
     dist.barrier()
-    m.close()
+    if cfg5 is None:
+        m.close()
     dist.destroy_process_group()

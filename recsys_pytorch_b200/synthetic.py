@@ -29,9 +29,16 @@ def _csr_from_keys(keys, num_users, num_items):
     return indptr, cols, rows
 
 
-def make_interactions(num_users, num_items, seed=2020, device="cuda", mu=3.5, sigma=0.8, dmin=10, dmax=1000,
-                      alpha=1.0, holdout_frac=0.2, chunk_users=2_000_000, item_seed=None):
-    """Returns (train: DeviceCSR, target: DeviceCSR).  `item_seed` (multi-GPU shards of ONE dataset): the popularity
+def make_interactions(num_users, num_items, seed=2020, device="cuda", **kw):
+    """Returns (train: DeviceCSR, target: DeviceCSR); see `make_interactions_raw` for the recipe and options."""
+    (tp, ti), (vp, vi) = make_interactions_raw(num_users, num_items, seed=seed, device=device, **kw)
+    return DeviceCSR(tp, ti, (num_users, num_items)), DeviceCSR(vp, vi, (num_users, num_items))
+
+
+def make_interactions_raw(num_users, num_items, seed=2020, device="cuda", mu=3.5, sigma=0.8, dmin=10, dmax=1000,
+                          alpha=1.0, holdout_frac=0.2, chunk_users=2_000_000, item_seed=None):
+    """Returns ((train_indptr int64, train_indices int32), (target_indptr, target_indices)) as plain tensors on
+    `device` (which may be the CPU: the host arm of bench.py builds its sample of the dataset with the same recipe).  `item_seed` (multi-GPU shards of ONE dataset): the popularity
     order of the catalogue comes from its own generator, so ranks that draw different users (`seed`) still agree on
     which items are popular."""
     device = torch.device(device)
@@ -76,9 +83,8 @@ def make_interactions(num_users, num_items, seed=2020, device="cuda", mu=3.5, si
             else:
                 base_va += int(p[-1])
     z = torch.zeros(1, dtype=torch.int64, device=device)
-    train = DeviceCSR(torch.cat([z] + tr_ptr).contiguous(), torch.cat(tr_idx).contiguous(), (num_users, num_items))
-    target = DeviceCSR(torch.cat([z] + va_ptr).contiguous(), torch.cat(va_idx).contiguous(), (num_users, num_items))
-    return train, target
+    return ((torch.cat([z] + tr_ptr).contiguous(), torch.cat(tr_idx).contiguous()),
+            (torch.cat([z] + va_ptr).contiguous(), torch.cat(va_idx).contiguous()))
 
 
 def to_scipy(csr: DeviceCSR):

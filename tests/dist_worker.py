@@ -44,6 +44,29 @@ def main():
     chk = tu.V.double().sum().reshape(1)
     dist.all_gather(both, chk)
     assert all(torch.equal(b, both[0]) for b in both), "item replicas diverged (overlapped steps)"
+    # the overlapped schedule against its one-step-stale numpy oracle on the union of the ranks' triples (rank 0 replays)
+    import numpy as np
+    from oracle import bpr_oracle as O
+    nu_s, ni_s = 4000, 1200
+    ulo_s, uhi_s = shard_range(nu_s, world, rank)
+    trs, _ = synthetic.make_interactions(uhi_s - ulo_s, ni_s, seed=40 + rank, device=dev)
+    ts = UserShardedBPR(nu_s, ni_s, d, trs, rank, world, dev, lr=3.0, reg=0.01, init_std=0.1, seed=13)
+    U_init, V_init = ts.U.cpu().numpy()[:, :d], ts.V.cpu().numpy()[:, :d]
+    rec = []
+    for s in range(4):
+        users = torch.randperm(uhi_s - ulo_s, device=dev, generator=g)[:1024].to(torch.int32)
+        op, on = torch.empty_like(users), torch.empty_like(users)
+        ts.step_overlapped(users, 300 + s, 1024 * world, out_pos=op, out_neg=on)
+        rec.append((users.cpu().numpy() + ulo_s, op.cpu().numpy(), on.cpu().numpy()))
+    ts.flush(); torch.cuda.synchronize()
+    allr = [None] * world
+    dist.all_gather_object(allr, (rec, U_init, ts.U.cpu().numpy()[:, :d], ts.V.cpu().numpy()[:, :d]))
+    if rank == 0:
+        batches = [tuple(np.concatenate([allr[r][0][s][k] for r in range(world)]) for k in range(3)) for s in range(4)]
+        Ur, Vr = O.sgd_steps_stale_items(np.concatenate([a[1] for a in allr]), V_init, batches, 3.0, 0.01)
+        np.testing.assert_allclose(np.concatenate([a[2] for a in allr]), Ur, rtol=2e-5, atol=2e-6)
+        for a in allr:
+            np.testing.assert_allclose(a[3], Vr, rtol=2e-5, atol=2e-6)
     # "update in place, exchange the difference": same SGD sums as the delta-buffer schedule up to fp32 rounding
     ta = UserShardedBPR(nu, ni, d, trl, rank, world, dev, lr=1.0, reg=0.001, init_std=0.1, seed=9)
     tb = UserShardedBPR(nu, ni, d, trl, rank, world, dev, lr=1.0, reg=0.001, init_std=0.1, seed=9)

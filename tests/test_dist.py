@@ -194,6 +194,35 @@ def test_step_diff_world1_equals_delta_buffer_step(dev):
 
 
 @pytest.mark.gpu
+def test_step_overlapped_matches_one_step_stale_oracle(dev):
+    """The schedule the round-1 scaling run timed (item delta all-reduced on a side stream, applied one step late)
+    against its own numpy oracle (oracle/bpr_oracle.py::sgd_steps_stale_items), fixed triples read back via out_pos /
+    out_neg; rtol 2e-5.  (2 ranks over NCCL: tests/dist_worker.py does the same comparison on the union of triples.)"""
+    from recsys_pytorch_b200.dist import UserShardedBPR
+    rng = np.random.default_rng(21)
+    nu, ni, d, B = 3000, 700, 128, 1024
+    _, csr = _csr(rng, nu, ni, 2, 20, dev)
+    m = UserShardedBPR(nu, ni, d, csr, 0, 1, dev, lr=3.0, reg=0.01, init_std=0.1, seed=4)
+    U0, V0 = m.U.cpu().numpy()[:, :d], m.V.cpu().numpy()[:, :d]
+    batches = []
+    for s in range(5):
+        users = torch.from_numpy(rng.permutation(nu)[:B].astype(np.int32)).to(dev)
+        op, on = torch.empty_like(users), torch.empty_like(users)
+        m.step_overlapped(users, s + 1, B, out_pos=op, out_neg=on)
+        batches.append((users.cpu().numpy(), op.cpu().numpy(), on.cpu().numpy()))
+    m.flush()
+    torch.cuda.synchronize()
+    Ur, Vr = O.sgd_steps_stale_items(U0, V0, batches, 3.0, 0.01)
+    np.testing.assert_allclose(m.U.cpu().numpy()[:, :d], Ur, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m.V.cpu().numpy()[:, :d], Vr, rtol=2e-5, atol=2e-6)
+    # and it is NOT the synchronous trajectory: the staleness is real and measurable
+    Us, Vs = U0, V0
+    for b in batches:
+        Us, Vs, _ = O.sgd_step(Us, Vs, *b, 3.0, 0.01)
+    assert np.abs(Vs - Vr).max() > 1e-4
+
+
+@pytest.mark.gpu
 def test_sharded_evaluation_matches_evaluator(dev):
     """SURVEY 8(e) scoring: users are independent units - the per-shard metric sums add up to the Evaluator's means."""
     from recsys_pytorch_b200 import engine

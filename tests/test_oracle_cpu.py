@@ -265,3 +265,34 @@ def test_pointwise_generator_mirror_reproduces_reference_batches(golden):
     np.testing.assert_array_equal(np.concatenate(bu), g["gen_users"])
     np.testing.assert_array_equal(np.concatenate(bi), g["gen_items"])
     np.testing.assert_array_equal(np.concatenate(br).astype(np.float32), g["gen_ratings"])
+
+
+def test_stale_item_oracle_reduces_to_sgd_step_and_lags_one_step():
+    """oracle/bpr_oracle.py::sgd_steps_stale_items (the overlapped multi-GPU schedule): one batch == sgd_step; with two
+    batches the second step's gradients see U_1 but still V_0."""
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal((30, 8)).astype(np.float32); V = rng.standard_normal((20, 8)).astype(np.float32)
+    b1 = (rng.permutation(30)[:10], rng.integers(0, 20, 10), rng.integers(0, 20, 10))
+    b2 = (rng.permutation(30)[:10], rng.integers(0, 20, 10), rng.integers(0, 20, 10))
+    a = O.sgd_steps_stale_items(U, V, [b1], 0.5, 0.01); c = O.sgd_step(U, V, *b1, 0.5, 0.01)
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+    U2, V2 = O.sgd_steps_stale_items(U, V, [b1, b2], 0.5, 0.01)
+    dU2, dV2, _, _ = O.bpr_grads(c[0], V, *b2, 0.01)                 # gradients of step 2 at (U_1, V_0)
+    dU1, dV1, _, _ = O.bpr_grads(U, V, *b1, 0.01)
+    np.testing.assert_allclose(U2, c[0] - np.float32(0.5) * dU2, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(V2, V - np.float32(0.5) * dV1 - np.float32(0.5) * dV2, rtol=1e-6, atol=1e-6)
+
+
+def test_vectorised_sampler_mirror_equals_scalar_mirror():
+    rng = np.random.default_rng(4)
+    nu, ni = 300, 90
+    rows = [np.sort(rng.choice(ni, rng.integers(1, 70), replace=False)).astype(np.int32) for _ in range(nu)]
+    rows[7] = np.arange(ni, dtype=np.int32)                          # a user who has everything: neg = -1
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.concatenate(rows)
+    users = rng.permutation(nu)[:200]
+    users[3] = 7
+    p, n = O.sample_triples_vec(11, 5, users, indptr, indices, ni)
+    for t, u in enumerate(users):
+        assert (int(p[t]), int(n[t])) == O.sample_triple(11, 5, t, int(u), indptr, indices, ni)
+    assert n[3] == -1
