@@ -285,17 +285,24 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (fused BPR step): algorithmic bytes = 24d+8 per triple ----
     bytes_per_triple = 24 * d + 8
     achieved = bytes_per_triple * B / (ms_per_step * 1e-3) / 1e9
-    traffic = None
+    # roofline.traffic: DRAM bytes of ONE launch from the committed `ncu --set full` capture - valid only for the kernel
+    # that capture profiled, so it is tied to the kernel this run actually dispatched to
+    traffic, traffic_note = None, None
+    ran = _lib.last_step_kernel()
     prof = os.path.join(ROOT, "profiles", "bpr_step_dram_bytes.json")
     if os.path.exists(prof):
-        try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+        pj = json.load(open(prof))
+        if pj.get("kernel") == ran:
+            traffic, traffic_note = pj.get("dram_bytes_per_launch"), pj.get("source")
+        else:
+            traffic_note = "no capture of %s committed (profiles/bpr_step_dram_bytes.json is for %s)" % (ran, pj.get("kernel"))
+            if args.gather == "ldg" and not os.environ.get("B200REC_STEP_VARIANT"):
+                raise SystemExit("bench.py: " + traffic_note + " - re-capture the default kernel with ncu and update the file")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                "traffic": traffic, "peak_source": peak_src, "bytes_per_triple": bytes_per_triple,
-                "kernel": {"ldg": "bpr_step_fast_kernel<1,uniq,loss>", "async": "bpr_step_async_kernel<1,uniq,loss,8>",
-                           "tma": "bpr_step_tma_kernel<32,1,UPDATE>", "generic": "bpr_step_ldg_kernel<32,1,UPDATE>"}[args.gather]}
+                "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                "bytes_per_triple": bytes_per_triple, "kernel": ran,
+                "note": "the step is bound by the SM<->L2 fabric (3.04 GB of sectors per launch = the algorithmic bytes; "
+                        "~7.8 TB/s), not by HBM: the item rows hit L2, DRAM sees `traffic` (profiles/r02_bpr_ablation.md)"}
 
     cpu_base = None
     if not args.no_cpu:

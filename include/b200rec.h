@@ -88,6 +88,10 @@ int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int3
 #define B200REC_F_ASYNC_GATHER 16 /* fast path with the deep cp.async (LDGSTS) per-warp row ring */
 #define B200REC_F_ITEM_DELTA_BF16 32 /* with F_ITEM_DELTA: gV is a bf16 [num_items, ld] buffer (REDG.ADD.BF16x4) */
 #define B200REC_F_L2_HINTS 64    /* fast path: user rows evict-first, item rows / item deltas evict-last in L2 */
+/* b200rec_p2p_step only */
+#define B200REC_F_P2P_SEQUENTIAL 256 /* visit the source ranks one after the other instead of round-robin by chunk   */
+#define B200REC_F_P2P_NO_UWRITE 512  /* measurement only: do not write the user row back (results are then wrong)    */
+#define B200REC_F_P2P_NO_UREAD 1024  /* measurement only: do not read the user row (a constant is used instead)      */
 
 typedef struct b200rec_bpr_args {
     float *U;              /* [num_users, ld]  user_embedding.weight (models/MF.py:23)   */
@@ -124,6 +128,9 @@ typedef struct b200rec_bpr_args {
  * updates (Hogwild inside a step); SINK_STAGE + b200rec_bpr_apply reproduces
  * autograd's "all gradients from pre-step weights" semantics exactly. */
 int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream);
+/* diagnostics: which kernel the last b200rec_bpr_step of this process dispatched to, e.g.
+ * "bpr_step_group_kernel<8,32,0,1,1,0>" (G, float4 per row, prefetch sets, users-unique, loss, item-delta) */
+const char *b200rec_last_step_kernel(void);
 
 /* Pointwise MF step (models/MF.py:63-68 with the pointwise branch MF.py:101-102):
  *   x_b = U[users[b]] . V[items[b]];  loss_kind 0: F.binary_cross_entropy_with_logits(x, ratings) ('ce', MF.py:21),

@@ -82,6 +82,7 @@ _PROTOS = {
     "b200rec_last_error": (C.c_char_p, []),
     "b200rec_version": (_I, []),
     "b200rec_launch_count": (_L, []),
+    "b200rec_last_step_kernel": (C.c_char_p, []),
     "b200rec_top_k_array_index": (_I, [_P, _I, _I, _I, _P]),
     "b200rec_evaluate_holdout": (_I, [_I, _P, _I, _P, _I, _P, _P, _P]),
     "b200rec_evaluate_loo": (_I, [_I, _P, _I, _P, _I, _P, _P]),
@@ -169,6 +170,10 @@ def require_cuda(t, name, dtype=None):
     if not t.is_contiguous():
         raise B200RecError(EINVAL, f"{name} must be contiguous")
     return t
+
+
+def last_step_kernel() -> str:
+    return lib().b200rec_last_step_kernel().decode()
 
 
 def launch_count() -> int:

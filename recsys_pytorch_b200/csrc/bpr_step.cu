@@ -851,6 +851,12 @@ static int launch_bpr(BprParams &p, cudaStream_t s) {
 
 using namespace b200;
 
+// name of the kernel the last b200rec_bpr_step of this process dispatched to (bench.py ties its roofline.traffic figure,
+// an ncu capture of ONE named kernel, to what actually ran)
+static char g_last_step_kernel[96] = "";
+extern "C" const char *b200rec_last_step_kernel(void) { return g_last_step_kernel; }
+#define B200_NOTE_KERNEL(...) snprintf(g_last_step_kernel, sizeof(g_last_step_kernel), __VA_ARGS__)
+
 extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
     B200_REQUIRE(args != nullptr, B200REC_EINVAL, "bpr_step: args is NULL");
     const b200rec_bpr_args &a = *args;
@@ -917,6 +923,7 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
                 else { if (loss) B200_ASYNC(2, false, true, 4) else B200_ASYNC(2, false, false, 4) }
             }
 #undef B200_ASYNC
+            B200_NOTE_KERNEL("bpr_step_async_kernel<%d,%d,%d>", CPL, (int)uniq, (int)loss);
             B200_LAUNCH_CHECK();
             return B200REC_OK;
         }
@@ -965,6 +972,7 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
         else { if (loss) { if (idelta) rc_g = launch(bpr_step_group_kernel<GG, 32, PP, false, true, true>); else rc_g = launch(bpr_step_group_kernel<GG, 32, PP, false, true, false>); } \
                else { if (idelta) rc_g = launch(bpr_step_group_kernel<GG, 32, PP, false, false, true>); else rc_g = launch(bpr_step_group_kernel<GG, 32, PP, false, false, false>); } } \
         if (rc_g) return rc_g;                                                                               \
+        B200_NOTE_KERNEL("bpr_step_group_kernel<%d,32,%d,%d,%d,%d>", GG, PP, (int)uniq, (int)loss, (int)idelta); \
         B200_LAUNCH_CHECK();                                                                                 \
         return B200REC_OK;                                                                                   \
     }
@@ -988,9 +996,12 @@ extern "C" int b200rec_bpr_step(const b200rec_bpr_args *args, void *stream) {
             else { if (loss) B200_FAST(2, false, true) else B200_FAST(2, false, false) }
         }
 #undef B200_FAST
+        B200_NOTE_KERNEL("bpr_step_fast_kernel<%d,%d,%d,%d>", CPL, (int)uniq, (int)loss, (int)idelta);
         B200_LAUNCH_CHECK();
         return B200REC_OK;
     }
+    B200_NOTE_KERNEL("%s<%d,%d,sink%d>", (a.flags & B200REC_F_TMA_GATHER) ? "bpr_step_tma_kernel" : "bpr_step_ldg_kernel", G, CPL,
+                     a.sink);
     switch (G) {
         case 1: return launch_bpr<1, 1>(p, s);
         case 2: return launch_bpr<2, 1>(p, s);

@@ -12,22 +12,41 @@
 namespace b200 {
 
 constexpr int kMaxK = 1024;
-__constant__ double c_inv_log2[kMaxK + 2];  // [i] = 1.0 / log2(i + 2)
-__constant__ int c_Ks[64];
+__constant__ double c_inv_log2[kMaxK + 2];  // [i] = 1.0 / log2(i + 2); per DEVICE (constant memory is), uploaded once each
 
-static int upload_tables(int max_k, const int *Ks, int K_len, cudaStream_t s) {
-    static thread_local int uploaded_k = 0;
-    if (uploaded_k < max_k + 1) {
-        std::vector<double> t(kMaxK + 2);
-        for (int i = 0; i < kMaxK + 2; ++i) t[i] = 1.0 / log2((double)(i + 2));
-        B200_CUDA(cudaMemcpyToSymbolAsync(c_inv_log2, t.data(), sizeof(double) * (kMaxK + 2), 0,
-                                          cudaMemcpyHostToDevice, s));
-        B200_CUDA(cudaStreamSynchronize(s));  // t is a stack temporary
-        uploaded_k = kMaxK + 1;
+struct KsArg {      // the cut-offs travel as a kernel argument: no shared constant buffer that a later call on another
+    int n;          // stream could overwrite while an earlier kernel still reads it
+    int v[64];
+};
+
+// discount table: computed once on the host with the same libm call the reference uses (holdout.h:47, loo.h:51), kept in
+// static storage so the asynchronous upload needs no synchronisation, uploaded once per device
+static int upload_tables(int max_k, cudaStream_t s) {
+    static double table[kMaxK + 2];
+    static bool table_ready = false;
+    static bool uploaded[64] = {false};
+    (void)max_k;
+    if (!table_ready) {
+        for (int i = 0; i < kMaxK + 2; ++i) table[i] = 1.0 / log2((double)(i + 2));
+        table_ready = true;
     }
-    B200_CUDA(cudaMemcpyToSymbolAsync(c_Ks, Ks, sizeof(int) * K_len, 0, cudaMemcpyHostToDevice, s));
-    B200_CUDA(cudaStreamSynchronize(s));
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_REQUIRE(dev >= 0 && dev < 64, B200REC_EINVAL, "metrics: device index %d", dev);
+    if (!uploaded[dev]) {
+        B200_CUDA(cudaMemcpyToSymbolAsync(c_inv_log2, table, sizeof(double) * (kMaxK + 2), 0, cudaMemcpyHostToDevice, s));
+        // later calls may use OTHER streams: make the table visible device-wide before anyone reads it (once per device)
+        B200_CUDA(cudaStreamSynchronize(s));
+        uploaded[dev] = true;
+    }
     return B200REC_OK;
+}
+
+static KsArg make_ks(const int *Ks, int K_len) {
+    KsArg k;
+    k.n = K_len;
+    for (int j = 0; j < 64; ++j) k.v[j] = j < K_len ? Ks[j] : 0;
+    return k;
 }
 
 __device__ __forceinline__ bool in_truth(const int32_t *truth, int n, int v) {
@@ -40,10 +59,11 @@ __device__ __forceinline__ bool in_truth(const int32_t *truth, int n, int v) {
 __global__ void __launch_bounds__(128) holdout_kernel(const int32_t *__restrict__ topk, int n, int max_k,
                                                       const int32_t *__restrict__ row_ids,
                                                       const int64_t *__restrict__ tptr,
-                                                      const int32_t *__restrict__ tidx, int K_len,
+                                                      const int32_t *__restrict__ tidx, const KsArg ks,
                                                       float *__restrict__ out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
+    const int K_len = ks.n;
     const int64_t row = row_ids ? row_ids[r] : r;
     const int32_t *truth = tidx + tptr[row];
     const int truth_len = (int)(tptr[row + 1] - tptr[row]);
@@ -57,8 +77,8 @@ __global__ void __launch_bounds__(128) holdout_kernel(const int32_t *__restrict_
         }
         if (i < truth_len) iDCG = (float)((double)iDCG + c_inv_log2[i]);
         for (int j = 0; j < K_len; ++j)
-            if (c_Ks[j] == i + 1) {
-                res[j] = hits / (float)c_Ks[j];
+            if (ks.v[j] == i + 1) {
+                res[j] = hits / (float)ks.v[j];
                 res[K_len + j] = hits / (float)truth_len;
                 res[2 * K_len + j] = DCG / iDCG;
             }
@@ -69,10 +89,11 @@ __global__ void __launch_bounds__(128) holdout_kernel(const int32_t *__restrict_
 __global__ void __launch_bounds__(128) loo_kernel(const int32_t *__restrict__ topk, int n, int max_k,
                                                   const int32_t *__restrict__ row_ids,
                                                   const int64_t *__restrict__ tptr,
-                                                  const int32_t *__restrict__ tidx, int K_len,
+                                                  const int32_t *__restrict__ tidx, const KsArg ks,
                                                   float *__restrict__ out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
+    const int K_len = ks.n;
     const int64_t row = row_ids ? row_ids[r] : r;
     const int32_t truth = tidx[tptr[row]];
     const int32_t *cur = topk + (int64_t)r * max_k;
@@ -81,7 +102,7 @@ __global__ void __launch_bounds__(128) loo_kernel(const int32_t *__restrict__ to
     for (int i = 0; i < max_k; ++i)
         if (cur[i] == truth) { hit_at_k = i + 1; break; }
     for (int j = 0; j < K_len; ++j) {
-        if (c_Ks[j] >= hit_at_k) {
+        if (ks.v[j] >= hit_at_k) {
             res[j] = 1.0f;
             res[K_len + j] = (float)c_inv_log2[hit_at_k - 1];  // 1 / log2(hit_at_k + 1)
         } else {
@@ -129,10 +150,11 @@ extern "C" int b200rec_holdout_metrics(const int32_t *topk, int n, int max_k, co
     if (rc) return rc;
     if (n == 0) return B200REC_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    rc = upload_tables(max_k, Ks, K_len, s);
+    rc = upload_tables(max_k, s);
     if (rc) return rc;
     B200_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * 3 * K_len, s));  // np.zeros (holdout_func.pyx:37)
-    holdout_kernel<<<(n + 127) / 128, 128, 0, s>>>(topk, n, max_k, row_ids, truth_indptr, truth_indices, K_len, out);
+    holdout_kernel<<<(n + 127) / 128, 128, 0, s>>>(topk, n, max_k, row_ids, truth_indptr, truth_indices,
+                                                   make_ks(Ks, K_len), out);
     B200_LAUNCH_CHECK();
     return B200REC_OK;
 }
@@ -144,9 +166,10 @@ extern "C" int b200rec_loo_metrics(const int32_t *topk, int n, int max_k, const 
     if (rc) return rc;
     if (n == 0) return B200REC_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    rc = upload_tables(max_k, Ks, K_len, s);
+    rc = upload_tables(max_k, s);
     if (rc) return rc;
-    loo_kernel<<<(n + 127) / 128, 128, 0, s>>>(topk, n, max_k, row_ids, truth_indptr, truth_indices, K_len, out);
+    loo_kernel<<<(n + 127) / 128, 128, 0, s>>>(topk, n, max_k, row_ids, truth_indptr, truth_indices, make_ks(Ks, K_len),
+                                               out);
     B200_LAUNCH_CHECK();
     return B200REC_OK;
 }
@@ -156,6 +179,8 @@ extern "C" int b200rec_column_means(const float *mat, int64_t n, int cols, doubl
     cudaStream_t s = (cudaStream_t)stream;
     // per-device scratch kept for the life of the process: a cudaMallocAsync/cudaFreeAsync pair here costs ~1 ms to
     // map and ~2 ms to trim at the caller's next device synchronisation (measured), for 32 KB
+    // (the call ends with a synchronisation of `s`, and one host thread drives a device: the buffer is free again when
+    // the next call on any stream of this device starts)
     static double *scratch[64] = {nullptr};
     int dev = 0;
     B200_CUDA(cudaGetDevice(&dev));

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
         // trips of the remote ones), then the leftovers source by source
         int mn = 0x7fffffff;
         for (int k = 0; k < W; ++k) mn = min(mn, (s_cnt[k] + 31) >> 5);
+        if (a.flags & B200REC_F_P2P_SEQUENTIAL) mn = 0;
         s_rr = mn;
         int acc = mn * W;
         for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += ((s_cnt[k] + 31) >> 5) - mn; }
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
 template <int G, bool UNIQ, bool LOSS>
 __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_constant__ P2PParams p) {
     constexpr int F4 = 32, CPL = F4 / G, TPW = 32 / G, ITERS = 32 / TPW, LD = F4 * 4;
+    const bool no_uwrite = (p.a.flags & B200REC_F_P2P_NO_UWRITE) != 0, no_uread = (p.a.flags & B200REC_F_P2P_NO_UREAD) != 0;
     __shared__ int s_cnt[B200REC_MAX_RANKS];
     __shared__ int s_pref[B200REC_MAX_RANKS + 1];
     __shared__ int s_src[B200REC_MAX_RANKS];
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_consta
         // trips of the remote ones), then the leftovers source by source
         int mn = 0x7fffffff;
         for (int k = 0; k < W; ++k) mn = min(mn, (s_cnt[k] + 31) >> 5);
+        if (a.flags & B200REC_F_P2P_SEQUENTIAL) mn = 0;
         s_rr = mn;
         int acc = mn * W;
         for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += ((s_cnt[k] + 31) >> 5) - mn; }
@@ -337,8 +340,13 @@ __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_consta
                 const float *pu = Uhome + (int64_t)tu * LD + sl * 4;
                 const float *pi = vptr(ti, false) + sl * 4;
                 const float *pj = vptr(tj, false) + sl * 4;
+                if (no_uread) {
 #pragma unroll
-                for (int q = 0; q < CPL; ++q) ru[q] = ld4(pu + q * G * 4);
+                    for (int q = 0; q < CPL; ++q) ru[q] = make_float4(0.01f, 0.01f, 0.01f, 0.01f);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) ru[q] = ld4(pu + q * G * 4);
+                }
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) ri[q] = ld4(pi + q * G * 4);
 #pragma unroll
@@ -369,8 +377,10 @@ __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_consta
                     di.z = fmaf(a1, vu.z, c_r * vi.z); di.w = fmaf(a1, vu.w, c_r * vi.w);
                     dj.x = fmaf(-a1, vu.x, c_r * vj.x); dj.y = fmaf(-a1, vu.y, c_r * vj.y);
                     dj.z = fmaf(-a1, vu.z, c_r * vj.z); dj.w = fmaf(-a1, vu.w, c_r * vj.w);
-                    if (UNIQ) st4(pu + q * G * 4, make_float4(vu.x + du.x, vu.y + du.y, vu.z + du.z, vu.w + du.w));
-                    else red4(pu + q * G * 4, du);
+                    if (!no_uwrite) {
+                        if (UNIQ) st4(pu + q * G * 4, make_float4(vu.x + du.x, vu.y + du.y, vu.z + du.z, vu.w + du.w));
+                        else red4(pu + q * G * 4, du);
+                    }
                     red4(pi + q * G * 4, di);
                     red4(pj + q * G * 4, dj);
                 }

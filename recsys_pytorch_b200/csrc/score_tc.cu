@@ -784,6 +784,13 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
             topk_list_offer(rk, k, key, ok, lane);
         }
         __syncwarp();
+        // fewer than k unmasked candidates survived (tiny catalogue, a user who has nearly everything): the list still
+        // ends in the sentinel - the exact kernel, which ranks the masked -inf items in id order, finishes this row
+        if (key_id(rk[k - 1]) == 0x7FFFFFFF) {
+            if (lane == 0) redo_rows[atomicAdd(redo_count, 1)] = row;
+            __syncwarp();
+            continue;
+        }
         for (int pp = lane; pp < k; pp += 32) {
             out_idx[(int64_t)row * k + pp] = key_id(rk[pp]);
             if (out_score) out_score[(int64_t)row * k + pp] = key_score(rk[pp]);
@@ -863,6 +870,13 @@ __global__ void __launch_bounds__(256) rerank_staged_kernel(const float *__restr
             __syncwarp();
         }
         __syncwarp();
+        // fewer than k unmasked candidates survived (tiny catalogue, a user who has nearly everything): the list still
+        // ends in the sentinel - the exact kernel, which ranks the masked -inf items in id order, finishes this row
+        if (key_id(rk[k - 1]) == 0x7FFFFFFF) {
+            if (lane == 0) redo_rows[atomicAdd(redo_count, 1)] = row;
+            __syncwarp();
+            continue;
+        }
         for (int pp = lane; pp < k; pp += 32) {
             out_idx[(int64_t)row * k + pp] = key_id(rk[pp]);
             if (out_score) out_score[(int64_t)row * k + pp] = key_score(rk[pp]);

@@ -89,15 +89,24 @@ class LightGCN(MF):
         self._tmp = [torch.zeros_like(self.E0), torch.zeros_like(self.E0)]
         self.gOut = torch.zeros_like(self.E0)
         self.gE0 = torch.zeros_like(self.E0)
-        self.user_embedding = _View(self.E0, 0, self.num_users, d)
-        self.item_embedding = _View(self.E0, self.num_users, N, d)
-        self.Graph = None
+        self.user_embedding = _View(self.E0, 0, self.num_users, d, self)
+        self.item_embedding = _View(self.E0, self.num_users, N, d, self)
+        self._graph = None
         self._adam = None
         self._csr_cache = {}
         self._prop_fresh = False
         self.global_step = 0
 
     # ---- graph / propagation ----------------------------------------- #
+    @property
+    def Graph(self):
+        return self._graph
+
+    @Graph.setter
+    def Graph(self, g):                                               # a new graph invalidates the propagated tables
+        self._graph = g
+        self._prop_fresh = False
+
     def getSparseGraph(self, rating_matrix):                         # LightGCN.py:228-267
         csr = rating_matrix if isinstance(rating_matrix, engine.DeviceCSR) else \
             engine.DeviceCSR.from_scipy(rating_matrix, self.device)
@@ -105,7 +114,10 @@ class LightGCN(MF):
 
     def propagate(self, src, dst):
         """dst = mean_{l=0..L} A_hat^l src  (LightGCN.py:174-202).  2L reads/writes of an [N, ld] table."""
-        indptr, cols, vals = self.Graph
+        if self._graph is None:
+            raise RuntimeError("LightGCN: no graph yet - call fit(), or set model.Graph = model.getSparseGraph(train) "
+                               "before propagating / predicting (models/LightGCN.py:38-40 builds it in fit too)")
+        indptr, cols, vals = self._graph
         if getattr(self, "_plan_for", None) is not indptr:          # long rows (popular items) are split: plan per graph
             self._plan, self._plan_for = engine.spmm_plan(indptr), indptr
         L, d = self.num_layers, self.emb_dim
@@ -192,9 +204,10 @@ class LightGCN(MF):
 class _View:
     """`.weight` view of rows [lo,hi) of the joint table (user_embedding / item_embedding of LightGCN.py:48-49)."""
 
-    def __init__(self, store, lo, hi, d):
+    def __init__(self, store, lo, hi, d, owner=None):
         self.store = store[lo:hi]
         self.embedding_dim = d
+        self._owner = owner
 
     @property
     def weight(self):
@@ -204,3 +217,5 @@ class _View:
         with torch.no_grad():
             self.store.zero_()
             self.store[:, :self.embedding_dim].copy_(torch.as_tensor(w, dtype=torch.float32))
+        if self._owner is not None:                                   # E_0 changed: the propagated tables are stale
+            self._owner._prop_fresh = False

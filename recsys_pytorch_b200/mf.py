@@ -7,11 +7,17 @@ Mirrors `models/BaseModel.py:3-14` and `models/MF.py:13-132` (constructor
 the path is a hand-written sm_100a kernel reached through the C ABI
 (include/b200rec.h).  There is no PyTorch / CPU fallback: a CPU device raises.
 
-Extra hparams (all optional; defaults keep `conf/MF.yaml` working):
-    optimizer   'sgd' (default: L2-regularised SGD, BASELINE north_star) |
-                'adam' (the reference's dense torch.optim.Adam(lr=1e-3), MF.py:30) |
+Extra hparams (all optional).  With `conf/MF.yaml` as it is (hidden_dim, pointwise, loss_func only) the model trains
+exactly like the reference: dense Adam(lr=1e-3) on N(0,1) tables - including the reference's slow start (NDCG@10 stays
+near 0.014 on ml-100k for hundreds of epochs at batch 256, one triple per user and epoch; CPU simulation with
+oracle/bpr_oracle.py).  The throughput path is opt-in:
+    optimizer   'adam' (default = the reference's dense torch.optim.Adam(lr=1e-3), MF.py:30) |
+                'sgd' (L2-regularised SGD, the fused one-kernel step of BASELINE north_star) |
                 'lazy_adam' (row-wise Adam = torch.optim.SparseAdam semantics: only touched rows move)
-    lr, reg     SGD step size / per-occurrence L2 (reference has neither: Q1)
+    lr          step size.  For 'sgd' it multiplies the MEAN-reduced gradient (MF.py:105 `.mean()`), so one triple moves
+                its rows by lr / batch_size; `lr_per_triple` sets that per-triple step directly (lr = lr_per_triple x
+                batch_size at fit time; 0.05-0.1 is a sensible value, what bench.py uses)
+    reg         per-occurrence L2 (the reference has none: Q1)
     step        'fused' (ONE kernel per batch, Hogwild inside a step) |
                 'exact' (stage + apply: autograd's pre-step-weights semantics)
     sampler     'device' (default) | 'reference' (generators.py:168-224 call for call)
@@ -98,15 +104,15 @@ class MF(BaseModel):
         self.num_users = dataset.num_users
         self.num_items = dataset.num_items
         self.hidden_dim = int(hparams["hidden_dim"])
-        self.pointwise = bool(_hp(hparams, "pointwise", False))
-        if self.pointwise:
-            raise NotImplementedError("pointwise MF (models/MF.py:49-52,101-102) is outside the BPR hot path")
+        self.pointwise = bool(_hp(hparams, "pointwise", False))          # MF.py:19
+        self.loss_func_name = str(_hp(hparams, "loss_func", "ce")).lower()   # MF.py:21: 'ce' -> BCE-with-logits, else MSE
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise B200RecError(ECUDA, "recsys_pytorch_b200.MF needs a CUDA device: there is no CPU path")
 
-        self.optimizer_name = str(_hp(hparams, "optimizer", "sgd")).lower()
+        self.optimizer_name = str(_hp(hparams, "optimizer", "adam")).lower()
         self.lr = float(_hp(hparams, "lr", 1e-3 if "adam" in self.optimizer_name else 0.05))
+        self.lr_per_triple = _hp(hparams, "lr_per_triple", None)
         self.reg = float(_hp(hparams, "reg", 0.0))
         self.step_mode = str(_hp(hparams, "step", "fused")).lower()
         self.sampler = str(_hp(hparams, "sampler", "device")).lower()
@@ -152,7 +158,14 @@ class MF(BaseModel):
         return engine.mf_forward(self.U, self.V, self.hidden_dim, self._i32(user_ids, self.device),
                                  self._i32(item_ids, self.device))
 
-    def process_one_batch(self, users, items, ratings):            # MF.py:99-107 (pairwise branch), forward only
+    def process_one_batch(self, users, items, ratings):            # MF.py:99-107, forward only
+        if self.pointwise:                                           # :101-102  loss_func(pos_ratings, ratings)
+            users, items = self._i32(users, self.device), self._i32(items, self.device)
+            r = torch.as_tensor(ratings, dtype=torch.float32).to(self.device).contiguous()
+            loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+            engine.pointwise_step(self.U, self.V, self.hidden_dim, users, items, r, loss_func=self.loss_func_name,
+                                  sink=SINK_NONE, loss_sum=loss)
+            return (loss / users.numel()).to(torch.float32)[0]
         users, items, neg = (self._i32(t, self.device) for t in (users, items, ratings))
         loss = torch.zeros(1, dtype=torch.float64, device=self.device)
         engine.bpr_step(self.U, self.V, self.hidden_dim, users, items, neg, sink=SINK_NONE, loss_sum=loss)
@@ -214,6 +227,31 @@ class MF(BaseModel):
             engine.bpr_step(self.U, self.V, d, users, pos, neg, csr=csr, lr=self.lr, reg=self.reg, sink=SINK_UPDATE,
                             seed=self.seed, step=step_key, loss_sum=loss_slot, flags=self._flags(users_unique))
 
+    def train_batch_pointwise(self, users, items, ratings, loss_slot=None):
+        """Pointwise mode (MF.py:49-52,63-68,101-102): zero_grad -> loss_func(forward(u, i), ratings) -> backward ->
+        optimizer.step as one fused kernel (+ the dense Adam sweep for the reference's optimiser)."""
+        users, items = self._i32(users, self.device), self._i32(items, self.device)
+        r = torch.as_tensor(ratings, dtype=torch.float32).to(self.device).contiguous()
+        d = self.hidden_dim
+        self.global_step += 1
+        if self.optimizer_name == "adam":
+            gU, gV = self._grad_buffers()
+            gU.zero_(); gV.zero_()
+            engine.pointwise_step(self.U, self.V, d, users, items, r, loss_func=self.loss_func_name, reg=self.reg,
+                                  sink=SINK_GRAD, gU=gU, gV=gV, loss_sum=loss_slot)
+            if self._adam is None:
+                self._adam = [torch.zeros_like(self.U), torch.zeros_like(self.U), torch.zeros_like(self.V),
+                              torch.zeros_like(self.V), 0]
+            self._adam[4] += 1
+            t = self._adam[4]
+            engine.adam_dense(self.U, gU, self._adam[0], self._adam[1], t, lr=self.lr)
+            engine.adam_dense(self.V, gV, self._adam[2], self._adam[3], t, lr=self.lr)
+        elif self.optimizer_name == "sgd":
+            engine.pointwise_step(self.U, self.V, d, users, items, r, loss_func=self.loss_func_name, lr=self.lr,
+                                  reg=self.reg, sink=SINK_UPDATE, loss_sum=loss_slot)
+        else:
+            raise NotImplementedError("pointwise MF supports optimizer 'adam' (reference) and 'sgd'")
+
     def train_batch_async(self, users_host, csr=None, step_key=0, users_unique=False):
         """Pipelined form of `train_batch` for host-resident batches: `users_host` (pinned int32 CPU tensor) is
         copied on a side stream into one of two device buffers while the previous step still computes; the
@@ -246,6 +284,10 @@ class MF(BaseModel):
 
     def fit(self, dataset, exp_config, evaluator=None, early_stop=None, loggers=None):   # MF.py:44-97
         train_matrix = dataset.train_data
+        if self.lr_per_triple is not None and self.optimizer_name == "sgd":
+            self.lr = float(self.lr_per_triple) * int(exp_config.batch_size)
+        if self.pointwise:
+            return self._fit_pointwise(dataset, exp_config, evaluator, early_stop, loggers)
         gen = PairwiseGenerator(train_matrix, num_negatives=1, num_positives_per_user=1,
                                 batch_size=exp_config.batch_size, shuffle=True, device=self.device,
                                 sampler=self.sampler, seed=self.seed)
@@ -265,6 +307,38 @@ class MF(BaseModel):
                     self.train_batch(users, pos, neg, users_unique=gen.users_unique, loss_slot=slots[b:b + 1])
                     sizes.append(users.numel())
             # epoch_loss = sum of per-batch mean losses (MF.py:70); one D2H per epoch
+            epoch_loss = float((slots.cpu() / torch.tensor(sizes, dtype=torch.float64)).sum()) if sizes else 0.0
+            if exp_config.verbose:
+                print("epoch %3d loss = %.4f" % (epoch, epoch_loss))
+            epoch_summary = {"loss": epoch_loss}
+            if evaluator is not None and epoch >= exp_config.test_from and epoch % exp_config.test_step == 0:
+                scores = evaluator.evaluate(self)
+                epoch_summary.update(scores)
+                if loggers is not None:
+                    for logger in loggers:
+                        logger.log_metrics(epoch_summary, epoch=epoch)
+                if early_stop is not None:
+                    is_update, should_stop = early_stop.step(scores, epoch)
+                    if should_stop:
+                        break
+            elif loggers is not None:
+                for logger in loggers:
+                    logger.log_metrics(epoch_summary, epoch=epoch)
+        best_score = early_stop.best_score if early_stop is not None else scores
+        return {"scores": best_score}
+
+    def _fit_pointwise(self, dataset, exp_config, evaluator, early_stop, loggers):       # MF.py:44-97, pointwise branch
+        from .generators import PointwiseGenerator
+        gen = PointwiseGenerator(dataset.train_data, return_rating=True, num_negatives=1,
+                                 batch_size=exp_config.batch_size, shuffle=True, device=torch.device("cpu"))  # :49-52
+        scores = None
+        for epoch in range(1, exp_config.num_epochs + 1):
+            self.train()
+            slots = torch.zeros(len(gen), dtype=torch.float64, device=self.device)
+            sizes = []
+            for b, (users, items, ratings) in enumerate(gen):
+                self.train_batch_pointwise(users, items, ratings, loss_slot=slots[b:b + 1])
+                sizes.append(users.numel())
             epoch_loss = float((slots.cpu() / torch.tensor(sizes, dtype=torch.float64)).sum()) if sizes else 0.0
             if exp_config.verbose:
                 print("epoch %3d loss = %.4f" % (epoch, epoch_loss))

@@ -334,7 +334,7 @@ class P2PShardedBPR:
         assert self._step_args is not None, "call connect() first"
         a = self._step_args[self._n & 1]
         a.lr, a.reg, a.inv_batch = self.lr, self.reg, 1.0 / float(global_batch)
-        a.flags = F_USERS_UNIQUE if users_unique else 0
+        a.flags = (F_USERS_UNIQUE if users_unique else 0) | int(getattr(self, "extra_flags", 0))
         a.loss_sum = ptr(_lib.require_cuda(loss_sum, "loss_sum", torch.float64)) if loss_sum is not None else None
         a.n_processed = ptr(self.n_processed)
         if self.head:

@@ -74,7 +74,7 @@ def main():
     assert np.array_equal(full.cpu().numpy()[:, :d], Vc)
     # fixed-triple mode across shards: user on this rank, negative anywhere
     items = np.random.default_rng(7).permutation(ni)
-    B = 512
+    B = min(512, ni // (2 * world), hi - lo)
     ul = torch.from_numpy(prng.permutation(hi - lo)[:B].astype(np.int32)).to(dev)
     pi = items[rank * 2 * B: rank * 2 * B + B].astype(np.int32); pj = items[rank * 2 * B + B: (rank + 1) * 2 * B].astype(np.int32)
     m.lr, m.reg = 0.9, 0.01

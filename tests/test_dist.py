@@ -189,8 +189,14 @@ def test_step_diff_world1_equals_delta_buffer_step(dev):
         b.step_diff(users, s + 1, B)
     b.flush()
     torch.cuda.synchronize()
-    np.testing.assert_allclose(b.V.cpu().numpy(), a.V.cpu().numpy(), rtol=1e-4, atol=1e-6)
-    np.testing.assert_allclose(b.U.cpu().numpy(), a.U.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    # the delta-buffer step evaluates every gradient on the pre-step item rows, the in-place step is Hogwild inside a
+    # launch (500 items, 1024 triples: every item row collides): the two differ at second order in the step, bounded
+    # here against the distance the tables travelled (same bound as test_fused_step_with_collisions_is_close)
+    V0 = UserShardedBPR(nu, ni, d, csr, 0, 1, dev, lr=2.0, reg=0.01, init_std=0.1, seed=4).V.cpu().numpy()
+    moved = np.abs(a.V.cpu().numpy() - V0).max()
+    assert moved > 1e-3
+    assert np.abs(b.V.cpu().numpy() - a.V.cpu().numpy()).max() < 0.05 * moved
+    assert np.abs(b.U.cpu().numpy() - a.U.cpu().numpy()).max() < 0.05 * moved
 
 
 @pytest.mark.gpu

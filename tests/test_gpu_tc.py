@@ -101,6 +101,29 @@ def test_tc_heavy_mask_rows_and_ties_fall_back_to_exact(dev):
     assert torch.equal(it, ie) and torch.equal(st, se)
 
 
+def test_tc_tiny_catalogue_and_rows_with_fewer_than_k_unmasked_items(dev):
+    """a catalogue no larger than the candidate buffer, and users whose unmasked items number fewer than k
+    (the reference then returns masked -inf ids) - the tensor-core path must hand such rows to the exact
+    kernel instead of emitting the list sentinel; result identical to B200REC_SCORE_EXACT."""
+    rng = np.random.default_rng(12)
+    for (nu, ni, d, k) in ((70, 300, 64, 50), (64, 512, 128, 100), (33, 2000, 128, 100)):
+        U = engine.alloc_table(nu, d, dev, 1.0); V = engine.alloc_table(ni, d, dev, 1.0)
+        rows = []
+        for u in range(nu):
+            if u % 5 == 0:                                         # leaves only k - 3 unmasked items
+                keep = rng.choice(ni, k - 3, replace=False)
+                rows.append(np.setdiff1d(np.arange(ni), keep).astype(np.int32))
+            else:
+                rows.append(np.sort(rng.choice(ni, rng.integers(0, 40), replace=False)).astype(np.int32))
+        indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+        mask = engine.DeviceCSR(torch.from_numpy(indptr).to(dev), torch.from_numpy(np.concatenate(rows)).to(dev), (nu, ni))
+        users = torch.arange(nu, dtype=torch.int32, device=dev)
+        ie, se = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_EXACT)
+        it, st = engine.score_topk(U, V, d, users, mask, k, algo=SCORE_TC)
+        assert int(it.max()) < ni and int(it.min()) >= 0
+        assert torch.equal(it, ie) and torch.equal(st, se)
+
+
 def test_tc_large_catalogue_properties(dev):
     """BASELINE configs[1] item count (100k), top-100: sorted by (score desc, id asc), no masked item,
     identical to the exact kernel on a sample of rows."""

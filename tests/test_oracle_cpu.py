@@ -296,3 +296,24 @@ def test_vectorised_sampler_mirror_equals_scalar_mirror():
     for t, u in enumerate(users):
         assert (int(p[t]), int(n[t])) == O.sample_triple(11, 5, t, int(u), indptr, indices, ni)
     assert n[3] == -1
+
+
+def test_pointwise_oracle_replays_reference_ml100k_trajectory(golden):
+    """tests/golden/ml100k_pointwise.npz (the reference's pointwise MF + its own generator's batches, 6 dense-Adam
+    steps): the numpy restatement reproduces losses and tables."""
+    g = golden["ml100k_pointwise"]
+    for lf in ("ce", "mse"):
+        U, V = g[f"{lf}_U0"].copy(), g[f"{lf}_V0"].copy()
+        opt = O.DenseAdam([U.shape, V.shape], lr=1e-3)
+        off = 0
+        for s_, n in enumerate(g[f"{lf}_lens"]):
+            u, i, r = g[f"{lf}_users"][off:off + n], g[f"{lf}_items"][off:off + n], g[f"{lf}_ratings"][off:off + n]
+            off += n
+            loss = O.pointwise_loss(U, V, u, i, r, lf)
+            loss = loss[0] if isinstance(loss, tuple) else loss
+            assert abs(float(loss) - float(g[f"{lf}_losses"][s_])) < 2e-5 * max(1.0, float(g[f"{lf}_losses"][s_]))
+            dU, dV, _, _ = O.pointwise_grads(U, V, u, i, r, lf)
+            U, V = opt.step([U, V], [dU, dV])
+        for got, ref in ((U, g[f"{lf}_U"]), (V, g[f"{lf}_V"])):
+            bad = ~np.isclose(got, ref, rtol=2e-4, atol=2e-5)
+            assert bad.mean() < 0.01 and np.abs(got - ref).max() < 7 * 1e-3
