@@ -89,7 +89,8 @@ int b200rec_mf_forward(const float *U, const float *V, int ld, int d, const int3
 #define B200REC_F_ITEM_DELTA_BF16 32 /* with F_ITEM_DELTA: gV is a bf16 [num_items, ld] buffer (REDG.ADD.BF16x4) */
 #define B200REC_F_L2_HINTS 64    /* fast path: user rows evict-first, item rows / item deltas evict-last in L2 */
 /* b200rec_p2p_step only */
-#define B200REC_F_P2P_SEQUENTIAL 256 /* visit the source ranks one after the other instead of round-robin by chunk   */
+#define B200REC_F_P2P_ROUND_ROBIN 256 /* measurement only: visit ALL source ranks round-robin by chunk (slow beyond 2 ranks) */
+#define B200REC_F_P2P_PURE_SEQUENTIAL 2048 /* measurement only: no local chunks interleaved with the remote stream        */
 #define B200REC_F_P2P_NO_UWRITE 512  /* measurement only: do not write the user row back (results are then wrong)    */
 #define B200REC_F_P2P_NO_UREAD 1024  /* measurement only: do not read the user row (a constant is used instead)      */
 

@@ -97,6 +97,41 @@ __global__ void __launch_bounds__(kRouteThreads) p2p_route_kernel(const b200rec_
 // ---------------------------------------------------------------------------------------------------------------
 // fused step over the triples routed to this rank
 // ---------------------------------------------------------------------------------------------------------------
+// Work order.  The dynamic chunk counter c walks the remote homes ONE AFTER THE OTHER (me+1, me+2, ...) and slips one
+// chunk of this rank's own (NVLink-free) triples in after every W-1 remote chunks, so local HBM/L2 work overlaps the
+// NVLink round trips.  Measured (profiles/r02_p2p_notes.md): visiting ALL homes round-robin by chunk is fine with one
+// peer (N=2: 0.78 vs 0.94 ms) but collapses with three or seven (N=4: 4.99 vs 1.78 ms, N=8: 10 ms) - whatever the
+// cause (peer-aperture translation is the suspect), a rank must stream from one peer at a time.
+// pref[k] = first chunk of source slot k in plain sequential order (slot W-1 = local), m = interleaved local chunks.
+__device__ __forceinline__ void chunk_of(int c, int W, int m, const int *pref, bool round_robin, int &k, int &off) {
+    if (round_robin) {                                   // measurement mode: every source by turns while all have chunks
+        if (c < m * W) { k = c % W; off = (c / W) << 5; return; }
+        int c2 = c - m * W, kk = 0;                      // leftovers source by source
+        for (;; ++kk) {
+            const int left = pref[kk + 1] - pref[kk] - m;
+            if (c2 < left) break;
+            c2 -= left;
+        }
+        k = kk; off = (m + c2) << 5;
+        return;
+    }
+    const int R = pref[W - 1];                           // remote chunks; local chunks: pref[W] - R
+    int r;                                               // linear index into the remote stream, or -1 = local chunk q
+    int q = 0;
+    if (W == 1) { k = 0; off = c << 5; return; }
+    if (c < W * m) {
+        const int qq = c / W, pos = c % W;
+        if (pos == W - 1) { r = -1; q = qq; } else r = qq * (W - 1) + pos;
+    } else {
+        const int c2 = c - W * m, remR = R - m * (W - 1);
+        if (c2 < remR) r = m * (W - 1) + c2; else { r = -1; q = m + (c2 - remR); }
+    }
+    if (r < 0) { k = W - 1; off = q << 5; return; }
+    k = 0;
+    while (r >= pref[k + 1]) ++k;
+    off = (r - pref[k]) << 5;
+}
+
 template <int CPL>
 struct P2PRows {
     float4 u[CPL], i[CPL], j[CPL];
@@ -132,16 +167,19 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
     if (threadIdx.x <= W) s_bounds[threadIdx.x] = a.item_bounds[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
-        // chunk order: round-robin over the sources while every source still has chunks (a rank then pulls from all
-        // homes at once - uniform all-to-all traffic on the switch - and its local triples overlap the NVLink round
-        // trips of the remote ones), then the leftovers source by source
-        int mn = 0x7fffffff;
-        for (int k = 0; k < W; ++k) mn = min(mn, (s_cnt[k] + 31) >> 5);
-        if (a.flags & B200REC_F_P2P_SEQUENTIAL) mn = 0;
-        s_rr = mn;
-        int acc = mn * W;
-        for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += ((s_cnt[k] + 31) >> 5) - mn; }
+        // s_pref: chunk prefix over the sources in visiting order (slots 0..W-2 are the remote homes me+1, me+2, ...,
+        // slot W-1 is this rank itself); s_rr: how many local chunks are interleaved with the remote stream (chunk_of)
+        int acc = 0;
+        for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += (s_cnt[k] + 31) >> 5; }
         s_pref[W] = acc;
+        const int R = s_pref[W - 1], nl = acc - R;
+        int m = (W > 1) ? min(nl, R / (W - 1)) : 0;
+        if (a.flags & B200REC_F_P2P_PURE_SEQUENTIAL) m = 0;
+        if (a.flags & B200REC_F_P2P_ROUND_ROBIN) {
+            m = 0x7fffffff;
+            for (int k = 0; k < W; ++k) m = min(m, (s_cnt[k] + 31) >> 5);
+        }
+        s_rr = m;
         if (blockIdx.x == 0 && a.n_processed) {
             int tot = 0;
             for (int k = 0; k < W; ++k) tot += s_cnt[k];
@@ -166,8 +204,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
     for (; c < n_chunks; c = c_next) {
         if (lane == 0) c_next = (int)atomicAdd(work, 1u);   // latency hides behind this chunk's rows
         int k, off;
-        if (c < s_rr * W) { k = c % W; off = (c / W) << 5; }
-        else { k = 0; while (c >= s_pref[k + 1]) ++k; off = (s_rr + c - s_pref[k]) << 5; }
+        chunk_of(c, W, s_rr, s_pref, (a.flags & B200REC_F_P2P_ROUND_ROBIN) != 0, k, off);
         const int n_here = min(32, s_cnt[k] - off);
         int u = 0, i = 0, j = 0;
         if (lane < n_here) { u = s_iu[k][off + lane]; i = s_ii[k][off + lane]; j = s_ij[k][off + lane]; }
@@ -257,7 +294,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 3 : (CPL == 2 ? 2 : 1)) p2p_st
 // at a time: more independent loads in flight per lane (what hides the ~2 us NVLink round trip of a remote user row),
 // a 3-stage instead of a 5-stage reduction, and the scalar part paid once per 32/G triples (cf. bpr_step_group_kernel).
 template <int G, bool UNIQ, bool LOSS>
-__global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_constant__ P2PParams p) {
+__global__ void __launch_bounds__(256, 3) p2p_step_group_kernel(const __grid_constant__ P2PParams p) {
     constexpr int F4 = 32, CPL = F4 / G, TPW = 32 / G, ITERS = 32 / TPW, LD = F4 * 4;
     const bool no_uwrite = (p.a.flags & B200REC_F_P2P_NO_UWRITE) != 0, no_uread = (p.a.flags & B200REC_F_P2P_NO_UREAD) != 0;
     __shared__ int s_cnt[B200REC_MAX_RANKS];
@@ -281,16 +318,19 @@ __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_consta
     if (threadIdx.x <= W) s_bounds[threadIdx.x] = a.item_bounds[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
-        // chunk order: round-robin over the sources while every source still has chunks (a rank then pulls from all
-        // homes at once - uniform all-to-all traffic on the switch - and its local triples overlap the NVLink round
-        // trips of the remote ones), then the leftovers source by source
-        int mn = 0x7fffffff;
-        for (int k = 0; k < W; ++k) mn = min(mn, (s_cnt[k] + 31) >> 5);
-        if (a.flags & B200REC_F_P2P_SEQUENTIAL) mn = 0;
-        s_rr = mn;
-        int acc = mn * W;
-        for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += ((s_cnt[k] + 31) >> 5) - mn; }
+        // s_pref: chunk prefix over the sources in visiting order (slots 0..W-2 are the remote homes me+1, me+2, ...,
+        // slot W-1 is this rank itself); s_rr: how many local chunks are interleaved with the remote stream (chunk_of)
+        int acc = 0;
+        for (int k = 0; k < W; ++k) { s_pref[k] = acc; acc += (s_cnt[k] + 31) >> 5; }
         s_pref[W] = acc;
+        const int R = s_pref[W - 1], nl = acc - R;
+        int m = (W > 1) ? min(nl, R / (W - 1)) : 0;
+        if (a.flags & B200REC_F_P2P_PURE_SEQUENTIAL) m = 0;
+        if (a.flags & B200REC_F_P2P_ROUND_ROBIN) {
+            m = 0x7fffffff;
+            for (int k = 0; k < W; ++k) m = min(m, (s_cnt[k] + 31) >> 5);
+        }
+        s_rr = m;
         if (blockIdx.x == 0 && a.n_processed) {
             int tot = 0;
             for (int k = 0; k < W; ++k) tot += s_cnt[k];
@@ -313,8 +353,7 @@ __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_consta
     for (; c < n_chunks; c = c_next) {
         if (lane == 0) c_next = (int)atomicAdd(work, 1u);
         int k, off;
-        if (c < s_rr * W) { k = c % W; off = (c / W) << 5; }
-        else { k = 0; while (c >= s_pref[k + 1]) ++k; off = (s_rr + c - s_pref[k]) << 5; }
+        chunk_of(c, W, s_rr, s_pref, (a.flags & B200REC_F_P2P_ROUND_ROBIN) != 0, k, off);
         const int n_here = min(32, s_cnt[k] - off);
         int u = 0, i = 0, j = 0;
         if (lane < n_here) { u = s_iu[k][off + lane]; i = s_ii[k][off + lane]; j = s_ij[k][off + lane]; }
@@ -326,29 +365,74 @@ __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_consta
             for (int q = 1; q < W; ++q) o += (id >= s_bounds[q]);
             return s_V[o] + (int64_t)(id - s_bounds[o]) * LD;
         };
+        // Hot positive of the chunk.  A rank owns the item rows of its range, so under a Zipf catalogue the rank holding
+        // THE most popular item sends a third of its positive-row reductions to one row (4 L2 lines) - they serialise
+        // in the slice's atomic unit: measured 0.99 ms per 1M triples on that rank against 0.46 ms elsewhere (N=4), the
+        // whole step waits for it.  The triples of the chunk that share the most frequent positive are therefore
+        // processed first, their item update is summed in registers and leaves as ONE reduction per chunk, and the row
+        // is read once.
+        const unsigned vmask = __ballot_sync(0xffffffffu, lane < n_here);
+        const unsigned same = __match_any_sync(0xffffffffu, lane < n_here ? i : -1 - lane);
+        const int cnt_same = (lane < n_here) ? __popc(same) : 0;
+        const int mx = __reduce_max_sync(0xffffffffu, cnt_same);
+        unsigned hot = 0;
+        if (mx >= 3) hot = __shfl_sync(0xffffffffu, same, __ffs(__ballot_sync(0xffffffffu, cnt_same == mx)) - 1);
+        const int nh = __popc(hot);
+        const unsigned cold = vmask & ~hot;
+        const int i_hot = nh ? __shfl_sync(0xffffffffu, i, __ffs(hot) - 1) : -1;
+        float4 hrow[CPL], hacc[CPL];
+        if (nh) {
+            const float *ph = vptr(i_hot, false) + sl * 4;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) { hrow[q] = ld4(ph + q * G * 4); hacc[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        }
+        // the user row (the one that may come over NVLink: ~2.5 us) is fetched ONE ITERATION AHEAD, so its round trip
+        // overlaps the item-row work of the current pair of triples
+        auto src_of = [&](int pos) -> int {                      // lane that holds the triple processed at `pos`
+            if (pos >= n_here) return 0;
+            return pos < nh ? __fns(hot, 0, pos + 1) : __fns(cold, 0, pos - nh + 1);
+        };
+        float4 nu[CPL];
+        int src_nx = src_of(sg);
+        int tu_nx = __shfl_sync(0xffffffffu, u, src_nx);
+        if (sg < n_here && !no_uread) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) nu[q] = ld4(Uhome + (int64_t)tu_nx * LD + sl * 4 + q * G * 4);
+        }
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             if (it * TPW >= n_here) break;                       // warp-uniform
-            const int src = it * TPW + sg;
-            const int tu = __shfl_sync(0xffffffffu, u, src);
+            const int pos = it * TPW + sg;                       // position in the processing order: hot triples first
+            const bool ok = pos < n_here;
+            const bool is_hot = pos < nh;
+            const int src = src_nx;
+            const int tu = tu_nx;
             const int ti = __shfl_sync(0xffffffffu, i, src);
             const int tj = __shfl_sync(0xffffffffu, j, src);
-            const bool ok = src < n_here;
             float4 ru[CPL], ri[CPL], rj[CPL];
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) ru[q] = nu[q];
+            src_nx = src_of(pos + TPW);
+            tu_nx = __shfl_sync(0xffffffffu, u, src_nx);
+            if (pos + TPW < n_here && !no_uread) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) nu[q] = ld4(Uhome + (int64_t)tu_nx * LD + sl * 4 + q * G * 4);
+            }
             float part = 0.f;
             if (ok) {
-                const float *pu = Uhome + (int64_t)tu * LD + sl * 4;
-                const float *pi = vptr(ti, false) + sl * 4;
                 const float *pj = vptr(tj, false) + sl * 4;
                 if (no_uread) {
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) ru[q] = make_float4(0.01f, 0.01f, 0.01f, 0.01f);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) ru[q] = ld4(pu + q * G * 4);
                 }
+                if (is_hot) {
 #pragma unroll
-                for (int q = 0; q < CPL; ++q) ri[q] = ld4(pi + q * G * 4);
+                    for (int q = 0; q < CPL; ++q) ri[q] = hrow[q];
+                } else {
+                    const float *pi = vptr(ti, false) + sl * 4;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) ri[q] = ld4(pi + q * G * 4);
+                }
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) rj[q] = ld4(pj + q * G * 4);
 #pragma unroll
@@ -365,7 +449,7 @@ __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_consta
                 const float a1 = c_g * (1.f - s);
                 if (LOSS && sl == 0) loss_local += (x < -15.f) ? -x : -__logf(s);
                 float *pu = Uhome + (int64_t)tu * LD + sl * 4;
-                float *pi = vptr(ti, true) + sl * 4;
+                float *pi = is_hot ? nullptr : vptr(ti, true) + sl * 4;
                 float *pj = vptr(tj, true) + sl * 4;
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
@@ -381,9 +465,25 @@ __global__ void __launch_bounds__(256) p2p_step_group_kernel(const __grid_consta
                         if (UNIQ) st4(pu + q * G * 4, make_float4(vu.x + du.x, vu.y + du.y, vu.z + du.z, vu.w + du.w));
                         else red4(pu + q * G * 4, du);
                     }
-                    red4(pi + q * G * 4, di);
+                    if (is_hot) { hacc[q].x += di.x; hacc[q].y += di.y; hacc[q].z += di.z; hacc[q].w += di.w; }
+                    else red4(pi + q * G * 4, di);
                     red4(pj + q * G * 4, dj);
                 }
+            }
+        }
+        if (nh) {   // one reduction for all hot triples of the chunk: fold the groups' partial sums, group 0 writes
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+#pragma unroll
+                for (int o = G; o < 32; o <<= 1) {
+                    hacc[q].x += __shfl_xor_sync(0xffffffffu, hacc[q].x, o); hacc[q].y += __shfl_xor_sync(0xffffffffu, hacc[q].y, o);
+                    hacc[q].z += __shfl_xor_sync(0xffffffffu, hacc[q].z, o); hacc[q].w += __shfl_xor_sync(0xffffffffu, hacc[q].w, o);
+                }
+            }
+            if (sg == 0) {
+                float *ph = vptr(i_hot, true) + sl * 4;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) red4(ph + q * G * 4, hacc[q]);
             }
         }
         c_next = __shfl_sync(0xffffffffu, c_next, 0);

@@ -208,7 +208,8 @@ def test_step_overlapped_matches_one_step_stale_oracle(dev):
     rng = np.random.default_rng(21)
     nu, ni, d, B = 3000, 700, 128, 1024
     _, csr = _csr(rng, nu, ni, 2, 20, dev)
-    m = UserShardedBPR(nu, ni, d, csr, 0, 1, dev, lr=3.0, reg=0.01, init_std=0.1, seed=4)
+    LR = 300.0          # per-triple step 0.3: large enough that one step of staleness moves rows by ~1e-2 (oracle simulation)
+    m = UserShardedBPR(nu, ni, d, csr, 0, 1, dev, lr=LR, reg=0.01, init_std=0.1, seed=4)
     U0, V0 = m.U.cpu().numpy()[:, :d], m.V.cpu().numpy()[:, :d]
     batches = []
     for s in range(5):
@@ -218,14 +219,14 @@ def test_step_overlapped_matches_one_step_stale_oracle(dev):
         batches.append((users.cpu().numpy(), op.cpu().numpy(), on.cpu().numpy()))
     m.flush()
     torch.cuda.synchronize()
-    Ur, Vr = O.sgd_steps_stale_items(U0, V0, batches, 3.0, 0.01)
-    np.testing.assert_allclose(m.U.cpu().numpy()[:, :d], Ur, rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(m.V.cpu().numpy()[:, :d], Vr, rtol=2e-5, atol=2e-6)
+    Ur, Vr = O.sgd_steps_stale_items(U0, V0, batches, LR, 0.01)
+    np.testing.assert_allclose(m.U.cpu().numpy()[:, :d], Ur, rtol=2e-5, atol=5e-6)
+    np.testing.assert_allclose(m.V.cpu().numpy()[:, :d], Vr, rtol=2e-5, atol=5e-6)
     # and it is NOT the synchronous trajectory: the staleness is real and measurable
     Us, Vs = U0, V0
     for b in batches:
-        Us, Vs, _ = O.sgd_step(Us, Vs, *b, 3.0, 0.01)
-    assert np.abs(Vs - Vr).max() > 1e-4
+        Us, Vs, _ = O.sgd_step(Us, Vs, *b, LR, 0.01)
+    assert np.abs(Vs - Vr).max() > 1e-3
 
 
 @pytest.mark.gpu

@@ -18,6 +18,9 @@ perms = [torch.randperm(n_loc, device=dev, generator=g)[:B].to(torch.int32).cont
 m.route(perms[0], 77); m._n += 1; m.route(perms[1], 78); m._n += 1; m.barrier()
 
 
+LAST = [0.0]
+
+
 def timed(n=6):
     dist.barrier() if world > 1 else None
     torch.cuda.synchronize()
@@ -26,23 +29,43 @@ def timed(n=6):
     for k in range(n):
         m.compute(B * world)
     e1.record(); torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+    LAST[0] = e0.elapsed_time(e1) / n
+    t = torch.tensor([LAST[0]], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
 
-SEQ, NOW, NOR = 256, 512, 1024
+def stage_ids_locally():
+    """diagnostic: bulk-copy every inbound outbox segment (ids + count) into local memory and point the step at the copies"""
+    from recsys_pytorch_b200._lib import lib, check, current_stream
+    import ctypes as C
+    keep = []
+    for b in range(2):
+        a = m._step_args[b]
+        for s_ in range(world):
+            for name in ("in_u", "in_i", "in_j"):
+                loc = torch.empty(m.cap, dtype=torch.int32, device=dev)
+                check(lib().b200rec_peer_copy(loc.data_ptr(), getattr(a, name)[s_], m.cap * 4, current_stream()))
+                getattr(a, name)[s_] = loc.data_ptr(); keep.append(loc)
+            loc = torch.empty(1, dtype=torch.int32, device=dev)
+            check(lib().b200rec_peer_copy(loc.data_ptr(), a.in_cnt[s_], 4, current_stream()))
+            a.in_cnt[s_] = loc.data_ptr(); keep.append(loc)
+    torch.cuda.synchronize()
+    return keep
+
+
+RR, NOW, NOR, SEQ = 256, 512, 1024, 2048
 for var in ("16", "0"):
     os.environ["B200REC_P2P_VARIANT"] = var
-    for name, fl in (("round-robin", 0), ("sequential", SEQ), ("rr no-uwrite", NOW), ("rr no-uread no-uwrite", NOW | NOR),
-                     ("seq no-uwrite", SEQ | NOW), ("seq no-uread no-uwrite", SEQ | NOW | NOR)):
+    for name, fl in (("interleaved (default)", 0), ("pure sequential", SEQ), ("round-robin all", RR), ("il no-uwrite", NOW),
+                     ("il no-uread no-uwrite", NOW | NOR), ("seq no-uread no-uwrite", SEQ | NOW | NOR)):
         if var == "0" and (fl & (NOW | NOR)):
             continue
         m.extra_flags = fl
         timed(2)
         ms = timed()
-        if rank == 0:
-            print("variant %-3s %-26s %.3f ms" % (var, name, ms), flush=True)
+        print("rank %d variant %-3s %-26s max %.3f ms own %.3f ms" % (rank, var, name, ms, LAST[0]), flush=True)
+print("rank %d items in shard %d  processed %d" % (rank, m.ihi - m.ilo, int(m.n_processed.item())), flush=True)
 if world > 1:
     dist.barrier(); m.close(); dist.destroy_process_group()
