@@ -319,6 +319,25 @@ int b200rec_spmm_csr_split(const int64_t *indptr, const int32_t *indices, const 
                            const int64_t *seg_end, int n_seg, const int32_t *long_rows,
                            const int32_t *long_seg_ptr, int n_long, float *partial, void *stream);
 
+/* models/NGCF.py:198-212, one propagation layer after side = A_hat @ ego (b200rec_spmm_csr):
+ *   z = side W_gc + b_gc + (ego * side) W_bi + b_bi;  ego_next = dropout(leaky_relu(z, 0.2), mess_dropout);
+ *   nrm = max(|ego_next|_2, 1e-12);  acc += acc_scale * ego_next / nrm      (the running mean of :216-218)
+ * W_*: [d,d] row-major (in x out) as nn.Parameter stores them, b_*: [d].  d <= 64.  mess_dropout > 0 draws its mask
+ * from the library's counter RNG keyed by (seed, step, layer, row, column) - pass 0 for evaluation. */
+int b200rec_ngcf_layer_forward(const float *ego, const float *side, const float *W_gc, const float *b_gc,
+                               const float *W_bi, const float *b_bi, int n_rows, int ld, int d, int layer,
+                               float mess_dropout, uint64_t seed, uint64_t step, float *ego_next, float *nrm,
+                               float *acc, float acc_scale, void *stream);
+/* autograd backward of that layer.  g_out = dL/d(acc) (dense [n_rows, ld]); g_next = gradient reaching ego_next from
+ * the layer above (NULL for the top layer).  Writes g_z (scratch), g_side = d(side), g_ego = the direct part of d(ego)
+ * (the caller adds A_hat @ g_side with b200rec_spmm_csr), and ACCUMULATES dW_gc, dW_bi [d,d] and db [d] (= d b_gc =
+ * d b_bi; caller zeroes them). */
+int b200rec_ngcf_layer_backward(const float *g_out, const float *g_next, const float *ego, const float *side,
+                                const float *ego_next, const float *nrm, const float *W_gc, const float *W_bi,
+                                int n_rows, int ld, int d, int layer, float mess_dropout, uint64_t seed, uint64_t step,
+                                float acc_scale, float *g_z, float *g_side, float *g_ego, float *dW_gc, float *dW_bi,
+                                float *db, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

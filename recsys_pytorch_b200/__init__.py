@@ -8,7 +8,7 @@ this package is the host-side mirror of the reference's Python interface.
 from . import _lib  # noqa: F401
 from ._lib import B200RecError, LIB_PATH  # noqa: F401
 
-__all__ = ["MF", "B200MF", "BaseModel", "LightGCN", "PairwiseGenerator", "Evaluator", "UIRTDataset", "engine", "B200RecError"]
+__all__ = ["MF", "B200MF", "BaseModel", "LightGCN", "NGCF", "PairwiseGenerator", "Evaluator", "UIRTDataset", "engine", "B200RecError"]
 
 
 def __getattr__(name):  # lazy: importing the package must not require torch.cuda
@@ -18,6 +18,9 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name == "LightGCN":
         from . import lightgcn
         return lightgcn.LightGCN
+    if name == "NGCF":
+        from . import ngcf
+        return ngcf.NGCF
     if name == "PairwiseGenerator":
         from .generators import PairwiseGenerator
         return PairwiseGenerator
@@ -27,7 +30,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name == "UIRTDataset":
         from .dataset import UIRTDataset
         return UIRTDataset
-    if name in ("engine", "synthetic", "dist", "evaluation", "generators", "mf", "lightgcn", "dataset"):
+    if name in ("engine", "synthetic", "dist", "evaluation", "generators", "mf", "lightgcn", "ngcf", "p2p", "dataset"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

@@ -119,6 +119,9 @@ _PROTOS = {
     "b200rec_loo_metrics": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "b200rec_column_means": (_I, [_P, _L, _I, _P, _P]),
     "b200rec_spmm_csr": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _F, _I, _P]),
+    "b200rec_ngcf_layer_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, C.c_uint64, C.c_uint64, _P, _P, _P, _F, _P]),
+    "b200rec_ngcf_layer_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, C.c_uint64, C.c_uint64, _F,
+                                        _P, _P, _P, _P, _P, _P, _P]),
     "b200rec_spmm_csr_split": (_I, [_P, _P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _F, _I, _L, _P, _P, _I, _P, _P, _I, _P, _P]),
 }
 EXPORTS = tuple(_PROTOS)

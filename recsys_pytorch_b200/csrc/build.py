@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libb200rec.so")
-SOURCES = ["capi.cu", "bpr_step.cu", "p2p.cu", "pointwise_step.cu", "score_exact.cu", "score_tc.cu", "metrics.cu", "spmm.cu"]
+SOURCES = ["capi.cu", "bpr_step.cu", "p2p.cu", "pointwise_step.cu", "score_exact.cu", "score_tc.cu", "metrics.cu", "spmm.cu", "ngcf.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC"]
 

@@ -294,8 +294,9 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
     layout = args.layout
     loss = torch.zeros(1, dtype=torch.float64, device=dev)
     secondary = None
-    if layout == "user_sharded" and not getattr(args, "no_secondary", False):
-        # the north_star layout measured in the same run (fewer steps: it is all-reduce bound)
+    if layout == "user_sharded" and getattr(args, "nccl_north_star", False):
+        # the north_star layout exactly as written (replicated user table, NCCL all-reduce of the [B, ld] user deltas),
+        # measured in the same run on request (it needs the whole CSR and user table on every rank)
         secondary = _bench_item_sharded(args, c, rank, world, dev, timed_region, nu, ni, max(3, args.steps // 10))
     if layout == "item_sharded":
         # replicated CSR + replicated user table; every rank walks the same global batch of N*B_local users
@@ -365,6 +366,8 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
     ms, clk = timed_under_load(step_counted, step_idle, args.steps, world, dev.index or 0, rank=rank, pre_steps=500,
                                post_steps=150)
     launches = counted[1] - counted[0]
+    reps = [ms] + [timed_region(lambda s: step(1000 * (r + 1) + s), args.steps, world) for r in range(2)]
+    ms = float(np.median(reps))                               # median of 3 timed repeats of the K steps
     # e2e: same step with the batch's user ids arriving from pinned host memory and the loss read back
     host = [p.cpu().pin_memory() for p in perms]
 
@@ -399,6 +402,24 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
                     "k": c["eval_k"], "algo": "tc", "flops_per_pair": 2 * d,
                     "note": "whole evaluate() per rank incl. metrics and the metric all-reduce; users sharded, item "
                             "table replicated"}
+    # the item-sharded P2P layout and the scoring sweep, measured in the same run (failures are reported, not fatal)
+    p2p_res, cfg5 = None, None
+    if layout == "user_sharded" and not getattr(args, "no_secondary", False):
+        del tr, train
+        torch.cuda.empty_cache()
+        try:
+            from . import p2p as _p2p
+            p2p_res = _p2p.measure_p2p(c, rank, world, dev, timed_region, steps=max(5, args.steps // 2))
+        except Exception as e:                                       # pragma: no cover
+            p2p_res = {"error": repr(e)[:300]} if rank == 0 else None
+    if not getattr(args, "no_legs", False):
+        try:
+            from . import bench_legs
+            torch.cuda.empty_cache()
+            cfg5 = bench_legs.cfg5_leg(dev, rank, world, float(getattr(args, "bf16_tf", 1590.0)), peak_src,
+                                       small=bool(c.get("small")))
+        except Exception as e:                                       # pragma: no cover
+            cfg5 = {"error": repr(e)[:300]}
     if rank == 0:
         val = B_glob * args.steps / (ms * 1e-3)
         bpt = 24 * d + 8
@@ -409,8 +430,9 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
                "config": {"workload": "BPRMF synthetic %dx%d d=%d, %s over %d GPUs" % (nu, ni, d, layout, world),
                           "batch_triples": B_glob, "per_gpu_triples": B_local, "optimizer": "sgd+l2",
                           "parallelism": "%s%d" % (layout, world), "collective": coll, "gather": args.gather,
-                          "exchange": (exchange if layout == "user_sharded" else None),
-                          "l2_policy": "inputs larger than L2"},
+                          "exchange": (exchange if layout == "user_sharded" else None), "lr_per_triple": c["lr_per_triple"],
+                          "l2_policy": "inputs larger than L2", "timing": "median of 3 repeats of the K steps",
+                          "repeats_ms": reps},
                "clocks": clk,
                "e2e": {"value": B_glob * args.steps / (ms_e2e * 1e-3), "unit": "triples/s",
                        "h2d_bytes_per_step": int(perms[0].numel() * 4), "d2h_bytes_per_step": 8,
@@ -424,7 +446,11 @@ def bench_multi_gpu(args, c, rank, world, dev, timed_region, timed_under_load, h
         if eval_leg is not None:
             out["eval"] = eval_leg
         if secondary is not None:
-            out["north_star_item_sharded"] = secondary
+            out["north_star_item_sharded_nccl"] = secondary
+        if p2p_res is not None:
+            out["item_sharded_p2p"] = p2p_res
+        if cfg5 is not None:
+            out["eval_cfg5"] = cfg5
         print(json.dumps(out))
     dist.barrier()
     dist.destroy_process_group()

@@ -80,6 +80,7 @@ class LightGCN(MF):
         self.gather = str(_hp(hparams, "gather", "ldg")).lower()
         self.score_algo = SCORE_TC if str(_hp(hparams, "score_algo", "exact")).lower() == "tc" else SCORE_EXACT
         self.seed = int(_hp(hparams, "seed", 2020))
+        self.pointwise, self.lr_per_triple = False, None             # read by the shared MF.fit loop
         std = float(_hp(hparams, "init_std", 0.01))                 # nn.init.normal_(w, 0, 0.01), LightGCN.py:50-51
 
         N, d = self.num_users + self.num_items, self.emb_dim

@@ -284,9 +284,9 @@ class MF(BaseModel):
 
     def fit(self, dataset, exp_config, evaluator=None, early_stop=None, loggers=None):   # MF.py:44-97
         train_matrix = dataset.train_data
-        if self.lr_per_triple is not None and self.optimizer_name == "sgd":
+        if getattr(self, "lr_per_triple", None) is not None and self.optimizer_name == "sgd":
             self.lr = float(self.lr_per_triple) * int(exp_config.batch_size)
-        if self.pointwise:
+        if getattr(self, "pointwise", False):
             return self._fit_pointwise(dataset, exp_config, evaluator, early_stop, loggers)
         gen = PairwiseGenerator(train_matrix, num_negatives=1, num_positives_per_user=1,
                                 batch_size=exp_config.batch_size, shuffle=True, device=self.device,

@@ -447,6 +447,32 @@ def build_rank(c, rank, world, dev, d=None, max_batch=None, lr=None, head=None, 
     return m, train, target, hist
 
 
+def measure_p2p(c, rank, world, dev, timed_region, steps=8, warmup=3):
+    """Compact measurement of the P2P layout at the weak-scaling shape (used by dist.bench_multi_gpu to report this
+    layout beside the default one in the same run).  Returns a dict (rank 0) / None."""
+    B_local = c["batch"]
+    B_glob = B_local * world
+    m, train, target, hist = build_rank(c, rank, world, dev, lr=c["lr_per_triple"] * B_glob, max_batch=B_local, head=0)
+    n_loc = m.uhi - m.ulo
+    g = torch.Generator(device=dev); g.manual_seed(c["seed"] + rank)
+    perms = [torch.randperm(n_loc, device=dev, generator=g)[:B_local].to(torch.int32).contiguous() for _ in range(4)]
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    for s in range(warmup):
+        m.step(perms[s % 4], s + 1, B_glob, loss_sum=loss)
+    ms = timed_region(lambda s: m.step(perms[s % 4], warmup + s + 1, B_glob, loss_sum=loss), steps, world)
+    n_ev = min(int(c["eval_users"]), n_loc)
+    scores, n = m.evaluate(torch.arange(n_ev, dtype=torch.int32, device=dev), target, [c["eval_k"]])
+    out = {"value": B_glob * steps / (ms * 1e-3), "unit": "triples/s", "steps": steps, "ms_per_step": ms / steps,
+           "batch_triples": B_glob, "ndcg@%d" % c["eval_k"]: scores["NDCG@%d" % c["eval_k"]],
+           "layout": "item table sharded by item-id range (north_star) + user table sharded by user-id range; user rows "
+                     "through NVSwitch peer memory inside the fused step kernel; one 4-byte all-reduce per step (barrier)",
+           "workload": "%dx%d d=%d" % (m.num_users, m.num_items, c["d"])}
+    m.close()
+    del train, target
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
 def bench_p2p(args, c, rank, world, dev, timed_region, timed_under_load, hbm_gbs, peak_src):
     """Weak scaling, one fused P2P step per batch: every GPU brings 1.25M users, 125k items and 1M triples per step."""
     import json

@@ -317,3 +317,29 @@ def test_pointwise_oracle_replays_reference_ml100k_trajectory(golden):
         for got, ref in ((U, g[f"{lf}_U"]), (V, g[f"{lf}_V"])):
             bad = ~np.isclose(got, ref, rtol=2e-4, atol=2e-5)
             assert bad.mean() < 0.01 and np.abs(got - ref).max() < 7 * 1e-3
+
+
+def test_ngcf_oracle_matches_reference_forward_and_autograd(golden):
+    """tests/golden/ngcf_ml100k.npz (reference NGCF, models/NGCF.py:182-221 + autograd): the numpy restatement of the
+    propagation and its closed-form backward reproduce the propagated tables, the loss and every parameter gradient."""
+    g, lg = golden["ngcf_ml100k"], golden["lightgcn_ml100k"]
+    nu, ni = g["U0"].shape[0], g["V0"].shape[0]
+    import scipy.sparse as sp
+    A = sp.csr_matrix((lg["adj_vals"], (lg["adj_rows"], lg["adj_cols"])), shape=(nu + ni, nu + ni))   # same graph recipe
+    E0 = np.concatenate([g["U0"], g["V0"]])
+    Wg, bg, Wb, bb = ([g["%s_%d" % (nm, k)] for k in range(2)] for nm in ("W_gc", "b_gc", "W_bi", "b_bi"))
+    out, cache = O.ngcf_forward(A, E0, Wg, bg, Wb, bb, keep=True)
+    np.testing.assert_allclose(out[:nu], g["prop_U"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(out[nu:], g["prop_V"], rtol=2e-5, atol=2e-6)
+    u, i, j = g["users"], g["pos"], g["neg"]
+    loss, _ = O.bpr_loss(out[:nu], out[nu:], u, i, j)
+    assert abs(float(loss) - float(g["loss"])) < 2e-6
+    dU, dV, _, _ = O.bpr_grads(out[:nu], out[nu:], u, i, j)
+    dE0, dWg, dbg, dWb, dbb = O.ngcf_backward(A, np.concatenate([dU, dV]), cache, Wg, Wb)
+    np.testing.assert_allclose(dE0[:nu], g["dU0"], rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(dE0[nu:], g["dV0"], rtol=2e-4, atol=2e-7)
+    for k in range(2):
+        np.testing.assert_allclose(dWg[k], g["dW_gc_%d" % k], rtol=2e-4, atol=2e-7)
+        np.testing.assert_allclose(dbg[k], g["db_gc_%d" % k], rtol=2e-4, atol=2e-7)
+        np.testing.assert_allclose(dWb[k], g["dW_bi_%d" % k], rtol=2e-4, atol=2e-7)
+        np.testing.assert_allclose(dbb[k], g["db_bi_%d" % k], rtol=2e-4, atol=2e-7)
