@@ -469,13 +469,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gather", default="ldg", choices=["ldg", "async", "tma", "generic"])
     ap.add_argument("--score-algo", dest="score_algo", default="tc", choices=["exact", "tc"])
-    ap.add_argument("--layout", default="user_sharded", choices=["p2p", "item_sharded", "user_sharded"],
-                    help="N>1: user_sharded (default - the fastest measured at every N: users sharded, item table "
-                         "replicated, dense item delta all-reduced one step late; also measures the p2p layout in the same "
-                         "run and reports it under 'item_sharded_p2p'), p2p (item AND user tables sharded by id range, user "
-                         "rows through NVSwitch peer memory inside the fused step) or item_sharded (north_star as written: "
-                         "replicated user table + NCCL all-reduce of the user-delta buffer).  N=8 is BASELINE configs[2] "
-                         "(10M x 1M) in every layout")
+    ap.add_argument("--layout", default="p2p", choices=["p2p", "item_sharded", "user_sharded"],
+                    help="N>1: p2p (default - item table sharded by item-id range as north_star asks AND user table "
+                         "sharded by user-id range, user rows through NVSwitch peer memory inside the fused step; the "
+                         "fastest measured at BASELINE configs[2]: 5.28 G triples/s on 8 GPUs), user_sharded (users "
+                         "sharded, item table replicated, dense item delta all-reduced one step late: 3.91 G at N=8, "
+                         "2.67 G at N=2; also reports the p2p layout under 'item_sharded_p2p') or item_sharded (north_star "
+                         "exactly as written: replicated user table + NCCL all-reduce of the user-delta buffer: 0.61 G). "
+                         "N=8 is BASELINE configs[2] (10M x 1M) in every layout")
     ap.add_argument("--nccl-north-star", dest="nccl_north_star", action="store_true",
                     help="N>1 user_sharded: also measure the north_star layout as written (NCCL all-reduce of user deltas)")
     ap.add_argument("--no-secondary", dest="no_secondary", action="store_true")

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("B200REC_LIB") or os.path.join(_HERE, "libb200rec.so")
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 SINK_UPDATE, SINK_STAGE, SINK_GRAD, SINK_NONE = 0, 1, 2, 3
 F_USERS_UNIQUE, F_TMA_GATHER, F_ITEM_DELTA, F_GENERIC, F_ASYNC_GATHER, F_ITEM_DELTA_BF16, F_L2_HINTS = 1, 2, 4, 8, 16, 32, 64
+F_P2P_ROUND_ROBIN, F_P2P_NO_UWRITE, F_P2P_NO_UREAD, F_P2P_PURE_SEQUENTIAL = 256, 512, 1024, 2048
 GATHER_FLAGS = {"ldg": 0, "tma": F_TMA_GATHER, "async": F_ASYNC_GATHER, "generic": F_GENERIC, "ldg_hints": F_L2_HINTS}
 SCORE_EXACT, SCORE_TC = 0, 1
 

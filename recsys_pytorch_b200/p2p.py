@@ -43,22 +43,41 @@ class _CudaArray:
 
 
 class PeerArena:
-    """One IPC-exportable device allocation (cudaMalloc through the C ABI - torch's caching allocator sub-allocates and
-    cannot be exported block by block), carved into torch views."""
+    """One peer-mappable device allocation per rank, carved into torch views.
+
+    symmetric=True (multi-process runs): the block comes from torch's symmetric-memory allocator (CUDA VMM: cuMemCreate
+    + shareable handles, 2 MB granules); `rendezvous()` exchanges the handles and returns every rank's address in THIS
+    process.  Measured reason (profiles/r02_p2p_notes.md): with legacy cudaIpc mappings a kernel that gathers from
+    several peers at once runs 5-7x slower than the same pattern over same-process / VMM mappings.
+    symmetric=False: plain cudaMalloc through the C ABI (single-process emulation; exportable with the legacy 64-byte
+    cudaIpc handle via `handle()` / `import_peer`)."""
 
     ALIGN = 256
 
-    def __init__(self, nbytes, device):
+    def __init__(self, nbytes, device, symmetric=False):
         self.device = torch.device(device)
         self.nbytes = int(nbytes)
-        p = C.c_void_p()
-        with torch.cuda.device(self.device):
-            check(_lib.lib().b200rec_peer_alloc(self.nbytes, C.byref(p)))
-        self.ptr = int(p.value)
-        self._carrier = _CudaArray(self.ptr, self.nbytes)
-        self.buf = torch.as_tensor(self._carrier, device=self.device)
-        assert self.buf.data_ptr() == self.ptr and self.buf.numel() == self.nbytes
+        self.symmetric = bool(symmetric)
+        self._hdl = None
+        if self.symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buf = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+            self.ptr = int(self.buf.data_ptr())
+        else:
+            p = C.c_void_p()
+            with torch.cuda.device(self.device):
+                check(_lib.lib().b200rec_peer_alloc(self.nbytes, C.byref(p)))
+            self.ptr = int(p.value)
+            self._carrier = _CudaArray(self.ptr, self.nbytes)
+            self.buf = torch.as_tensor(self._carrier, device=self.device)
+            assert self.buf.data_ptr() == self.ptr and self.buf.numel() == self.nbytes
         self._off = 0
+
+    def rendezvous(self, group=None):
+        """Collective (symmetric arenas): addresses of every rank's arena in this process."""
+        import torch.distributed._symmetric_memory as symm_mem
+        self._hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        return [int(a) for a in self._hdl.buffer_ptrs]
 
     def carve(self, shape, dtype):
         """(tensor view, byte offset) of the next `shape` block."""
@@ -69,12 +88,15 @@ class PeerArena:
         return self.buf[off:off + n].view(dtype).view(*shape), off
 
     def handle(self) -> bytes:
+        assert not self.symmetric
         h = (C.c_ubyte * PEER_HANDLE_BYTES)()
         check(_lib.lib().b200rec_peer_export(self.ptr, h))
         return bytes(h)
 
     def free(self):
-        if self.ptr:
+        if self.symmetric:
+            self.buf, self._hdl, self.ptr = None, None, 0
+        elif self.ptr:
             self.buf = None
             check(_lib.lib().b200rec_peer_free(self.ptr))
             self.ptr = 0
@@ -189,7 +211,24 @@ class P2PShardedBPR:
         self.cap = int(max_batch if max_batch is not None else nu)
         W, cap, ld = world, self.cap, self.ld
         need = (6 * W * cap * 4 + 2 * 256 + 4 * (nu + ni) * ld + 16 * PeerArena.ALIGN)
-        self.arena = PeerArena(need, self.device)
+        # multi-process: a symmetric (VMM) arena of the same size on every rank; B200REC_P2P_ARENA=ipc forces legacy IPC
+        import os
+        self._symm = (world > 1 and dist.is_initialized() and os.environ.get("B200REC_P2P_ARENA", "symm") != "ipc")
+        self.arena = None
+        if self._symm:
+            t = torch.tensor([need], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                # collective: every rank constructs its shard
+            need = int(t.item())
+            ok = torch.ones(1, dtype=torch.int32, device=self.device)
+            try:
+                self.arena = PeerArena(need, self.device, symmetric=True)
+            except Exception:                                       # no VMM / symmetric-memory support here
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)               # every rank takes the same path
+            if int(ok.item()) == 0:
+                self.arena, self._symm = None, False
+        if self.arena is None:
+            self.arena = PeerArena(need, self.device, symmetric=False)
         # identical carve order on every rank: the outbox offsets depend on (world, cap) only
         self.ob, self.ob_off = [], []
         for _ in range(2):
@@ -258,13 +297,17 @@ class P2PShardedBPR:
         if self.world == 1 or not dist.is_initialized():
             self._wire([self.arena.ptr], [self._meta()])
             return self
-        mine = (self.arena.handle(), self._meta())
+        mine = (None if self._symm else self.arena.handle(), self._meta())
         allm = [None] * self.world
         dist.all_gather_object(allm, mine)
-        bases = []
-        with torch.cuda.device(self.device):
-            for s in range(self.world):
-                bases.append(self.arena.ptr if s == self.rank else import_peer(allm[s][0]))
+        if self._symm:
+            bases = self.arena.rendezvous()
+            assert bases[self.rank] == self.arena.ptr
+        else:
+            bases = []
+            with torch.cuda.device(self.device):
+                for s in range(self.world):
+                    bases.append(self.arena.ptr if s == self.rank else import_peer(allm[s][0]))
         self._wire(bases, [m[1] for m in allm])
         self.barrier()
         return self
@@ -334,7 +377,10 @@ class P2PShardedBPR:
         assert self._step_args is not None, "call connect() first"
         a = self._step_args[self._n & 1]
         a.lr, a.reg, a.inv_batch = self.lr, self.reg, 1.0 / float(global_batch)
-        a.flags = (F_USERS_UNIQUE if users_unique else 0) | int(getattr(self, "extra_flags", 0))
+        # chunk order: all homes round-robin over VMM (symmetric) mappings - the switch sees uniform all-to-all traffic;
+        # one peer at a time over legacy IPC mappings, where round-robin collapses (profiles/r02_p2p_notes.md)
+        order = _lib.F_P2P_ROUND_ROBIN if getattr(self, "_symm", False) else 0
+        a.flags = (F_USERS_UNIQUE if users_unique else 0) | int(getattr(self, "extra_flags", order))
         a.loss_sum = ptr(_lib.require_cuda(loss_sum, "loss_sum", torch.float64)) if loss_sum is not None else None
         a.n_processed = ptr(self.n_processed)
         if self.head:
@@ -398,7 +444,7 @@ class P2PShardedBPR:
         return evaluate_user_shard(self.U, V_full, self.d, eval_users_local, self.train, truth_local, ks, protocol)
 
     def close(self):
-        if self._peer_base is not None and not self._emulated:
+        if self._peer_base is not None and not self._emulated and not self._symm:
             for s, b in enumerate(self._peer_base):
                 if s != self.rank and b:
                     _lib.lib().b200rec_peer_close(b)

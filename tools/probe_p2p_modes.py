@@ -58,8 +58,8 @@ def stage_ids_locally():
 RR, NOW, NOR, SEQ = 256, 512, 1024, 2048
 for var in ("16", "0"):
     os.environ["B200REC_P2P_VARIANT"] = var
-    for name, fl in (("interleaved (default)", 0), ("pure sequential", SEQ), ("round-robin all", RR), ("il no-uwrite", NOW),
-                     ("il no-uread no-uwrite", NOW | NOR), ("seq no-uread no-uwrite", SEQ | NOW | NOR)):
+    for name, fl in (("one peer + local interleaved", 0), ("round-robin all", RR), ("rr no-uwrite", RR | NOW),
+                     ("rr no-uread no-uwrite", RR | NOW | NOR)):
         if var == "0" and (fl & (NOW | NOR)):
             continue
         m.extra_flags = fl
