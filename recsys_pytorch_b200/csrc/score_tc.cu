@@ -1109,7 +1109,10 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         p.n_rows = nr; p.num_items = num_items; p.n_tiles = L.n_tiles; p.k = k; p.d = d;
         p.users = users + r0; p.mask_indptr = mi; p.mask_indices = mx; p.inv_perm = inv_perm;
         p.wide = nullptr;
-        p.append_budget = getenv("B200REC_TC_BUDGET") ? atoi(getenv("B200REC_TC_BUDGET")) : 1536 + 8 * k;
+        p.append_budget = 1536 + 8 * k;
+#ifdef B200REC_TC_DIAG
+        if (getenv("B200REC_TC_BUDGET")) p.append_budget = atoi(getenv("B200REC_TC_BUDGET"));
+#endif
         if (mi) {
             unsigned long long *wide = reinterpret_cast<unsigned long long *>(base + L.off_wide);
             bloom_kernel<<<(nr + 7) / 8, 256, 0, s>>>(users + r0, nr, mi, mx, inv_perm, wide);
@@ -1119,7 +1122,10 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
         p.row_norm = unorm; p.tile_norm = tnorm;
         p.scale_v = reinterpret_cast<float *>(scal + 2); p.scale_u = reinterpret_cast<float *>(scal + 3);
         p.cand = cand; p.cand_cnt = cnt; p.dump = dump ? dump + (size_t)r0 * L.items_pad : nullptr;
-        // diagnostics only: ablation flags, kernel time and filter counters on stderr
+        // diagnostics (ablation flags, kernel time and filter counters on stderr) are compiled in only with
+        // -DB200REC_TC_DIAG (tools/build_ablate.sh); the product library carries none of it
+        p.ablate = 0; p.dbg = nullptr; p.dbg_warp = nullptr; p.dbg_row = nullptr;
+#ifdef B200REC_TC_DIAG
         const char *abl_env = getenv("B200REC_TC_ABLATE");
         const bool diag = getenv("B200REC_TC_TIME") != nullptr;
         p.ablate = abl_env ? atoi(abl_env) : 0;
@@ -1139,6 +1145,7 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
             cudaEventCreate(&ev0); cudaEventCreate(&ev1);
             cudaEventRecord(ev0, s);
         }
+#endif
         switch (L.KB) {
             case 1: rc = (L.tile == kPPN) ? launch_candidates_pp<1>(ma, mb, p, nr_pad / kBM, s)
                                           : launch_candidates<1>(ma, mb, p, nr_pad / kBM, s); break;
@@ -1148,6 +1155,7 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
             default: rc = launch_candidates<4>(ma, mb, p, nr_pad / kBM, s); break;
         }
         if (rc) return rc;
+#ifdef B200REC_TC_DIAG
         if (diag) {
             cudaEventRecord(ev1, s);
             cudaEventSynchronize(ev1);
@@ -1201,6 +1209,7 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
             }
             cudaEventDestroy(ev0); cudaEventDestroy(ev1);
         }
+#endif
         if (!oi) continue;  // dump-only bring-up call
         B200_CUDA(cudaMemsetAsync(redo_n, 0, 4, s));
         const size_t rsmem = (size_t)8 * k * 8 + (size_t)8 * ((d + 3) & ~3) * 4;
@@ -1212,8 +1221,10 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
             if (occ < 1) occ = 1;
             if (rgrid > sms * occ) rgrid = sms * occ;
         }
+#ifdef B200REC_TC_DIAG
         cudaEvent_t er0 = nullptr, er1 = nullptr;
         if (diag) { cudaEventCreate(&er0); cudaEventCreate(&er1); cudaEventRecord(er0, s); }
+#endif
         const bool staged = getenv("B200REC_RERANK") && atoi(getenv("B200REC_RERANK")) == 2 && (ld & 3) == 0;
         if (staged) {   // experimental (see rerank_staged_kernel); the default stays the validated kernel
             const size_t dp = (size_t)((d + 3) & ~3);
@@ -1230,15 +1241,18 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
                                                     oi + (size_t)r0 * k, os ? os + (size_t)r0 * k : nullptr, redo, redo_n);
         }
         B200_LAUNCH_CHECK();
+#ifdef B200REC_TC_DIAG
         if (diag) {
             cudaEventRecord(er1, s); cudaEventSynchronize(er1);
             float ms = 0.f; cudaEventElapsedTime(&ms, er0, er1);
             fprintf(stderr, "[b200rec tc] rerank kernel rows=%d: %.3f ms\n", nr, ms);
             cudaEventDestroy(er0); cudaEventDestroy(er1);
         }
+#endif
         int n_redo = 0;
         B200_CUDA(cudaMemcpyAsync(&n_redo, redo_n, 4, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaStreamSynchronize(s));
+#ifdef B200REC_TC_DIAG
         if (getenv("B200REC_TC_STATS")) {  // diagnostics only
             std::vector<int32_t> hc((size_t)nr);
             cudaMemcpy(hc.data(), cnt, (size_t)nr * 4, cudaMemcpyDeviceToHost);
@@ -1247,6 +1261,7 @@ int score_topk_tc_impl(const float *U, const float *V, int ld, int d, const int3
             fprintf(stderr, "[b200rec tc] rows=%d redo=%d (cnt<0: %lld) mean_cand=%.1f max_cand=%lld k=%d tiles=%d\n", nr,
                     n_redo, over, nr > over ? (double)tot / (double)(nr - over) : 0.0, mxc, k, p.n_tiles);
         }
+#endif
         if (n_redo > 0) {  // rows the candidate buffer could not hold: exact kernel, then scatter back
             gather_ids_kernel<<<(n_redo + 255) / 256, 256, 0, s>>>(users + r0, redo, n_redo, ruser);
             B200_LAUNCH_CHECK();
