@@ -28,7 +28,7 @@ import numpy as np
 import scipy.sparse as sp
 import torch
 
-__all__ = ["UIRTDataset", "split_by_user_reference", "split_by_user_device"]
+__all__ = ["UIRTDataset", "DeviceIngest", "ingest_device", "split_by_user_reference", "split_by_user_device"]
 
 
 def _read_uirt(path, sep):
@@ -106,6 +106,71 @@ def split_by_user_device(u, t, ratio, split_random=True, generator=None):
     held = torch.zeros(n, dtype=torch.bool, device=dev)
     held[order] = held_sorted
     return held
+
+
+class DeviceIngest:
+    """Result of `ingest_device`: everything stays on the device the arrays came from.  `parts[name]` = (indptr int64
+    [U+1], indices int32 sorted per row) for name in train_data / valid_target / test_target; `raw_users` / `raw_items`
+    map new id -> original id (the inverse of the reference's user2id / item2id, dataset.py:155-162)."""
+
+    def __init__(self, num_users, num_items, raw_users, raw_items, parts, protocol):
+        self.num_users, self.num_items = int(num_users), int(num_items)
+        self.raw_users, self.raw_items, self.parts, self.protocol = raw_users, raw_items, parts, protocol
+
+    def device_csr(self, name):
+        from . import engine
+        if name == "valid_input":
+            name = "train_data"
+        indptr, indices = self.parts[name]
+        return engine.DeviceCSR(indptr, indices, (self.num_users, self.num_items))
+
+    def to_scipy(self, name):
+        indptr, indices = self.parts["train_data" if name == "valid_input" else name]
+        return sp.csr_matrix((np.ones(indices.numel()), indices.cpu().numpy(), indptr.cpu().numpy()),
+                             shape=(self.num_users, self.num_items))
+
+
+def _csr_from_pairs(u, i, num_users, num_items):
+    """Sorted, de-duplicated CSR (implicit ones) from (row, col) pairs - torch sort / unique / bincount on any device."""
+    key = torch.unique(u * num_items + i)                          # sorted; utils/types.py:5-11 + sum_duplicates
+    rows = torch.div(key, num_items, rounding_mode="floor")
+    indptr = torch.zeros(num_users + 1, dtype=torch.int64, device=u.device)
+    indptr[1:] = torch.cumsum(torch.bincount(rows, minlength=num_users), 0)
+    return indptr.contiguous(), (key - rows * num_items).to(torch.int32).contiguous()
+
+
+def ingest_device(users, items, timestamps=None, min_item_per_user=0, min_user_per_item=0, protocol="holdout",
+                  valid_ratio=0.1, test_ratio=0.2, leave_k=1, split_random=True, seed=1234, device=None):
+    """The whole ingest of data/dataset.py:129-199 + data/preprocess.py:9-90 as device array code: ONE
+    pass of the user filter, user ids fixed BEFORE the item filter (:133-158), ONE pass of the item filter, dense re-id
+    in ascending raw-id order, the two per-user splits (the first - sized by valid_ratio / leave_k - becomes TEST, the
+    second VALID: quirk Q6), CSR with sorted int32 columns.  `users` / `items`: raw integer ids of the interactions
+    (any integer tensor / array); implicit feedback (ratings are ones).  No pandas, no Python loop over users; the same
+    code runs on CPU tensors (tests) and CUDA tensors (10M-user catalogues)."""
+    dev = torch.device(device) if device is not None else (users.device if isinstance(users, torch.Tensor) else torch.device("cpu"))
+    u = torch.as_tensor(users).to(dev, torch.int64)
+    i = torch.as_tensor(items).to(dev, torch.int64)
+    t = torch.as_tensor(timestamps).to(dev, torch.float64) if timestamps is not None else torch.ones(u.numel(), dtype=torch.float64, device=dev)
+    _, inv, cnt = torch.unique(u, return_inverse=True, return_counts=True)
+    keep = cnt[inv] >= min_item_per_user
+    u, i, t = u[keep], i[keep], t[keep]
+    raw_users = torch.unique(u)                                     # user2id is built BEFORE the item filter (:155-158)
+    _, inv, cnt = torch.unique(i, return_inverse=True, return_counts=True)
+    keep = cnt[inv] >= min_user_per_item
+    u, i, t = u[keep], i[keep], t[keep]
+    raw_items = torch.unique(i)
+    nu, ni = int(raw_users.numel()), int(raw_items.numel())
+    u = torch.searchsorted(raw_users, u)
+    i = torch.searchsorted(raw_items, i)
+    first, second = (leave_k, leave_k) if protocol == "leave_one_out" else (valid_ratio, test_ratio)
+    g = torch.Generator(device=dev); g.manual_seed(int(seed))
+    held1 = split_by_user_device(u, t, first, split_random, g)
+    rest = torch.nonzero(~held1).flatten()
+    held2 = split_by_user_device(u[rest], t[rest], second, split_random, g)
+    tr, va = rest[~held2], rest[held2]
+    parts = {"train_data": _csr_from_pairs(u[tr], i[tr], nu, ni), "valid_target": _csr_from_pairs(u[va], i[va], nu, ni),
+             "test_target": _csr_from_pairs(u[held1], i[held1], nu, ni)}
+    return DeviceIngest(nu, ni, raw_users, raw_items, parts, protocol)
 
 
 class UIRTDataset:
