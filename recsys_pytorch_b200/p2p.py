@@ -146,6 +146,29 @@ def owner_from_bounds(ids, bounds):
     return np.searchsorted(np.asarray(bounds[1:-1]), np.asarray(ids), side="right")
 
 
+def relabel_columns(indptr, indices, shape, new_id):
+    """Column ids of a CSR renumbered through `new_id` (old -> new) and re-sorted inside every row (the sampler's
+    rejection test binary-searches the row).  Plain tensor code, any device."""
+    dev = indices.device
+    rows = torch.repeat_interleave(torch.arange(shape[0], device=dev), indptr[1:] - indptr[:-1])
+    key, _ = torch.sort(rows * shape[1] + new_id[indices.long()])
+    return (key - rows * shape[1]).to(torch.int32).contiguous()
+
+
+def popularity_order(item_counts, head, seed=0):
+    """(new_order, new_id): the `head` most popular items first, in RANDOM order inside the head; the tail keeps its
+    original relative order.  Identical on every rank for identical (all-reduced) counts and seed."""
+    counts = torch.as_tensor(item_counts)
+    order = torch.argsort(counts, descending=True, stable=True)
+    g = torch.Generator(device="cpu"); g.manual_seed(int(seed))
+    head_items = order[:head][torch.randperm(int(head), generator=g).to(counts.device)] if head else order[:0]
+    tail_items, _ = torch.sort(order[head:])
+    new_order = torch.cat([head_items, tail_items])
+    new_id = torch.empty_like(new_order)
+    new_id[new_order] = torch.arange(new_order.numel(), device=counts.device)
+    return new_order, new_id
+
+
 def relabel_by_popularity(csrs, item_counts, head, seed=0):
     """Renumber the catalogue so that the `head` most popular items are the ids [0, head) - in RANDOM order inside the
     head, and the tail keeps its original relative order.  (Measured, profiles/r02_p2p_notes.md: laying the rows out in
@@ -154,22 +177,11 @@ def relabel_by_popularity(csrs, item_counts, head, seed=0):
     with re-sorted rows, new_id_of_old int64 tensor, counts in the new order).  Pure data preparation, once per dataset;
     every rank computes the same permutation (same histogram, same seed)."""
     counts = torch.as_tensor(item_counts)
-    dev0 = counts.device
-    order = torch.argsort(counts, descending=True, stable=True)
-    g = torch.Generator(device="cpu"); g.manual_seed(int(seed))
-    head_items = order[:head][torch.randperm(int(head), generator=g).to(dev0)] if head else order[:0]
-    tail_items, _ = torch.sort(order[head:])
-    new_order = torch.cat([head_items, tail_items])
-    new_id = torch.empty_like(new_order)
-    new_id[new_order] = torch.arange(new_order.numel(), device=dev0)
+    new_order, new_id = popularity_order(counts, head, seed)
     out = []
     for csr in csrs:
-        dev = csr.indices.device
-        nid = new_id.to(dev)
-        rows = torch.repeat_interleave(torch.arange(csr.shape[0], device=dev), csr.indptr[1:] - csr.indptr[:-1])
-        key = rows * csr.shape[1] + nid[csr.indices.long()]
-        key, _ = torch.sort(key)
-        out.append(engine.DeviceCSR(csr.indptr, (key - rows * csr.shape[1]).to(torch.int32).contiguous(), csr.shape))
+        cols = relabel_columns(csr.indptr, csr.indices, csr.shape, new_id.to(csr.indices.device))
+        out.append(engine.DeviceCSR(csr.indptr, cols, csr.shape))
     return out, new_id, counts[new_order]
 
 

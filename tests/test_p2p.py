@@ -294,3 +294,52 @@ def test_p2p_two_gpus_real_ipc():
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
                           os.path.join(ROOT, "tests", "p2p_worker.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "P2P_WORKER_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+# ------------------------------------------------------------------ CPU: world_size-2 gloo, host logic of the layout ----
+def _gloo_p2p_worker(rank, world, port, q):
+    """What every rank does before the first step (p2p.build_rank), on CPU tensors over gloo: local item histogram ->
+    all-reduce -> identical popularity order, head and balanced tail bounds on every rank; local CSR relabelled with sorted
+    rows; every triple a rank would draw has exactly one owner."""
+    import torch.distributed as dist
+    from recsys_pytorch_b200.p2p import balanced_item_bounds, owner_from_bounds, popularity_order, relabel_columns, uniform_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ni, nu_local, head = 500, 300, 40
+    rng = np.random.default_rng(10 + rank)                      # different users per rank
+    pop = 1.0 / np.random.default_rng(1).permutation(np.arange(1, ni + 1)); pop /= pop.sum()   # one global popularity
+    rows = [np.unique(rng.choice(ni, size=rng.integers(2, 30), p=pop)).astype(np.int64) for _ in range(nu_local)]
+    indptr = torch.zeros(nu_local + 1, dtype=torch.int64); indptr[1:] = torch.tensor(np.cumsum([len(r) for r in rows]))
+    indices = torch.from_numpy(np.concatenate(rows)).to(torch.int32)
+    hist = torch.bincount(indices.long(), minlength=ni)
+    dist.all_reduce(hist)                                        # the one collective of the set-up
+    order, new_id = popularity_order(hist, head, seed=7)
+    bounds = balanced_item_bounds(hist[order], world, head)
+    cols = relabel_columns(indptr, indices, (nu_local, ni), new_id)
+    ok = True
+    for r in range(nu_local):                                    # rows: sorted, same set of items under the renumbering
+        got = cols[indptr[r]:indptr[r + 1]].numpy()
+        ok &= bool((np.diff(got) > 0).all()) and set(got.tolist()) == set(new_id[torch.from_numpy(rows[r])].tolist())
+    ok &= bool((hist[order][:head].min() >= hist[order][head:].max()).item())        # the head IS the most popular items
+    own = owner_from_bounds(np.arange(head, ni), bounds)
+    ok &= bounds[0] == head and bounds[-1] == ni and all((own == r).sum() == bounds[r + 1] - bounds[r] for r in range(world))
+    ok &= uniform_bounds(2 * nu_local, world)[rank + 1] - uniform_bounds(2 * nu_local, world)[rank] == nu_local
+    allb = [None] * world
+    dist.all_gather_object(allb, (bounds, new_id.tolist()))
+    ok &= all(b == allb[0] for b in allb)                        # identical on every rank
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_p2p_setup_is_identical_on_every_rank():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + os.getpid() % 500
+    procs = [ctx.Process(target=_gloo_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok in res), res
