@@ -8,14 +8,14 @@
 //   route   (local)  sample (i, j) for the rank's own batch users from its CSR shard, find owner(i) in the item
 //                    bounds, draw j from owner(i)'s range (i and j stay co-located - the north_star deviation from
 //                    generators.py:178-189: "uniform over the owner shard's non-positives"), and append (u, i, j) to
-//                    the outbox segment of that owner.  Outboxes live in IPC-exported memory of the routing rank.
+//                    the outbox segment of that owner.  Outboxes live in the peer-mapped arena of the routing rank (CUDA VMM / IPC).
 //   barrier          one tiny stream-ordered all-reduce (host side, dist.py) - routes of step s and steps <= s-1 done.
 //   step    (fused)  every rank PULLS the triples routed to it from all outboxes (coalesced peer loads of the ids),
 //                    loads the user row from its HOME rank's table over NVLink (512 B at d=128), the two item rows
 //                    from its own shard (L2-resident: 64 MB per GPU at cfg3), computes x, g, applies the item updates
 //                    with local vector atomics and writes the updated user row back to its home (peer store).
 //                    NVLink traffic: 4*ld bytes per triple per direction for the (W-1)/W remote fraction - half of a
-//                    replicated-table all-gather of user deltas, 1/W-th... of its receive volume.
+//                    replicated-table all-gather of user deltas.
 //
 // Fixed-triple parity mode (SURVEY 8(e) bullet 2): with given (pos, neg) the negative may live on another shard; the
 // step kernel then resolves V[j] through the peer table too (peer load + peer vector atomic), so ANY triple list gives
