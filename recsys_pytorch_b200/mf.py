@@ -387,6 +387,8 @@ class MF(BaseModel):
             bu = eval_users[st:st + test_batch_size]
             chunk = engine.predict_dense(U, V, d, self._i32(bu, self.device), mask)
             pred_matrix[bu] = chunk.cpu().numpy()
+        if hasattr(eval_pos, "nonzero"):                           # MF.py:130 masks EVERY row of eval_pos, evaluated or not
+            pred_matrix[eval_pos.nonzero()] = float("-inf")
         return pred_matrix
 
     def predict_topk_device(self, eval_users, eval_pos, k, want_scores=False):

@@ -399,7 +399,10 @@ def test_plugin_fit_reference_compat_reaches_reference_ndcg(golden, dev):
     pred = m.predict(np.arange(ds.num_users), ds.valid_input, 1024)
     assert pred.shape == (ds.num_users, ds.num_items) and pred.dtype == np.float64
     assert np.isinf(pred[ds.train_data.nonzero()]).all()
-    class Legacy:                                        # a model WITHOUT predict_topk_device -> reference sequence
+    part = m.predict(np.arange(10), ds.valid_input, 1024)         # MF.py:130 masks every row, evaluated or not
+    assert np.isinf(part[ds.train_data.nonzero()]).all() and np.allclose(part[:10], pred[:10], rtol=1e-6, atol=0)
+    assert np.isin(part[10:], [0.0, -np.inf]).all()
+    class Legacy:                                       # a model WITHOUT predict_topk_device -> reference sequence
         device = dev
         def eval(self): pass
         def predict(self, u, p, b): return m.predict(u, p, b)
