@@ -116,6 +116,31 @@ def test_oracle_lightgcn(golden):
 
 
 # ---- host logic ---------------------------------------------------------------
+def test_build_norm_adj_on_cpu_tensors_matches_reference_graph(golden):
+    """lightgcn.build_norm_adj is plain torch array code: run on CPU tensors it must give the adjacency the reference's
+    getSparseGraph built (models/LightGCN.py:228-267; golden from oracle/make_golden.py::lightgcn) - same pattern, values
+    within 2 ulp (pow(-0.5) rounding).  The `-m gpu` twin runs the same function on CUDA tensors."""
+    import types
+    import torch
+    from recsys_pytorch_b200.lightgcn import build_norm_adj
+    g, ml = golden["lightgcn_ml100k"], golden["ml100k"]
+    nu, ni = int(ml["num_users"]), int(ml["num_items"])
+    csr = types.SimpleNamespace(indptr=torch.from_numpy(ml["train_indptr"].astype(np.int64)),
+                                indices=torch.from_numpy(ml["train_indices"].astype(np.int32)), shape=(nu, ni),
+                                nnz=int(len(ml["train_indices"])))
+    indptr, cols, vals = build_norm_adj(csr)
+    assert indptr.dtype == torch.int64 and cols.dtype == torch.int32 and vals.dtype == torch.float32
+    assert cols.numel() == int(g["adj_nnz"])
+    order = np.lexsort((g["adj_cols"], g["adj_rows"]))
+    np.testing.assert_array_equal(cols.numpy(), g["adj_cols"][order])
+    np.testing.assert_allclose(vals.numpy(), g["adj_vals"][order], rtol=5e-7, atol=0)
+    np.testing.assert_array_equal(np.diff(indptr.numpy()), np.bincount(g["adj_rows"], minlength=nu + ni))
+    # symmetric: the backward pass reuses the forward propagation on that ground
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vals.numpy(), cols.numpy(), indptr.numpy()), shape=(nu + ni, nu + ni))
+    assert abs(A - A.T).max() == 0.0
+
+
 def test_reference_sampler_restatement(golden):
     """sampler='reference' replays data/generators.py:168-224 draw for draw (same numpy seed -> same batches)."""
     import random
@@ -343,3 +368,38 @@ def test_ngcf_oracle_matches_reference_forward_and_autograd(golden):
         np.testing.assert_allclose(dbg[k], g["db_gc_%d" % k], rtol=2e-4, atol=2e-7)
         np.testing.assert_allclose(dWb[k], g["dW_bi_%d" % k], rtol=2e-4, atol=2e-7)
         np.testing.assert_allclose(dbb[k], g["db_bi_%d" % k], rtol=2e-4, atol=2e-7)
+
+
+def test_synthetic_interactions_recipe_on_cpu():
+    """synthetic.make_interactions_raw (SURVEY 8(d) recipe; plain torch, here on CPU - the host arm of bench.py builds its
+    sample of the dataset with it): sorted duplicate-free rows, every user keeps >= 1 train and >= 1 target item, train and
+    target are disjoint, ~20 % held out, degrees inside [dmin, dmax], Zipf popularity, and shards drawn with different
+    user seeds but one `item_seed` agree on which items are popular (what the multi-GPU layouts rely on)."""
+    import torch
+    from recsys_pytorch_b200 import synthetic
+    nu, ni = 4000, 3000
+    (tp, ti), (vp, vi) = synthetic.make_interactions_raw(nu, ni, seed=11, device="cpu")
+    assert tp.dtype == torch.int64 and ti.dtype == torch.int32 and tp.numel() == nu + 1 and vp.numel() == nu + 1
+    tp, ti, vp, vi = (x.numpy() for x in (tp, ti, vp, vi))
+    assert tp[0] == 0 and vp[0] == 0 and tp[-1] == len(ti) and vp[-1] == len(vi)
+    dt, dv = np.diff(tp), np.diff(vp)
+    assert dt.min() >= 1 and dv.min() >= 1
+    tot = dt + dv
+    assert tot.max() <= 1000 and tot.min() >= 2 and np.median(tot) > 15           # clip(lognormal(3.5, .8), 10, 1000) minus in-row duplicates
+    assert np.all(dv == np.minimum(np.maximum(np.ceil(tot * 0.2), 1), tot - 1))    # ceil(20 %) of every row, >= 1, train keeps >= 1
+    for r in range(0, nu, 37):
+        a, b = ti[tp[r]:tp[r + 1]], vi[vp[r]:vp[r + 1]]
+        assert np.all(np.diff(a) > 0) and np.all(np.diff(b) > 0) and len(np.intersect1d(a, b)) == 0
+        assert a.min() >= 0 and a.max() < ni
+    pop = np.bincount(np.concatenate([ti, vi]), minlength=ni)
+    assert pop.max() > 20 * np.median(pop)                                           # Zipf(1) head
+    # one catalogue popularity for shards with different users
+    (ap, ai), _ = synthetic.make_interactions_raw(nu, ni, seed=1, device="cpu", item_seed=99)
+    (bp, bi), _ = synthetic.make_interactions_raw(nu, ni, seed=2, device="cpu", item_seed=99)
+    assert not np.array_equal(ai.numpy()[:200], bi.numpy()[:200])
+    ha, hb = np.bincount(ai.numpy(), minlength=ni), np.bincount(bi.numpy(), minlength=ni)
+    top_a, top_b = set(np.argsort(-ha)[:30].tolist()), set(np.argsort(-hb)[:30].tolist())
+    assert len(top_a & top_b) >= 24
+    # deterministic in the seed
+    (cp, ci), _ = synthetic.make_interactions_raw(nu, ni, seed=1, device="cpu", item_seed=99)
+    assert torch.equal(ap, cp) and torch.equal(ai, ci)
