@@ -102,8 +102,7 @@ def bpr_step(U, V, d, users, pos=None, neg=None, csr: DeviceCSR | None = None, l
 
 def pointwise_step(U, V, d, users, items, ratings, loss_func="ce", lr=0.0, reg=0.0, sink=SINK_UPDATE, gU=None, gV=None,
                    loss_sum=None, inv_batch=0.0):
-    """models/MF.py:63-68 in pointwise mode (MF.py:101-102) as one fused kernel (see b200rec_pointwise_step).
-    Not yet validated on hardware."""
+    """models/MF.py:63-68 in pointwise mode (MF.py:101-102) as one fused kernel (see b200rec_pointwise_step)."""
     require_cuda(U, "U", torch.float32); require_cuda(V, "V", torch.float32)
     ratings = require_cuda(ratings, "ratings", torch.float32)
     check(_lib.lib().b200rec_pointwise_step(

@@ -403,3 +403,25 @@ def test_synthetic_interactions_recipe_on_cpu():
     # deterministic in the seed
     (cp, ci), _ = synthetic.make_interactions_raw(nu, ni, seed=1, device="cpu", item_seed=99)
     assert torch.equal(ap, cp) and torch.equal(ai, ci)
+
+
+def test_oracle_at_cfg2_row_width_and_batch_regime(golden):
+    """SURVEY 8(c) golden (iii): d = 128, ONE 65,536-triple batch with a Zipf head (hottest item 7,164 times) through the
+    reference's forward / process_one_batch / autograd / SGD swap (oracle/make_golden_cfg2shape.py).  The numpy oracle
+    reproduces scores, loss, the sampled dense-gradient rows and the post-step rows; its fp64 accumulation differs from the
+    reference's fp32 `embedding_dense_backward` by < 1e-5 of the gradient scale."""
+    from oracle.make_golden_cfg2shape import LR, inputs
+    g = golden["cfg2shape_bpr"]
+    U0, V0, u, i, j, su, si = inputs(int(g["seed"]))
+    assert np.array_equal(su, g["sample_users"]) and np.array_equal(si, g["sample_items"])     # same regenerated inputs
+    dU, dV, _, x = O.bpr_grads(U0, V0, u, i, j)
+    loss, _ = O.bpr_loss(U0, V0, u, i, j)
+    np.testing.assert_allclose(x, g["x"], rtol=1e-5, atol=5e-7)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    for got, ref in ((dU[su], g["dU_rows"]), (dV[si], g["dV_rows"])):
+        np.testing.assert_allclose(got, ref, rtol=2e-5, atol=1e-5 * np.abs(ref).max())
+    assert abs(np.abs(dU.astype(np.float64)).sum() / float(g["dU_abs_sum"]) - 1) < 1e-6          # the unsampled rows too
+    assert abs(np.abs(dV.astype(np.float64)).sum() / float(g["dV_abs_sum"]) - 1) < 1e-6
+    Ur, Vr, _ = O.sgd_step(U0, V0, u, i, j, float(LR), 0.0)
+    np.testing.assert_allclose(Ur[su], g["U_rows"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(Vr[si], g["V_rows"], rtol=2e-6, atol=1e-7)
