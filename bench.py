@@ -413,6 +413,27 @@ def _cpu_train_legs(c, batches_by_size, steps, warmup, table_sizes):
     return legs
 
 
+def cpu_lightgcn_leg(small=False, nu=25_000, ni=100_000, d=64, L=3):
+    """BASELINE.md section 3 row 4 on a bounded sample: the reference's LightGCN propagation (models/LightGCN.py:174-202,
+    restated on the same torch ops: L x torch.sparse.mm + stack + mean; autograd backward) on the adjacency of the FIRST
+    `nu` users of the cfg4 recipe over the full 100k-item catalogue, d = 64, L = 3."""
+    from oracle import torch_port as TP
+    from recsys_pytorch_b200 import synthetic
+    if small:
+        nu, ni = 5_000, 20_000
+    (tp, ti), _ = synthetic.make_interactions_raw(nu, ni, seed=2020, device="cpu")
+    t0 = time.perf_counter()
+    G = TP.lightgcn_graph(tp.numpy(), ti.numpy(), nu, ni)
+    t_graph = time.perf_counter() - t0
+    fw, fb = TP.time_lightgcn(G, d, L, reps=2)
+    nnzA, N = int(G._nnz()), nu + ni
+    bytes_layer = nnzA * (8 + 4 * d) + N * 4 * d                      # same algorithmic model as the GPU leg
+    return {"sample": "adjacency of the first %d users x %d items of the cfg4 recipe (nnz %d), d=%d, L=%d; median of 2"
+                      % (nu, ni, nnzA, d, L),
+            "graph_build_s": t_graph, "propagate_s": fw, "s_per_layer": fw / L, "propagate_fwd_bwd_s": fw + fb,
+            "achieved_gbs": bytes_layer * L / fw / 1e9, "ns_per_nnz_layer": fw / L / nnzA * 1e9}
+
+
 def cpu_baseline_leg(c, args, gpu_triples=None, steps=3, warmup=1):
     """Bounded sample on the host cores: the reference's own step (dense autograd grads + dense Adam over all U+I
     rows, models/MF.py:64-68) at the same table sizes, on the (u, i, j) batches the GPU engine itself sampled
@@ -421,6 +442,11 @@ def cpu_baseline_leg(c, args, gpu_triples=None, steps=3, warmup=1):
     cores = _host_threads()
     legs = _cpu_train_legs(c, gpu_triples, steps, warmup, (c["num_users"], c["num_items"]))
     head = legs["adam_b65536"] if "adam_b65536" in legs else next(iter(legs.values()))
+    if not getattr(args, "no_legs", False):
+        try:
+            legs["lightgcn_cfg4_sample"] = cpu_lightgcn_leg(small=bool(args.small))
+        except Exception as e:                                       # pragma: no cover
+            legs["lightgcn_cfg4_sample"] = {"error": repr(e)[:300]}
     return {"value": head["triples_per_s"], "unit": "triples/s", "cores": cores, "kind": "port", "legs": legs,
             "sample": "%d timed steps per leg of the reference step (MF.py:64-68 restated on torch CPU: dense autograd "
                       "grads + dense optimiser sweep over %d rows) on the very (u,i,j) batches the device sampler "
@@ -444,6 +470,10 @@ def run_reference(args):
     batches = {big: _cpu_batches(c, tr, big, n_b, 1), 256: _cpu_batches(c, tr, 256, n_b, 2)}
     legs = _cpu_train_legs(c, batches, args.steps, args.warmup, (c["num_users"], c["num_items"]))
     head = legs["adam_b%d" % big]
+    try:
+        legs["lightgcn_cfg4_sample"] = cpu_lightgcn_leg(small=bool(args.small))
+    except Exception as e:                                           # pragma: no cover
+        legs["lightgcn_cfg4_sample"] = {"error": repr(e)[:300]}
     # evaluation leg: the chunked restatement (MF.py:109-112 + in-chunk -inf mask + func.h top-k + holdout.h) on 8
     # chunks of 1024 users
     fns, kind = TP.native_eval_lib()

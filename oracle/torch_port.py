@@ -100,3 +100,56 @@ def time_train(model, batches, warmup=1):
     for b in batches[warmup:]:
         model.train_step(*b)
     return (time.perf_counter() - t0) / max(len(batches) - warmup, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LightGCN propagation (BASELINE configs[3]) - same torch ops as the reference
+# ---------------------------------------------------------------------------------------------------------------
+def lightgcn_graph(indptr, indices, num_users, num_items):
+    """The tensor models/LightGCN.py:228-267 ends with: A_hat = D^-1/2 [[0,R],[R^T,0]] D^-1/2 as a coalesced fp32
+    torch sparse COO matrix of size (U+I)^2 (:259-266 `_convert_sp_mat_to_sp_tensor` + `.coalesce()`), built here
+    from the train CSR without the scipy dok/lil detour."""
+    indptr = np.asarray(indptr, np.int64); indices = np.asarray(indices, np.int64)
+    rows = np.repeat(np.arange(num_users, dtype=np.int64), np.diff(indptr))
+    deg_u = np.diff(indptr).astype(np.float64)
+    deg_i = np.bincount(indices, minlength=num_items).astype(np.float64)
+    with np.errstate(divide="ignore"):
+        du, di = np.power(deg_u, -0.5), np.power(deg_i, -0.5)          # :249-250
+    du[np.isinf(du)] = 0.0; di[np.isinf(di)] = 0.0
+    v = ((du[rows].astype(np.float32) * np.float32(1.0)) * di[indices].astype(np.float32)).astype(np.float32)
+    r = np.concatenate([rows, indices + num_users]); c = np.concatenate([indices + num_users, rows])
+    n = num_users + num_items
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                                # torch's "sparse invariant checks" notice
+        g = torch.sparse_coo_tensor(torch.from_numpy(np.stack([r, c])), torch.from_numpy(np.concatenate([v, v])), (n, n))
+        return g.coalesce()
+
+
+def lightgcn_embedding(graph, all_emb, num_layers):
+    """models/LightGCN.py:174-202 (node_dropout = 0, split = False): L sparse.mm's, stack, mean over layers."""
+    embs = [all_emb]
+    for _ in range(num_layers):
+        all_emb = torch.sparse.mm(graph, all_emb)                      # :196
+        embs.append(all_emb)
+    return torch.mean(torch.stack(embs, dim=1), dim=1)                 # :198-200
+
+
+def time_lightgcn(graph, d, num_layers, reps=3):
+    """(seconds per forward propagation, seconds per forward + backward) - the reference's autograd walks the same L
+    sparse.mm's backwards; median of `reps` after one warm-up."""
+    n = graph.shape[0]
+    E = (torch.randn(n, d) * 0.01).requires_grad_(True)
+    fw, fb = [], []
+    for r in range(reps + 1):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            lightgcn_embedding(graph, E, num_layers)
+        t1 = time.perf_counter()
+        out = lightgcn_embedding(graph, E, num_layers)
+        out.sum().backward()
+        t2 = time.perf_counter()
+        E.grad = None
+        if r:
+            fw.append(t1 - t0); fb.append(t2 - t1)
+    return float(np.median(fw)), float(np.median(fb))

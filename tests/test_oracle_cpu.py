@@ -425,3 +425,23 @@ def test_oracle_at_cfg2_row_width_and_batch_regime(golden):
     Ur, Vr, _ = O.sgd_step(U0, V0, u, i, j, float(LR), 0.0)
     np.testing.assert_allclose(Ur[su], g["U_rows"], rtol=2e-6, atol=1e-7)
     np.testing.assert_allclose(Vr[si], g["V_rows"], rtol=2e-6, atol=1e-7)
+
+
+def test_torch_port_lightgcn_matches_reference_golden(golden):
+    """oracle/torch_port.py's LightGCN restatement (the timed CPU baseline of bench.py's cfg4 leg) against what the
+    reference's getSparseGraph / _lightgcn_embedding produced on ml-100k."""
+    import torch
+    from oracle import torch_port as TP
+    g, ml = golden["lightgcn_ml100k"], golden["ml100k"]
+    nu, ni = int(ml["num_users"]), int(ml["num_items"])
+    G = TP.lightgcn_graph(ml["train_indptr"], ml["train_indices"], nu, ni)
+    assert G._nnz() == int(g["adj_nnz"])
+    order = np.lexsort((g["adj_cols"], g["adj_rows"]))
+    idx = G.indices().numpy()
+    np.testing.assert_array_equal(idx[0], g["adj_rows"][order]); np.testing.assert_array_equal(idx[1], g["adj_cols"][order])
+    np.testing.assert_allclose(G.values().numpy(), g["adj_vals"][order], rtol=5e-7, atol=0)
+    out = TP.lightgcn_embedding(G, torch.from_numpy(np.concatenate([g["U0"], g["V0"]])), 3).numpy()
+    np.testing.assert_allclose(out[:nu], g["prop_U"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(out[nu:], g["prop_V"], rtol=1e-5, atol=1e-8)
+    fw, fb = TP.time_lightgcn(G, 16, 3, reps=1)
+    assert fw > 0 and fb > 0
