@@ -434,6 +434,31 @@ def cpu_lightgcn_leg(small=False, nu=25_000, ni=100_000, d=64, L=3):
             "achieved_gbs": bytes_layer * L / fw / 1e9, "ns_per_nnz_layer": fw / L / nnzA * 1e9}
 
 
+def cpu_cfg5_leg(small=False, num_items=1_000_000, d=128, k=100, n_chunks=4, chunk_users=128):
+    """BASELINE.md section 3 row 5 on a bounded sample: the reference's predict() cannot allocate [U, I] at 10M x 1M, so
+    its chunked restatement is timed - predict_batch_users (models/MF.py:109-112) + in-chunk -inf mask (:130) + the
+    reference's own C++ top-k (func.h:12-31) + holdout metrics (holdout.h:20-103) - on `n_chunks` chunks of
+    `chunk_users` users against the full 1M-item catalogue, d = 128, K = 100."""
+    from oracle import torch_port as TP
+    from recsys_pytorch_b200 import synthetic
+    if small:
+        num_items, n_chunks = 50_000, 2
+    n = n_chunks * chunk_users
+    (tp, ti), (vp, vi) = synthetic.make_interactions_raw(n, num_items, seed=77, device="cpu", item_seed=2020)
+    tp, ti, vp, vi = (x.numpy() for x in (tp, ti, vp, vi))
+    fns, kind = TP.native_eval_lib()
+    model = TP.RefMF(n, num_items, d, init_std=0.1)
+    TP.eval_chunk(model, np.arange(min(8, n)), tp, ti, vp, vi, k, fns)                   # warm-up (page in, thread pool)
+    t0 = time.perf_counter(); pairs = 0
+    for ch in range(n_chunks):
+        pairs += TP.eval_chunk(model, np.arange(ch * chunk_users, (ch + 1) * chunk_users), tp, ti, vp, vi, k, fns)[0]
+    sec = time.perf_counter() - t0
+    return {"sample": "%d chunks of %d users x %d items, d=%d, K=%d (chunked predict + mask + top-k + holdout metrics)"
+                      % (n_chunks, chunk_users, num_items, d, k),
+            "scored_pairs_per_sec": pairs / sec, "seconds": sec, "native": kind,
+            "projected_full_sweep_s": 10_000_000 * float(num_items) / (pairs / sec)}
+
+
 def cpu_baseline_leg(c, args, gpu_triples=None, steps=3, warmup=1):
     """Bounded sample on the host cores: the reference's own step (dense autograd grads + dense Adam over all U+I
     rows, models/MF.py:64-68) at the same table sizes, on the (u, i, j) batches the GPU engine itself sampled
@@ -447,6 +472,10 @@ def cpu_baseline_leg(c, args, gpu_triples=None, steps=3, warmup=1):
             legs["lightgcn_cfg4_sample"] = cpu_lightgcn_leg(small=bool(args.small))
         except Exception as e:                                       # pragma: no cover
             legs["lightgcn_cfg4_sample"] = {"error": repr(e)[:300]}
+        try:
+            legs["eval_cfg5_sample"] = cpu_cfg5_leg(small=bool(args.small))
+        except Exception as e:                                       # pragma: no cover
+            legs["eval_cfg5_sample"] = {"error": repr(e)[:300]}
     return {"value": head["triples_per_s"], "unit": "triples/s", "cores": cores, "kind": "port", "legs": legs,
             "sample": "%d timed steps per leg of the reference step (MF.py:64-68 restated on torch CPU: dense autograd "
                       "grads + dense optimiser sweep over %d rows) on the very (u,i,j) batches the device sampler "
@@ -474,6 +503,10 @@ def run_reference(args):
         legs["lightgcn_cfg4_sample"] = cpu_lightgcn_leg(small=bool(args.small))
     except Exception as e:                                           # pragma: no cover
         legs["lightgcn_cfg4_sample"] = {"error": repr(e)[:300]}
+    try:
+        legs["eval_cfg5_sample"] = cpu_cfg5_leg(small=bool(args.small))
+    except Exception as e:                                           # pragma: no cover
+        legs["eval_cfg5_sample"] = {"error": repr(e)[:300]}
     # evaluation leg: the chunked restatement (MF.py:109-112 + in-chunk -inf mask + func.h top-k + holdout.h) on 8
     # chunks of 1024 users
     fns, kind = TP.native_eval_lib()
