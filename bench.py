@@ -322,6 +322,26 @@ def run_b200(args):
             cpu_base = cpu_baseline_leg(c, args, gpu_triples)
         except Exception as e:                                       # pragma: no cover - reported, never fatal
             cpu_base = {"value": None, "unit": "triples/s", "cores": None, "kind": "port", "error": repr(e)[:300]}
+        # scores and loss of the SAME (u,i,j) batch on the trained tables, CUDA kernel vs the
+        # reference's torch CPU ops (models/MF.py:38-42,99-105)
+        try:
+            u_, p_, n_ = gpu_triples[max(gpu_triples)][0]
+            xg = torch.empty(u_.numel(), dtype=torch.float32, device=dev)
+            lg = torch.zeros(1, dtype=torch.float64, device=dev)
+            engine.bpr_step(model.U, model.V, d, *(t.to(dev, torch.int32) for t in (u_, p_, n_)), sink=_lib.SINK_NONE,
+                            loss_sum=lg, x_out=xg)
+            Uc, Vc = model.U[:, :d].cpu(), model.V[:, :d].cpu()
+            xc = torch.sum(Uc[u_] * Vc[p_], 1) - torch.sum(Uc[u_] * Vc[n_], 1)
+            lc = float(-torch.sigmoid(xc).log().mean())
+            cpu_base["parity_same_triples"] = {
+                "triples": int(u_.numel()), "max_abs_err_score_diff": float((xg.cpu() - xc).abs().max()),
+                "max_abs_score_diff": float(xc.abs().max()), "loss_gpu": float(lg.item()) / u_.numel(), "loss_cpu": lc,
+                "abs_err_loss": abs(float(lg.item()) / u_.numel() - lc),
+                "what": "x = s(u,i) - s(u,j) and -mean log sigmoid(x) of one device-sampled batch on the tables as trained "
+                        "by this run: fused kernel (forward-only sink) vs torch CPU fp32"}
+        except Exception as e:                                       # pragma: no cover
+            if isinstance(cpu_base, dict):
+                cpu_base["parity_same_triples"] = {"error": repr(e)[:300]}
     # secondary workloads: a failure there is reported under its key, it never costs the headline line
     legs = {}
     if not args.no_legs:
