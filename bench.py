@@ -333,10 +333,11 @@ def run_b200(args):
             Uc, Vc = model.U[:, :d].cpu(), model.V[:, :d].cpu()
             xc = torch.sum(Uc[u_] * Vc[p_], 1) - torch.sum(Uc[u_] * Vc[n_], 1)
             lc = float(-torch.sigmoid(xc).log().mean())
+            fin = lambda v: float(v) if np.isfinite(v) else None     # json has no inf / nan
             cpu_base["parity_same_triples"] = {
-                "triples": int(u_.numel()), "max_abs_err_score_diff": float((xg.cpu() - xc).abs().max()),
-                "max_abs_score_diff": float(xc.abs().max()), "loss_gpu": float(lg.item()) / u_.numel(), "loss_cpu": lc,
-                "abs_err_loss": abs(float(lg.item()) / u_.numel() - lc),
+                "triples": int(u_.numel()), "max_abs_err_score_diff": fin((xg.cpu() - xc).abs().max()),
+                "max_abs_score_diff": fin(xc.abs().max()), "loss_gpu": fin(lg.item() / u_.numel()), "loss_cpu": fin(lc),
+                "abs_err_loss": fin(abs(lg.item() / u_.numel() - lc)),
                 "what": "x = s(u,i) - s(u,j) and -mean log sigmoid(x) of one device-sampled batch on the tables as trained "
                         "by this run: fused kernel (forward-only sink) vs torch CPU fp32"}
         except Exception as e:                                       # pragma: no cover
