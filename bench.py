@@ -333,7 +333,7 @@ def run_b200(args):
             Uc, Vc = model.U[:, :d].cpu(), model.V[:, :d].cpu()
             xc = torch.sum(Uc[u_] * Vc[p_], 1) - torch.sum(Uc[u_] * Vc[n_], 1)
             lc = float(-torch.sigmoid(xc).log().mean())
-            fin = lambda v: float(v) if np.isfinite(v) else None     # json has no inf / nan
+            fin = lambda v: float(v) if np.isfinite(float(v)) else None   # json has no inf / nan
             cpu_base["parity_same_triples"] = {
                 "triples": int(u_.numel()), "max_abs_err_score_diff": fin((xg.cpu() - xc).abs().max()),
                 "max_abs_score_diff": fin(xc.abs().max()), "loss_gpu": fin(lg.item() / u_.numel()), "loss_cpu": fin(lc),
