@@ -445,3 +445,69 @@ def test_torch_port_lightgcn_matches_reference_golden(golden):
     np.testing.assert_allclose(out[nu:], g["prop_V"], rtol=1e-5, atol=1e-8)
     fw, fb = TP.time_lightgcn(G, 16, 3, reps=1)
     assert fw > 0 and fb > 0
+
+
+# ---- randomised differential pin: the C restatement vs the reference's OWN C++ (oracle/_ref, compiled from
+# /root/reference/evaluation/backend/cython/include where it lies; the built library travels to the GPU box) ----
+def _ref_native():
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_eval.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_eval.so not built (needs /root/reference at build time)")
+    from oracle.ref_harness import RefNative
+    return RefNative()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_topk_differential_vs_reference_cpp(oracle_c, seed):
+    """func.h:12-31 vs oracle/eval_oracle.c on random blocks: tie-free scores -> identical ids (every k up to the row
+    length, masked -inf columns, negative and subnormal values); tied scores -> identical score at every rank."""
+    ref = _ref_native()
+    rng = np.random.default_rng(100 + seed)
+    rows, cols = int(rng.integers(1, 40)), int(rng.integers(1, 3000))
+    vals = (rng.permutation(rows * cols).astype(np.float64) - rows * cols / 2).reshape(rows, cols)
+    S = (vals * rng.choice([1e-3, 1.0, 37.5, 1e-42])).astype(np.float32)                     # 1e-42: fp32 subnormals
+    if len(np.unique(S)) < S.size:                                                            # rounding produced ties
+        S = vals.astype(np.float32)
+    n_mask = int(rng.integers(0, max(cols // 3, 1)))
+    for r in range(rows):
+        S[r, rng.choice(cols, n_mask, replace=False)] = -np.inf
+    for k in sorted({1, min(5, cols), min(100, cols), max(cols - n_mask, 1)}):
+        np.testing.assert_array_equal(oracle_c.topk(S, k), ref.topk(S, k))
+    # ties: quantised scores
+    T = np.round(rng.standard_normal((rows, cols)) * 3).astype(np.float32)
+    k = min(20, cols)
+    a, b = oracle_c.topk(T, k).astype(np.int64), ref.topk(T, k).astype(np.int64)
+    np.testing.assert_array_equal(np.take_along_axis(T, a, 1), np.take_along_axis(T, b, 1))
+    assert all(len(set(row)) == k for row in a.tolist())                                     # k distinct items per row
+    if cols > 1:                                                                              # documented tie order: id ascending
+        sc = np.take_along_axis(T, a, 1)
+        same = sc[:, 1:] == sc[:, :-1]
+        assert np.all(a[:, 1:][same] > a[:, :-1][same])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_metrics_differential_vs_reference_cpp(oracle_c, seed):
+    """holdout.h:20-103 / loo.h:20-85 vs oracle/eval_oracle.c and the numpy twin, bit for bit, on random rankings: truth
+    sets of 1 .. 3K items, hits anywhere or nowhere, K lists with K = 1 and K = max_k."""
+    ref = _ref_native()
+    rng = np.random.default_rng(500 + seed)
+    users, items = int(rng.integers(1, 300)), int(rng.integers(60, 5000))
+    max_k = int(rng.integers(1, 51))
+    ks = np.array(sorted(set([1, max_k] + rng.integers(1, max_k + 1, 3).tolist())), np.int32)
+    topk = np.stack([rng.choice(items, max_k, replace=False) for _ in range(users)]).astype(np.int32)
+    truths = []
+    for u in range(users):
+        n = int(rng.integers(1, 3 * max_k + 2))
+        t = rng.choice(items, min(n, items), replace=False)
+        if rng.random() < 0.5:                                                               # plant hits at random ranks
+            m = min(len(t), 3, max_k)
+            t[:m] = topk[u, rng.choice(max_k, m, replace=False)]
+        truths.append(np.unique(t).astype(np.int32))
+    want = ref.holdout(topk, truths, ks)
+    np.testing.assert_array_equal(oracle_c.holdout(topk, truths, ks), want)
+    np.testing.assert_array_equal(O.holdout_metrics(topk, truths, ks), want)
+    assert np.isfinite(want).all() and want.min() >= 0 and want.max() <= 1.0 + 1e-6
+    loo_truths = [t[:1] for t in truths]
+    want = ref.loo(topk, loo_truths, ks)
+    np.testing.assert_array_equal(oracle_c.loo(topk, loo_truths, ks), want)
+    np.testing.assert_array_equal(O.loo_metrics(topk, loo_truths, ks), want)
