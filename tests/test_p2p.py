@@ -285,14 +285,17 @@ def test_p2p_same_data_ndcg_flat_across_world_sizes(dev, head, reduce, tol):
 
 
 @pytest.mark.gpu
-def test_p2p_two_gpus_real_ipc():
-    """Real thing: 2 processes, 2 GPUs, CUDA IPC peer mappings, NCCL barrier (tests/p2p_worker.py)."""
+@pytest.mark.parametrize("arena", ["ipc", "symm"])
+def test_p2p_two_gpus_real_ipc(arena):
+    """Real thing: 2 processes, 2 GPUs, real peer mappings, NCCL barrier (tests/p2p_worker.py) - over legacy CUDA-IPC
+    handles (`ipc`) and over the CUDA-VMM arena of torch's symmetric memory (`symm`, what bench.py --gpus N uses)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    port = 29600 + os.getpid() % 300
+    port = 29600 + os.getpid() % 300 + (7 if arena == "symm" else 0)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
-                          os.path.join(ROOT, "tests", "p2p_worker.py")], capture_output=True, text=True, timeout=600)
+                          os.path.join(ROOT, "tests", "p2p_worker.py")], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, B200REC_P2P_ARENA=arena))
     assert out.returncode == 0 and "P2P_WORKER_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
