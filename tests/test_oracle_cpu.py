@@ -511,3 +511,49 @@ def test_oracle_metrics_differential_vs_reference_cpp(oracle_c, seed):
     want = ref.loo(topk, loo_truths, ks)
     np.testing.assert_array_equal(oracle_c.loo(topk, loo_truths, ks), want)
     np.testing.assert_array_equal(O.loo_metrics(topk, loo_truths, ks), want)
+
+
+# ---- the reference-side binding INTEGRATION.md shows (Option A) actually builds and binds ----
+def test_integration_cython_shim_builds_and_binds(built_lib, tmp_path):
+    """Extract the Cython shim from INTEGRATION.md section 2 (the maintainer's replacement of
+    evaluation/backend/cython/func.pyx:8-25), build it against include/b200rec.h + libb200rec.so, import it and call it.
+    On a box with a GPU it must return the top-k; without one the library's error must surface as RuntimeError - never a
+    silent CPU answer."""
+    import subprocess
+    import sys
+    import textwrap
+    pytest.importorskip("Cython")
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"```cython\n(.*?)```", doc, re.S)
+    assert m, "INTEGRATION.md lost its cython block"
+    (tmp_path / "func_b200.pyx").write_text(m.group(1))
+    libdir = os.path.join(ROOT, "recsys_pytorch_b200")
+    (tmp_path / "setup.py").write_text(textwrap.dedent(f"""
+        from setuptools import setup, Extension
+        from Cython.Build import cythonize
+        import numpy as np
+        ext = Extension("func_b200", ["func_b200.pyx"], language="c++", include_dirs=[np.get_include(), r"{ROOT}/include"],
+                        library_dirs=[r"{libdir}"], libraries=["b200rec"], runtime_library_dirs=[r"{libdir}"],
+                        extra_compile_args=["-std=c++11", "-w"])
+        setup(ext_modules=cythonize([ext], language_level=3, quiet=True), script_args=["build_ext", "--inplace", "-q"])
+    """))
+    out = subprocess.run([sys.executable, "setup.py"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    probe = textwrap.dedent("""
+        import numpy as np, func_b200
+        S = np.random.default_rng(0).standard_normal((7, 50)).astype(np.float32)
+        try:
+            top = func_b200.predict_topk_cy(S, 5)
+        except RuntimeError as e:
+            print("RAISED", str(e)[:200])
+        else:
+            ref = np.argsort(-S, axis=1, kind="stable")[:, :5]
+            print("OK" if np.array_equal(top, ref) else "WRONG")
+    """)
+    out = subprocess.run([sys.executable, "-c", probe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    import torch
+    if torch.cuda.is_available():
+        assert out.stdout.strip() == "OK", out.stdout
+    else:
+        assert out.stdout.startswith("RAISED") and "CUDA" in out.stdout.upper(), out.stdout
