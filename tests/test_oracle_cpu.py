@@ -557,3 +557,69 @@ def test_integration_cython_shim_builds_and_binds(built_lib, tmp_path):
         assert out.stdout.strip() == "OK", out.stdout
     else:
         assert out.stdout.startswith("RAISED") and "CUDA" in out.stdout.upper(), out.stdout
+
+
+# ---- ABI: the ctypes mirrors of the argument structs against the C header, field by field ----
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """Every field of BprArgs / P2PRouteArgs / P2PStepArgs (recsys_pytorch_b200/_lib.py) sits at the offset gcc gives
+    the same-named member of the struct in include/b200rec.h, and the sizes agree - a silent drift here would hand the
+    kernels garbage pointers.  The struct INTEGRATION.md section 3b shows a maintainer is checked the same way."""
+    import ctypes as C
+    import subprocess
+    from recsys_pytorch_b200 import _lib
+    structs = {"b200rec_bpr_args": _lib.BprArgs, "b200rec_p2p_route_args": _lib.P2PRouteArgs,
+               "b200rec_p2p_step_args": _lib.P2PStepArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200rec.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines.append("return 0; }")
+    (tmp_path / "abi.c").write_text("\n".join(lines))
+    exe = str(tmp_path / "abi")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(tmp_path / "abi.c"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, cls in structs.items():
+        assert got[(cname, "sizeof")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    # the hand-written binding in INTEGRATION.md (Option C): same fields, same order, same types
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class BprArgs\(C\.Structure\):.*?_fields_ = (\[.*?\])\n", doc, re.S)
+    assert m, "INTEGRATION.md lost its BprArgs binding"
+    fields = eval(m.group(1), {"C": C})
+    assert [(n, t) for n, t in fields] == [(n, t) for n, t in _lib.BprArgs._fields_]
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every prototype in include/b200rec.h against the ctypes signature _lib.py installs: same number of parameters,
+    pointer where the header has a pointer, the same scalar class (int32 / int64 / uint64 / float) elsewhere, and the
+    same return class."""
+    import ctypes as C
+    from recsys_pytorch_b200 import _lib
+    hdr = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "b200rec.h")).read(), flags=re.S)
+    protos = re.findall(r"(?:^|\n)\s*((?:const\s+)?[A-Za-z_0-9]+\s*\**)\s*(b200rec_\w+)\s*\(([^;{]*?)\)\s*;", hdr)
+    seen = set()
+
+    def klass_of_c(text):
+        text = text.strip()
+        if "*" in text:
+            return "ptr"
+        base = text.replace("const", " ").split()[0] if text else "void"
+        return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "float": "f32", "void": "void"}[base]
+
+    def klass_of_ctypes(t):
+        if t is C.c_void_p or t is C.c_char_p or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_int: "i32", C.c_int32: "i32", C.c_int64: "i64", C.c_uint64: "u64", C.c_float: "f32"}[t]
+
+    for ret, name, params in protos:
+        res, args = _lib._PROTOS[name]
+        seen.add(name)
+        plist = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        assert len(plist) == len(args), (name, len(plist), len(args))
+        for k, (p, a) in enumerate(zip(plist, args)):
+            assert klass_of_c(p) == klass_of_ctypes(a), (name, k, p.strip(), a)
+        assert klass_of_c(ret) == klass_of_ctypes(res), (name, ret)
+    assert seen == set(_lib._PROTOS), set(_lib._PROTOS) ^ seen
