@@ -623,3 +623,24 @@ def test_ctypes_prototypes_match_the_header():
             assert klass_of_c(p) == klass_of_ctypes(a), (name, k, p.strip(), a)
         assert klass_of_c(ret) == klass_of_ctypes(res), (name, ret)
     assert seen == set(_lib._PROTOS), set(_lib._PROTOS) ^ seen
+
+
+def test_integration_python_snippets_are_valid_python():
+    """Every ```python block of INTEGRATION.md parses; the Option C block also executes up to its definitions (loads the
+    library, declares the struct, installs the argtypes) from the repo root."""
+    import textwrap
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = [textwrap.dedent(b) for b in re.findall(r"```python\n(.*?)```", doc, re.S)]
+    assert len(blocks) >= 4
+    for b in blocks:
+        compile(b, "INTEGRATION.md", "exec")
+    opt_c = [b for b in blocks if "class BprArgs" in b]
+    assert len(opt_c) == 1
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        ns = {}
+        exec(compile(opt_c[0], "INTEGRATION.md", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    assert callable(ns["fused_bpr_step"]) and callable(ns["fused_predict_topk"])
