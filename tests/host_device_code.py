@@ -1,0 +1,85 @@
+"""Test infrastructure: compile the INTEGER / INDEX device functions of the CUDA sources for the HOST (g++), straight
+from their source text, so that `-m "not gpu"` tests can run the very code the kernels execute against the Python
+mirrors in oracle/.  Nothing here is shipped or imported by the product.
+
+What is taken (verbatim, with `__device__ __forceinline__` rewritten to `static inline`):
+  csrc/common.cuh   mix64, rng_u32, f2ord, ord2f, make_key, key_id, key_score
+  csrc/sampler.cuh  everything (sample_pos, sample_neg, sample_neg2, fetch_triple)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "recsys_pytorch_b200", "csrc")
+
+_WRAP = r'''
+extern "C" {
+// fetch_triple for t = 0..B-1 exactly as a kernel lane calls it; valid_out[t] = 1 when the triple is processed
+void host_fetch_triples(const b200rec_bpr_args *a, int *valid_out, int *u_out, int *i_out, int *j_out) {
+    for (int64_t t = 0; t < a->B; ++t) {
+        bool valid = true; int u, i, j;
+        b200::fetch_triple(*a, t, valid, u, i, j);
+        valid_out[t] = valid ? 1 : 0; u_out[t] = u; i_out[t] = i; j_out[t] = j;
+    }
+}
+int host_sample_neg2(const int32_t *row, uint32_t deg, uint32_t cnt0, uint32_t lo1, uint32_t cnt1, uint64_t seed,
+                     uint64_t step, uint64_t t, int *j) {
+    return b200::sample_neg2(row, deg, cnt0, lo1, cnt1, seed, step, t, *j) ? 1 : 0;
+}
+uint32_t host_rng_u32(uint64_t seed, uint64_t step, uint64_t idx, uint32_t draw) { return b200::rng_u32(seed, step, idx, draw); }
+uint64_t host_make_key(float s, int32_t id) { return b200::make_key(s, id); }
+int32_t host_key_id(uint64_t k) { return b200::key_id(k); }
+float host_key_score(uint64_t k) { return b200::key_score(k); }
+}
+'''
+
+
+def _function(src, name):
+    """Source text of `__device__ __forceinline__ <ret> name(...) { ... }` (brace matched)."""
+    m = re.search(r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\(" % re.escape(name), src)
+    assert m, name
+    k = src.index("{", m.end())
+    depth, e = 0, k
+    while True:
+        depth += {"{": 1, "}": -1}.get(src[e], 0)
+        e += 1
+        if depth == 0:
+            break
+    return src[m.start():e]
+
+
+def build(out_dir):
+    """Returns a ctypes handle of the host build."""
+    common = open(os.path.join(CSRC, "common.cuh")).read()
+    sampler = open(os.path.join(CSRC, "sampler.cuh")).read()
+    body = sampler[sampler.index("namespace b200 {"):]                     # drop the pragma / include lines
+    helpers = "\n".join(_function(common, n) for n in ("mix64", "rng_u32", "f2ord", "ord2f", "make_key", "key_id", "key_score"))
+    text = "\n".join([
+        "#include <stdint.h>", "#include <string.h>", '#include "b200rec.h"',
+        "static inline uint32_t __float_as_uint(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }",
+        "static inline float __uint_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }",
+        "namespace b200 {", helpers, "}", body, _WRAP]).replace("__device__ __forceinline__", "static inline")
+    src = os.path.join(out_dir, "host_device_code.cpp")
+    lib = os.path.join(out_dir, "libhost_device_code.so")
+    with open(src, "w") as f:
+        f.write(text)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), src, "-o", lib],
+                   check=True)
+    h = C.CDLL(lib)
+    h.host_rng_u32.restype = C.c_uint32
+    h.host_rng_u32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    h.host_make_key.restype = C.c_uint64
+    h.host_make_key.argtypes = [C.c_float, C.c_int32]
+    h.host_key_id.restype = C.c_int32
+    h.host_key_id.argtypes = [C.c_uint64]
+    h.host_key_score.restype = C.c_float
+    h.host_key_score.argtypes = [C.c_uint64]
+    h.host_sample_neg2.restype = C.c_int
+    h.host_sample_neg2.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64,
+                                   C.c_uint64, C.POINTER(C.c_int)]
+    h.host_fetch_triples.restype = None
+    return h

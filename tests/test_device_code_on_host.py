@@ -1,0 +1,153 @@
+"""`-m "not gpu"`: the integer / index device functions of the CUDA sources (counter RNG, positive / negative sampling
+with rejection against the sorted CSR row, shard ranges, the 64-bit ranking key) compiled FOR THE HOST from their own
+source text (tests/host_device_code.py) and run against the Python mirrors the GPU parity tests rely on
+(oracle/bpr_oracle.py).  The `-m gpu` suite checks the same mirror against the kernels on the device; this closes the
+loop on a box without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import bpr_oracle as O
+from recsys_pytorch_b200 import _lib
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    from tests.host_device_code import build
+    return build(str(tmp_path_factory.mktemp("hostdev")))
+
+
+def _csr(rng, nu, ni, lo, hi):
+    rows = [np.sort(rng.choice(ni, int(rng.integers(lo, hi)), replace=False)).astype(np.int32) for _ in range(nu)]
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+    return indptr, (np.concatenate(rows) if indptr[-1] else np.zeros(0, np.int32)).astype(np.int32)
+
+
+def _fetch(host, users, indptr, indices, ni, seed, step, pos=None, neg=None, item_range=None):
+    a = _lib.BprArgs()
+    B = len(users)
+    users = np.ascontiguousarray(users, np.int32)
+    a.users, a.B, a.num_items = users.ctypes.data, B, ni
+    keep = [users]
+    for name, arr in (("pos", pos), ("neg", neg)):
+        if arr is not None:
+            arr = np.ascontiguousarray(arr, np.int32); keep.append(arr)
+            setattr(a, name, arr.ctypes.data)
+    a.csr_indptr, a.csr_indices = indptr.ctypes.data, indices.ctypes.data
+    a.seed, a.step = seed, step
+    op, on = np.full(B, -7, np.int32), np.full(B, -7, np.int32)
+    a.out_pos, a.out_neg = op.ctypes.data, on.ctypes.data
+    if item_range is not None:
+        a.item_lo, a.item_hi = item_range
+    v, u, i, j = (np.zeros(B, np.int32) for _ in range(4))
+    host.host_fetch_triples(C.byref(a), C.c_void_p(v.ctypes.data), C.c_void_p(u.ctypes.data), C.c_void_p(i.ctypes.data),
+                            C.c_void_p(j.ctypes.data))
+    return v.astype(bool), u, i, j, op, on
+
+
+def test_counter_rng_matches_the_mirror(host):
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        seed, step, idx = (int(x) for x in rng.integers(0, 2**63, 3))
+        draw = int(rng.integers(0, 300))
+        assert host.host_rng_u32(seed, step, idx, draw) == O.rng_u32(seed, step, idx, draw)
+    idx = rng.integers(0, 2**40, 500).astype(np.uint64)
+    vec = O.rng_u32_vec(2020, 7, idx, 3)
+    assert [host.host_rng_u32(2020, 7, int(t), 3) for t in idx] == [int(x) for x in vec]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_device_sampler_source_equals_the_mirror(host, seed):
+    """fetch_triple (csrc/sampler.cuh) for a whole batch == oracle sample_triple / sample_triples_vec: same positives,
+    same negatives, every negative a non-positive, skipped triples reported as -1."""
+    rng = np.random.default_rng(seed)
+    nu, ni, B = 400, int(rng.integers(50, 3000)), 1500
+    indptr, indices = _csr(rng, nu, ni, 1, min(40, ni // 2))
+    users = rng.integers(0, nu, B)
+    valid, u, i, j, op, on = _fetch(host, users, indptr, indices, ni, 2020 + seed, 5 + seed)
+    pos, neg = O.sample_triples_vec(2020 + seed, 5 + seed, users, indptr, indices, ni)
+    assert valid.all() and np.array_equal(u, users)
+    assert np.array_equal(i, pos) and np.array_equal(j, neg) and np.array_equal(op, pos) and np.array_equal(on, neg)
+    for t in range(0, B, 7):
+        row = indices[indptr[users[t]]:indptr[users[t] + 1]]
+        assert i[t] in row and j[t] not in row and 0 <= j[t] < ni
+        assert (int(i[t]), int(j[t])) == O.sample_triple(2020 + seed, 5 + seed, t, int(users[t]), indptr, indices, ni)
+    # given positives: only the negative is drawn (and it does not depend on the positive)
+    v2, _, i2, j2, _, _ = _fetch(host, users, indptr, indices, ni, 2020 + seed, 5 + seed, pos=pos[::-1].copy())
+    assert v2.all() and np.array_equal(i2, pos[::-1]) and np.array_equal(j2, neg)
+    # given both: nothing is sampled, nothing is written back
+    v3, _, i3, j3, op3, on3 = _fetch(host, users, indptr, indices, ni, 1, 1, pos=pos, neg=neg)
+    assert v3.all() and np.array_equal(i3, pos) and np.array_equal(j3, neg) and (op3 == -7).all() and (on3 == -7).all()
+
+
+def test_device_sampler_edge_cases(host):
+    """A user without positives emits no triple; a user whose positives cover the whole sampling range is skipped after
+    64 rejected draws (never trained positive-vs-positive); item-sharded ranges keep only the owned triples
+    and draw the negative from the shard."""
+    ni = 64
+    rows = [np.arange(ni, dtype=np.int32), np.zeros(0, np.int32), np.arange(0, ni, 2, dtype=np.int32)]
+    indptr = np.array([0, ni, ni, ni + ni // 2], np.int64)
+    indices = np.concatenate(rows)
+    users = np.array([0, 1, 2] * 50, np.int32)
+    valid, _, i, j, op, on = _fetch(host, users, indptr, indices, ni, 9, 1)
+    assert not valid[0::3].any() and (on[0::3] == -1).all() and (op[0::3] == -1).all()      # owns everything
+    assert not valid[1::3].any()                                                          # no positives
+    assert valid[2::3].all() and (i[2::3] % 2 == 0).all() and (j[2::3] % 2 == 1).all()
+    for t in range(2, 150, 3):
+        assert (int(i[t]), int(j[t])) == O.sample_triple(9, 1, t, 2, indptr, indices, ni)
+    # item-sharded: rank range [16, 48)
+    valid, _, i, j, _, on = _fetch(host, users, indptr, indices, ni, 9, 1, item_range=(16, 48))
+    own = valid[2::3]
+    assert own.any() and not own.all()
+    assert ((i[2::3][own] >= 16) & (i[2::3][own] < 48)).all() and ((j[2::3][own] >= 16) & (j[2::3][own] < 48)).all()
+    assert (j[2::3][own] % 2 == 1).all() and (on[2::3][~own] == -1).all()
+    for t in np.arange(2, 150, 3)[own]:
+        p, n = O.sample_triple(9, 1, int(t), 2, indptr, indices, ni, item_bounds=[0, 16, 48, 64])
+        assert (int(i[t]), int(j[t])) == (p, n)
+
+
+def test_head_plus_shard_negative_sampler(host):
+    """sample_neg2 (replicated head [0, head) U one tail shard, csrc/p2p.cu's router) against the mirror."""
+    rng = np.random.default_rng(3)
+    ni, head = 500, 40
+    bounds = [head, 150, 320, ni]
+    indptr, indices = _csr(rng, 200, ni, 1, 60)
+    for t in range(600):
+        user = int(rng.integers(0, 200))
+        row = np.ascontiguousarray(indices[indptr[user]:indptr[user + 1]])
+        r = int(rng.integers(0, 3))
+        j = C.c_int(0)
+        ok = host.host_sample_neg2(row.ctypes.data, len(row), head, bounds[r], bounds[r + 1] - bounds[r], 11, 4, t, C.byref(j))
+        # mirror: a positive inside shard r makes sample_triple use exactly that union
+        neg = 0
+        for tr in range(64):
+            q = O.rng_u32(11, 4, t, 1 + tr) * (head + bounds[r + 1] - bounds[r]) >> 32
+            neg = q if q < head else bounds[r] + (q - head)
+            k = int(np.searchsorted(row, neg))
+            if not (k < len(row) and int(row[k]) == neg):
+                break
+        else:
+            neg = -1
+        assert (j.value if ok else -1) == neg
+        if ok:
+            assert j.value not in row and (j.value < head or bounds[r] <= j.value < bounds[r + 1])
+
+
+def test_ranking_key_orders_by_score_desc_then_id_asc(host):
+    """make_key / key_id / key_score (csrc/common.cuh): the 64-bit key every top-k list sorts by.  Larger key == better
+    == (score descending, item id ascending) - the documented tie order; -inf (masked) sorts below every
+    finite score; the round trip is exact."""
+    rng = np.random.default_rng(5)
+    scores = np.concatenate([rng.standard_normal(300).astype(np.float32) * 10, np.float32([0.0, 1e-38, -1e-38, 3e38, -3e38]),
+                             np.float32([-np.inf, np.inf]), np.round(rng.standard_normal(200)).astype(np.float32)])
+    ids = rng.integers(0, 2**31 - 1, len(scores)).astype(np.int32)
+    keys = np.array([host.host_make_key(float(s), int(i)) for s, i in zip(scores, ids)], np.uint64)
+    for k, s, i in zip(keys, scores, ids):
+        assert host.host_key_id(int(k)) == int(i) and np.float32(host.host_key_score(int(k))) == s
+    order = np.argsort(keys)[::-1]                                   # best first
+    # score desc, id asc - on the IEEE total order: the key ranks -0.0 just below +0.0 (a float compare calls them equal;
+    # a dot product accumulated from +0.0 never yields -0.0, so only caller-supplied score blocks can show the difference)
+    want = np.lexsort((ids, np.signbit(scores) & (scores == 0), -scores.astype(np.float64)))
+    assert np.array_equal(scores[order], scores[want]) and np.array_equal(ids[order], ids[want])
+    assert np.signbit(scores).any() and (scores == 0).sum() >= 2     # the -0.0 / +0.0 case is exercised
