@@ -5,6 +5,7 @@ mirrors in oracle/.  Nothing here is shipped or imported by the product.
 What is taken (verbatim, with `__device__ __forceinline__` rewritten to `static inline`):
   csrc/common.cuh   mix64, rng_u32, f2ord, ord2f, make_key, key_id, key_score
   csrc/sampler.cuh  everything (sample_pos, sample_neg, sample_neg2, fetch_triple)
+  csrc/metrics.cu   in_truth, holdout_kernel, loo_kernel (one thread per user: the host driver loops over the thread ids)
 """
 from __future__ import annotations
 
@@ -83,3 +84,62 @@ def build(out_dir):
                                    C.c_uint64, C.POINTER(C.c_int)]
     h.host_fetch_triples.restype = None
     return h
+
+
+_METRICS_WRAP = r"""
+extern "C" {
+void host_holdout(const int32_t *topk, int n, int max_k, const int32_t *row_ids, const int64_t *tptr, const int32_t *tidx,
+                  const int *Ks, int K_len, float *out) {
+    for (int i = 0; i < b200::kMaxK + 2; ++i) b200::c_inv_log2[i] = 1.0 / log2((double)(i + 2));   // upload_tables()
+    b200::KsArg ks; ks.n = K_len; for (int j = 0; j < 64; ++j) ks.v[j] = j < K_len ? Ks[j] : 0;     // make_ks()
+    blockDim.x = 128;
+    for (int b = 0; b * 128 < n; ++b) for (int t = 0; t < 128; ++t) {
+        blockIdx.x = b; threadIdx.x = t;
+        b200::holdout_kernel(topk, n, max_k, row_ids, tptr, tidx, ks, out);
+    }
+}
+void host_loo(const int32_t *topk, int n, int max_k, const int32_t *row_ids, const int64_t *tptr, const int32_t *tidx,
+              const int *Ks, int K_len, float *out) {
+    for (int i = 0; i < b200::kMaxK + 2; ++i) b200::c_inv_log2[i] = 1.0 / log2((double)(i + 2));
+    b200::KsArg ks; ks.n = K_len; for (int j = 0; j < 64; ++j) ks.v[j] = j < K_len ? Ks[j] : 0;
+    blockDim.x = 128;
+    for (int b = 0; b * 128 < n; ++b) for (int t = 0; t < 128; ++t) {
+        blockIdx.x = b; threadIdx.x = t;
+        b200::loo_kernel(topk, n, max_k, row_ids, tptr, tidx, ks, out);
+    }
+}
+}
+"""
+
+
+def _kernel(src, name):
+    """Source text of `__global__ void __launch_bounds__(..) name(...) { ... }` as a plain function."""
+    m = re.search(r"__global__\s+void\s+__launch_bounds__\(\d+\)\s+%s\s*\(" % re.escape(name), src)
+    assert m, name
+    k = src.index("{", m.end())
+    depth, e = 0, k
+    while True:
+        depth += {"{": 1, "}": -1}.get(src[e], 0)
+        e += 1
+        if depth == 0:
+            break
+    return re.sub(r"__global__\s+void\s+__launch_bounds__\(\d+\)", "static void", src[m.start():e])
+
+
+def build_metrics(out_dir):
+    """Host build of the metric kernels of csrc/metrics.cu; returns a ctypes handle."""
+    src_cu = open(os.path.join(CSRC, "metrics.cu")).read()
+    ks_arg = re.search(r"struct KsArg \{.*?\};", src_cu, re.S).group(0)
+    text = "\n".join([
+        "#include <stdint.h>", "#include <math.h>",
+        "struct Dim3 { int x; }; static thread_local Dim3 blockIdx, blockDim, threadIdx;",
+        "namespace b200 {", "constexpr int kMaxK = 1024;", "static double c_inv_log2[kMaxK + 2];", ks_arg,
+        _function(src_cu, "in_truth"), _kernel(src_cu, "holdout_kernel"), _kernel(src_cu, "loo_kernel"), "}",
+        _METRICS_WRAP]).replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
+    src = os.path.join(out_dir, "host_metrics.cpp")
+    lib = os.path.join(out_dir, "libhost_metrics.so")
+    with open(src, "w") as f:
+        f.write(text)
+    # -ffp-contract=off / no fast-math: the arithmetic must stay the IEEE sequence the source spells out
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", lib], check=True)
+    return C.CDLL(lib)

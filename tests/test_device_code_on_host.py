@@ -151,3 +151,55 @@ def test_ranking_key_orders_by_score_desc_then_id_asc(host):
     want = np.lexsort((ids, np.signbit(scores) & (scores == 0), -scores.astype(np.float64)))
     assert np.array_equal(scores[order], scores[want]) and np.array_equal(ids[order], ids[want])
     assert np.signbit(scores).any() and (scores == 0).sum() >= 2     # the -0.0 / +0.0 case is exercised
+
+
+# ---- the metric kernels of csrc/metrics.cu, thread by thread on the host ------------------------------------------------
+@pytest.fixture(scope="module")
+def host_metrics(tmp_path_factory):
+    from tests.host_device_code import build_metrics
+    return build_metrics(str(tmp_path_factory.mktemp("hostmetrics")))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_metric_kernels_source_is_bitwise_the_reference_cpp(host_metrics, seed):
+    """holdout_kernel / loo_kernel (one thread per user) executed on the host from their own source == the reference's
+    holdout.h / loo.h (oracle/_ref when built, else the C restatement, which the differential tests pin to it), bit for
+    bit, incl. the row_ids indirection the sharded evaluation uses."""
+    import os
+    from tests.util import OracleC
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_path = os.path.join(root, "oracle", "_ref", "libref_eval.so")
+    if os.path.exists(ref_path):
+        from oracle.ref_harness import RefNative
+        ref = RefNative()
+    else:
+        ref = OracleC(os.path.join(root, "oracle", "liboracle.so"))
+    rng = np.random.default_rng(40 + seed)
+    users, items, max_k = int(rng.integers(1, 400)), int(rng.integers(80, 4000)), int(rng.integers(1, 60))
+    ks = np.array(sorted(set([1, max_k] + rng.integers(1, max_k + 1, 3).tolist())), np.int32)
+    n_truth_rows = users + 5                                                   # truth CSR has more rows than scored users
+    truths = []
+    for _ in range(n_truth_rows):
+        truths.append(np.sort(rng.choice(items, int(rng.integers(1, 2 * max_k + 2)), replace=False)).astype(np.int32))
+    row_ids = rng.permutation(n_truth_rows)[:users].astype(np.int32)
+    topk = np.stack([rng.choice(items, max_k, replace=False) for _ in range(users)]).astype(np.int32)
+    for r in range(0, users, 2):                                               # plant hits
+        t = truths[row_ids[r]]
+        m = min(len(t), max_k, 3)
+        topk[r, rng.choice(max_k, m, replace=False)] = t[:m]
+        if len(set(topk[r].tolist())) < max_k:                                 # keep rankings duplicate-free
+            topk[r] = rng.choice(items, max_k, replace=False)
+    tptr = np.zeros(n_truth_rows + 1, np.int64); tptr[1:] = np.cumsum([len(t) for t in truths])
+    tidx = np.concatenate(truths).astype(np.int32)
+    P = lambda a: C.c_void_p(a.ctypes.data)
+    out = np.zeros((users, 3 * len(ks)), np.float32)
+    host_metrics.host_holdout(P(topk), users, max_k, P(row_ids), P(tptr), P(tidx), P(ks), len(ks), P(out))
+    np.testing.assert_array_equal(out, ref.holdout(topk, [truths[r] for r in row_ids], ks))
+    np.testing.assert_array_equal(out, O.holdout_metrics(topk, [truths[r] for r in row_ids], ks))
+    out = np.zeros((users, 2 * len(ks)), np.float32)
+    host_metrics.host_loo(P(topk), users, max_k, P(row_ids), P(tptr), P(tidx), P(ks), len(ks), P(out))
+    np.testing.assert_array_equal(out, ref.loo(topk, [truths[r][:1] for r in row_ids], ks))
+    # without the indirection: row r of the truth CSR belongs to scored row r
+    out2 = np.zeros((users, 3 * len(ks)), np.float32)
+    host_metrics.host_holdout(P(topk), users, max_k, None, P(tptr), P(tidx), P(ks), len(ks), P(out2))
+    np.testing.assert_array_equal(out2, ref.holdout(topk, truths[:users], ks))
