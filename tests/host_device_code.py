@@ -6,6 +6,8 @@ What is taken (verbatim, with `__device__ __forceinline__` rewritten to `static 
   csrc/common.cuh   mix64, rng_u32, f2ord, ord2f, make_key, key_id, key_score
   csrc/sampler.cuh  everything (sample_pos, sample_neg, sample_neg2, fetch_triple)
   csrc/metrics.cu   in_truth, holdout_kernel, loo_kernel (one thread per user: the host driver loops over the thread ids)
+  csrc/p2p.cu       owner_of (shard of an item id), chunk_of (work order of the fused P2P step)
+  csrc/score_tc.cu  pow2_scale (the exact power-of-two rescale in front of the fp16 candidate pass)
 """
 from __future__ import annotations
 
@@ -143,3 +145,33 @@ def build_metrics(out_dir):
     # -ffp-contract=off / no fast-math: the arithmetic must stay the IEEE sequence the source spells out
     subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", lib], check=True)
     return C.CDLL(lib)
+
+
+_MISC_WRAP = r"""
+extern "C" {
+int host_owner_of(const int32_t *bounds, int world, int id) { return b200::owner_of(bounds, world, id); }
+void host_chunk_of(int c, int W, int m, const int *pref, int round_robin, int *k, int *off) {
+    b200::chunk_of(c, W, m, pref, round_robin != 0, *k, *off);
+}
+float host_pow2_scale(unsigned bits) { return b200::pow2_scale(bits); }
+}
+"""
+
+
+def build_misc(out_dir):
+    p2p = open(os.path.join(CSRC, "p2p.cu")).read()
+    tc = open(os.path.join(CSRC, "score_tc.cu")).read()
+    text = "\n".join([
+        "#include <stdint.h>", "#include <string.h>", "#include <math.h>",
+        "static inline float __uint_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }",
+        "namespace b200 {", _function(p2p, "owner_of"), _function(p2p, "chunk_of"), _function(tc, "pow2_scale"), "}",
+        _MISC_WRAP]).replace("__device__ __forceinline__", "static inline").replace("#pragma unroll 1", "")
+    src = os.path.join(out_dir, "host_misc.cpp")
+    lib = os.path.join(out_dir, "libhost_misc.so")
+    with open(src, "w") as f:
+        f.write(text)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", src, "-o", lib], check=True)
+    h = C.CDLL(lib)
+    h.host_pow2_scale.restype = C.c_float
+    h.host_pow2_scale.argtypes = [C.c_uint32]
+    return h

@@ -203,3 +203,77 @@ def test_metric_kernels_source_is_bitwise_the_reference_cpp(host_metrics, seed):
     out2 = np.zeros((users, 3 * len(ks)), np.float32)
     host_metrics.host_holdout(P(topk), users, max_k, None, P(tptr), P(tidx), P(ks), len(ks), P(out2))
     np.testing.assert_array_equal(out2, ref.holdout(topk, truths[:users], ks))
+
+
+# ---- P2P work order / shard lookup, fp16 rescale ---------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def host_misc(tmp_path_factory):
+    from tests.host_device_code import build_misc
+    return build_misc(str(tmp_path_factory.mktemp("hostmisc")))
+
+
+def test_p2p_owner_lookup_matches_host_bounds_logic(host_misc):
+    from recsys_pytorch_b200.p2p import owner_from_bounds
+    rng = np.random.default_rng(1)
+    for W in (1, 2, 3, 4, 8, 16):
+        n = 5000
+        cuts = np.sort(rng.choice(np.arange(1, n), W - 1, replace=False)) if W > 1 else np.zeros(0, int)
+        bounds = np.concatenate([[0], cuts, [n]]).astype(np.int32)
+        ids = np.concatenate([bounds[:-1], np.maximum(bounds[1:] - 1, 0), rng.integers(0, n, 300)])
+        want = owner_from_bounds(ids, bounds.tolist())
+        got = [host_misc.host_owner_of(C.c_void_p(bounds.ctypes.data), W, int(i)) for i in ids]
+        assert got == want.tolist()
+        assert all(bounds[r] <= i < bounds[r + 1] for i, r in zip(ids, got))
+
+
+@pytest.mark.parametrize("round_robin", [0, 1])
+def test_p2p_chunk_order_visits_every_chunk_exactly_once(host_misc, round_robin):
+    """chunk_of (csrc/p2p.cu): the dynamic chunk counter c -> (source slot, offset) must be a bijection onto the chunks of
+    every source, for both visiting orders, any world size, empty sources included - a slip here would drop or repeat
+    32 triples silently.  pref / m are computed the way the kernel's thread 0 does."""
+    rng = np.random.default_rng(7 + round_robin)
+    for case in range(300):
+        W = int(rng.choice([1, 2, 3, 4, 5, 8, 16]))
+        cnt = rng.integers(0, 400, W)
+        if case % 5 == 0:
+            cnt[rng.integers(0, W)] = 0
+        if case % 7 == 0:
+            cnt[:] = 0
+        chunks = (cnt + 31) >> 5
+        pref = np.zeros(W + 1, np.int32); pref[1:] = np.cumsum(chunks)
+        R, nl = int(pref[W - 1]), int(pref[W] - pref[W - 1])
+        m = min(nl, R // (W - 1)) if W > 1 else 0
+        if round_robin:
+            m = int(chunks.min())
+        seen = set()
+        k, off = C.c_int(0), C.c_int(0)
+        for c in range(int(pref[W])):
+            host_misc.host_chunk_of(c, W, m, C.c_void_p(pref.ctypes.data), round_robin, C.byref(k), C.byref(off))
+            assert 0 <= k.value < W and off.value % 32 == 0 and 0 <= off.value < 32 * chunks[k.value], (case, c, k.value, off.value)
+            seen.add((k.value, off.value))
+        assert len(seen) == int(pref[W])                       # no chunk twice -> with the range check: every chunk once
+        if not round_robin and W > 1 and m > 0:                # a local chunk (slot W-1) after every W-1 remote chunks
+            host_misc.host_chunk_of(W - 1, W, m, C.c_void_p(pref.ctypes.data), 0, C.byref(k), C.byref(off))
+            assert k.value == W - 1 and off.value == 0
+
+
+def test_fp16_rescale_is_an_exact_power_of_two_inside_the_fp16_range(host_misc):
+    """pow2_scale (csrc/score_tc.cu): the table-wide scale in front of the fp16 candidate pass is a power of two (the
+    rescale is exact in fp32) that maps max|x| into [2^13, 2^14) - far from fp16 overflow (65504) with the headroom of a
+    d = 256 dot product in the exponent; degenerate tables (all zero, inf, nan) get scale 1."""
+    rng = np.random.default_rng(2)
+    vals = np.concatenate([np.float32(2.0) ** rng.integers(-60, 60, 200), rng.standard_normal(300).astype(np.float32) * 7,
+                           np.float32([1e-30, 3e30, 65504.0, 1.0, 0.5, 16383.9, 16384.0])])
+    for v in np.abs(vals).astype(np.float32):
+        if v == 0:
+            continue
+        s = np.float32(host_misc.host_pow2_scale(int(np.float32(v).view(np.uint32))))
+        mant, ex = np.frexp(s)
+        assert mant == 0.5                                      # exact power of two
+        if 2.0 ** -86 <= float(v) < 2.0 ** 114:                 # the shift is clamped to +-100 outside this range
+            assert 2.0 ** 13 <= float(v) * float(s) < 2.0 ** 14
+        else:
+            assert abs(int(ex) - 1) == 100 and (float(v) * float(s) < 2.0 ** 14 or float(v) >= 2.0 ** 114)
+        assert np.float32(v) * s / s == np.float32(v)           # scaling and unscaling is lossless
+    for bits in (0, 0x7F800000, 0x7FC00000):                    # 0, +inf, nan
+        assert host_misc.host_pow2_scale(bits) == 1.0
