@@ -7,7 +7,8 @@ What is taken (verbatim, with `__device__ __forceinline__` rewritten to `static 
   csrc/sampler.cuh  everything (sample_pos, sample_neg, sample_neg2, fetch_triple)
   csrc/metrics.cu   in_truth, holdout_kernel, loo_kernel (one thread per user: the host driver loops over the thread ids)
   csrc/p2p.cu       owner_of (shard of an item id), chunk_of (work order of the fused P2P step)
-  csrc/score_tc.cu  pow2_scale (the exact power-of-two rescale in front of the fp16 candidate pass)
+  csrc/score_tc.cu  pow2_scale (the exact power-of-two rescale in front of the fp16 candidate pass), reorder_kernel (the
+                    visiting order head | stratified sample | rest)
 """
 from __future__ import annotations
 
@@ -116,7 +117,7 @@ void host_loo(const int32_t *topk, int n, int max_k, const int32_t *row_ids, con
 
 def _kernel(src, name):
     """Source text of `__global__ void __launch_bounds__(..) name(...) { ... }` as a plain function."""
-    m = re.search(r"__global__\s+void\s+__launch_bounds__\(\d+\)\s+%s\s*\(" % re.escape(name), src)
+    m = re.search(r"__global__\s+void\s+(?:__launch_bounds__\(\d+\)\s+)?%s\s*\(" % re.escape(name), src)
     assert m, name
     k = src.index("{", m.end())
     depth, e = 0, k
@@ -125,7 +126,7 @@ def _kernel(src, name):
         e += 1
         if depth == 0:
             break
-    return re.sub(r"__global__\s+void\s+__launch_bounds__\(\d+\)", "static void", src[m.start():e])
+    return re.sub(r"__global__\s+void\s+(?:__launch_bounds__\(\d+\))?", "static void ", src[m.start():e], count=1)
 
 
 def build_metrics(out_dir):
@@ -154,6 +155,15 @@ void host_chunk_of(int c, int W, int m, const int *pref, int round_robin, int *k
     b200::chunk_of(c, W, m, pref, round_robin != 0, *k, *off);
 }
 float host_pow2_scale(unsigned bits) { return b200::pow2_scale(bits); }
+// reorder_kernel<<<(n + 255) / 256, 256>>> thread by thread
+void host_reorder(const int32_t *perm, const uint32_t *norm_bits, int n, int H, int S, int stride, int32_t *perm_out,
+                  float *norm_out) {
+    blockDim.x = 256;
+    for (int b = 0; b * 256 < n; ++b) for (int t = 0; t < 256; ++t) {
+        blockIdx.x = b; threadIdx.x = t;
+        b200::reorder_kernel(perm, norm_bits, n, H, S, stride, perm_out, norm_out);
+    }
+}
 }
 """
 
@@ -164,8 +174,10 @@ def build_misc(out_dir):
     text = "\n".join([
         "#include <stdint.h>", "#include <string.h>", "#include <math.h>",
         "static inline float __uint_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }",
-        "namespace b200 {", _function(p2p, "owner_of"), _function(p2p, "chunk_of"), _function(tc, "pow2_scale"), "}",
-        _MISC_WRAP]).replace("__device__ __forceinline__", "static inline").replace("#pragma unroll 1", "")
+        "struct Dim3 { int x; }; static thread_local Dim3 blockIdx, blockDim, threadIdx;",
+        "namespace b200 {", _function(p2p, "owner_of"), _function(p2p, "chunk_of"), _function(tc, "pow2_scale"),
+        _kernel(tc, "reorder_kernel"), "}",
+        _MISC_WRAP]).replace("__device__ __forceinline__", "static inline").replace("#pragma unroll 1", "").replace("__restrict__", "")
     src = os.path.join(out_dir, "host_misc.cpp")
     lib = os.path.join(out_dir, "libhost_misc.so")
     with open(src, "w") as f:

@@ -277,3 +277,35 @@ def test_fp16_rescale_is_an_exact_power_of_two_inside_the_fp16_range(host_misc):
         assert np.float32(v) * s / s == np.float32(v)           # scaling and unscaling is lossless
     for bits in (0, 0x7F800000, 0x7FC00000):                    # 0, +inf, nan
         assert host_misc.host_pow2_scale(bits) == 1.0
+
+
+def test_tc_visiting_order_is_a_permutation_of_the_catalogue(host_misc):
+    """reorder_kernel (csrc/score_tc.cu): head | stratified sample | rest must place every rank of the descending-norm
+    order exactly once - with the (H, S, stride) the host derives in score_topk_tc_impl, at the edge sizes (the first
+    catalogue that gets a sample, one more, primes, tile multiples +-1) - and keep (item, norm) pairs together; each of
+    the three segments stays in descending-norm order."""
+    rng = np.random.default_rng(0)
+    for tile in (256, 128):
+        H, S_full = tile, 16 * tile
+        edge = 8 * (H + S_full)
+        sizes = [1, 2, tile - 1, tile, tile + 1, edge - 1, edge, edge + 1, edge + S_full - 1, 2 * edge + 17, 100_003, 99_991,
+                 3 * S_full * 7 + H, 250_000] + rng.integers(1, 300_000, 6).tolist()
+        for n in sizes:
+            sample = n >= 8 * (H + S_full)
+            S = S_full if sample else 0
+            stride = (n - H) // S_full if sample else 1
+            perm = rng.permutation(n).astype(np.int32)                               # item id at rank r
+            norms = np.sort(rng.random(n).astype(np.float32))[::-1].copy()           # descending
+            perm_out = np.full(n, -1, np.int32); norm_out = np.full(n, -1.0, np.float32)
+            P = lambda a: C.c_void_p(a.ctypes.data)
+            host_misc.host_reorder(P(perm), P(norms.view(np.uint32)), n, H, S, stride, P(perm_out), P(norm_out))
+            assert np.array_equal(np.sort(perm_out), np.arange(n)), (tile, n)        # a permutation: nothing lost, nothing twice
+            rank_of = np.empty(n, np.int64); rank_of[perm] = np.arange(n)
+            assert np.array_equal(norm_out, norms[rank_of[perm_out]])                # norms travel with their items
+            r = rank_of[perm_out]                                                     # rank visited at each position
+            assert np.array_equal(r[:min(H, n)], np.arange(min(H, n)))                # head: the H highest norms, in order
+            if sample:
+                assert np.array_equal(r[H:H + S], H + stride * np.arange(S))          # every stride-th rank of the rest
+                assert np.all(np.diff(r[H + S:]) > 0)                                 # rest: still descending norm
+            else:
+                assert np.array_equal(r, np.arange(n))
