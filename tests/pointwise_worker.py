@@ -1,5 +1,6 @@
 """Device check of b200rec_pointwise_step against the oracle and the reference's golden vectors; run in its own process
-by tests/test_gpu_pointwise.py (the kernel has not run on hardware yet: a fault must not take the suite's CUDA context)."""
+by tests/test_gpu_pointwise.py (green on a B200 since the round-1 driver run; its own process so that a fault cannot take
+the suite's CUDA context with it)."""
 import os
 import sys
 

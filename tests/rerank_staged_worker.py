@@ -1,5 +1,6 @@
-"""B200REC_RERANK=2 (rerank_staged_kernel, csrc/score_tc.cu) must give exactly the default result; own process because
-the kernel has not run on hardware yet (tests/test_gpu_experimental.py)."""
+"""B200REC_RERANK=2 (rerank_staged_kernel, csrc/score_tc.cu) must give exactly the default result; own process so that
+a fault in this opt-in path cannot take the suite's CUDA context with it (tests/test_gpu_experimental.py; green on a
+B200 since the round-1 driver run)."""
 import os
 import sys
 
