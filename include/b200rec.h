@@ -139,8 +139,8 @@ const char *b200rec_last_step_kernel(void);
  * sink = B200REC_SINK_UPDATE (rows updated in place with -lr * (grad + reg/B * row), vector atomics),
  *        B200REC_SINK_GRAD (raw gradient rows accumulated into dense gU/gV, for the reference's dense Adam) or
  *        B200REC_SINK_NONE (loss only).  loss_sum (device double, may be NULL) receives the SUM of per-sample losses.
- * STATUS: written against oracle/bpr_oracle.py::pointwise_loss/_grads (pinned to the reference's outputs in
- * tests/golden/tiny_pointwise.npz); its device test (tests/test_gpu_pointwise.py) has not run on hardware yet. */
+ * Pinned to the reference's outputs (tests/golden/tiny_pointwise.npz, ml100k_pointwise.npz) through
+ * oracle/bpr_oracle.py::pointwise_loss/_grads; device tests tests/test_gpu_pointwise.py, tests/test_gpu_parity.py. */
 int b200rec_pointwise_step(float *U, float *V, int ld, int d, const int32_t *users, const int32_t *items,
                            const float *ratings, int B, int loss_kind, float lr, float reg, int sink,
                            float *gU, float *gV, double *loss_sum, float inv_batch, void *stream);

@@ -799,8 +799,8 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float *__restrict__ U
     }
 }
 
-// Re-rank, staged variant (B200REC_RERANK=2; NOT the default: written after the round's GPU minutes were spent, it
-// has not run on hardware yet).  The default kernel lets every lane walk its own candidate's V row straight from L2
+// Re-rank, staged variant (B200REC_RERANK=2; NOT the default: equal results on a B200, tests/test_gpu_experimental.py,
+// but never faster than the default in a measurement).  The default kernel lets every lane walk its own candidate's V row straight from L2
 // (ncu run 24: 30 % of the stalls sit on those loads inside the FMA chain); here the warp first copies the rows of up to
 // RC candidates into shared memory with coalesced 16-byte loads that are all in flight at once, then RC lanes run the
 // SAME k-ordered fp32 FMA chain out of shared memory (row stride d_pad + 4 floats: conflict-free float4 reads).
