@@ -1,0 +1,230 @@
+"""Test infrastructure: a minimal SIMT emulator that runs the fused BPR step kernels of csrc/bpr_step.cu ON THE HOST,
+compiled from their own source text, so `-m "not gpu"` tests can execute the kernels' real code (warp-cooperative id
+exchange, sub-warp row groups, chunk handling, every sink, the on-device sampler) against the numpy oracle on a box
+without a GPU.  Nothing here is shipped or imported by the product; the GPU parity suite stays the authority for the
+hardware behaviour (memory model, tcgen05 / TMA paths are NOT emulated).
+
+How: every lane of a warp is a host thread; the warp intrinsics the kernels use (`__shfl_sync`, `__shfl_xor_sync`,
+`__ballot_sync`, `__syncwarp`) are rendezvous over a 32-party barrier with an exchange array; `red4` is four CAS float
+adds, `atomicAdd` the gcc builtin / a CAS loop; `__expf`, `__frcp_rn`, `__logf` map to libm (a few ulp from the device's
+fast paths - far inside the 2e-5 parity tolerance).  The 8 warps of a CTA run concurrently, CTAs one after another.
+Taken verbatim from the sources: mix64, rng_u32 (common.cuh); sampler.cuh; BprParams, bpr_grad, softplus_neg, group_sum,
+sink_chunk, bpr_step_ldg_kernel, RowSet, bpr_step_fast_kernel, GroupSet, bpr_step_group_kernel, bpr_apply_kernel
+(bpr_step.cu).  The launch parameters (chunk size, chunk count, 1/B, work counter) are set the way b200rec_bpr_step does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "recsys_pytorch_b200", "csrc")
+
+_PRELUDE = r'''
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <pthread.h>
+#include <thread>
+#include <vector>
+#include "b200rec.h"
+
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
+struct Dim3 { int x; };
+static thread_local Dim3 blockIdx, blockDim, threadIdx, gridDim;
+
+struct WarpCtx { pthread_barrier_t bar; uint64_t xchg[32]; };
+static thread_local WarpCtx *t_warp;
+static thread_local int t_lane;
+static inline void warp_bar() { pthread_barrier_wait(&t_warp->bar); }
+
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+    uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
+    t_warp->xchg[t_lane] = raw; warp_bar();
+    const uint64_t r = t_warp->xchg[src & 31]; warp_bar();
+    T out; memcpy(&out, &r, sizeof(T)); return out;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned m, T v, int o) { return __shfl_sync(m, v, t_lane ^ o); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    t_warp->xchg[t_lane] = pred ? 1 : 0; warp_bar();
+    unsigned r = 0; for (int l = 0; l < 32; ++l) r |= (unsigned)t_warp->xchg[l] << l;
+    warp_bar(); return r;
+}
+static inline void __syncwarp() { warp_bar(); }
+
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline void atomic_addf(float *p, float v) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(p), old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
+    do { float f; memcpy(&f, &old, 4); f += v; memcpy(&neu, &f, 4); }
+    while (!__atomic_compare_exchange_n(u, &old, neu, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+static inline double atomicAdd(double *p, double v) {
+    uint64_t *u = reinterpret_cast<uint64_t *>(p), old = __atomic_load_n(u, __ATOMIC_RELAXED), neu; double f;
+    do { memcpy(&f, &old, 8); double g = f + v; memcpy(&neu, &g, 8); }
+    while (!__atomic_compare_exchange_n(u, &old, neu, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return f;
+}
+static inline float emu_expf(float x) { return expf(x); }      // the kernels' __expf / __logf / __frcp_rn (glibc owns
+static inline float emu_logf(float x) { return logf(x); }      // the first two names, so the source text is renamed)
+static inline float emu_frcp_rn(float x) { return 1.0f / x; }
+
+struct __nv_bfloat16 { uint16_t v; };
+#define B200REC_FAST_MINB 3
+#define ABL(bit) 0
+
+namespace b200 {
+static inline float4 ld4(const float *p) { float4 v; memcpy(&v, p, 16); return v; }
+static inline void st4(float *p, float4 v) { memcpy(p, &v, 16); }
+static inline void red4(float *p, float4 v) { atomic_addf(p, v.x); atomic_addf(p + 1, v.y); atomic_addf(p + 2, v.z); atomic_addf(p + 3, v.w); }
+static inline uint64_t l2_policy_evict_first() { return 0; }
+static inline uint64_t l2_policy_evict_last() { return 0; }
+static inline float4 ld4_hint(const float *p, uint64_t) { return ld4(p); }
+static inline void st4_hint(float *p, float4 v, uint64_t) { st4(p, v); }
+static inline void red4_hint(float *p, float4 v, uint64_t) { red4(p, v); }
+static inline void red4_bf16(__nv_bfloat16 *, float4) { fprintf(stderr, "simt_host: bf16 sink not emulated\n"); abort(); }
+}
+'''
+
+_LAUNCH = r'''
+namespace {
+// <<<grid, 256>>>: CTAs one after another, the 8 warps of a CTA concurrently, every lane a host thread
+template <class K, class P> void emu_launch(K kern, int grid, const P &p) {
+    for (int b = 0; b < grid; ++b) {
+        std::vector<WarpCtx> warps(8);
+        for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
+        std::vector<std::thread> th;
+        for (int t = 0; t < 256; ++t)
+            th.emplace_back([&, t, b]() {
+                blockIdx.x = b; blockDim.x = 256; gridDim.x = grid; threadIdx.x = t;
+                t_warp = &warps[t >> 5]; t_lane = t & 31;
+                kern(p);
+            });
+        for (auto &x : th) x.join();
+        for (auto &w : warps) pthread_barrier_destroy(&w.bar);
+    }
+}
+}
+
+extern "C" {
+// kind: 0 = bpr_step_ldg_kernel (any ld <= 128*4, any sink), 1 = bpr_step_fast_kernel (ld = 128, SINK_UPDATE),
+//       2 = bpr_step_group_kernel<8,32,0,...> (ld = 128, SINK_UPDATE; the default training kernel)
+// chunk: triples per warp chunk for kinds 0 / 1 (0 = 32); grid: CTAs to emulate
+int emu_bpr_step(const b200rec_bpr_args *args, int kind, int chunk, int grid) {
+    using namespace b200;
+    const b200rec_bpr_args &a = *args;
+    const int d4 = a.ld / 4;
+    int G = 1; while (G < d4 && G < 32) G <<= 1;
+    const int CPL = (d4 + G - 1) / G, TPW = 32 / G;
+    BprParams p; p.a = a; p.work = nullptr; p.stages = 0;
+    p.invB = a.inv_batch > 0.f ? a.inv_batch : 1.0f / (float)a.B;
+    if (chunk <= 0) chunk = 32;
+    if (chunk < TPW) chunk = TPW;
+    p.chunk = chunk; p.n_chunks = ((int64_t)a.B + chunk - 1) / chunk;
+    unsigned work = 0;
+    const bool uniq = (a.flags & B200REC_F_USERS_UNIQUE) != 0, loss = a.loss_sum != nullptr;
+    const bool idelta = (a.flags & B200REC_F_ITEM_DELTA) != 0;
+    if (kind == 0) {
+#define SINKS(GG, CC)                                                                                       \
+        switch (a.sink) {                                                                                   \
+            case B200REC_SINK_UPDATE: emu_launch(bpr_step_ldg_kernel<GG, CC, B200REC_SINK_UPDATE>, grid, p); break; \
+            case B200REC_SINK_STAGE: emu_launch(bpr_step_ldg_kernel<GG, CC, B200REC_SINK_STAGE>, grid, p); break;   \
+            case B200REC_SINK_GRAD: emu_launch(bpr_step_ldg_kernel<GG, CC, B200REC_SINK_GRAD>, grid, p); break;     \
+            default: emu_launch(bpr_step_ldg_kernel<GG, CC, B200REC_SINK_NONE>, grid, p); break;                    \
+        }
+        if (G == 1) { SINKS(1, 1) } else if (G == 2) { SINKS(2, 1) } else if (G == 4) { SINKS(4, 1) }
+        else if (G == 8) { SINKS(8, 1) } else if (G == 16) { SINKS(16, 1) }
+        else if (CPL == 1) { SINKS(32, 1) } else if (CPL == 2) { SINKS(32, 2) } else if (CPL == 3) { SINKS(32, 3) } else { SINKS(32, 4) }
+#undef SINKS
+        return 0;
+    }
+    if (a.sink != B200REC_SINK_UPDATE || a.ld != 128) return -1;
+    p.work = &work;
+#define PICK(KERN, ...)                                                                                     \
+    if (uniq) { if (loss) { if (idelta) emu_launch(KERN<__VA_ARGS__, true, true, true>, grid, p); else emu_launch(KERN<__VA_ARGS__, true, true, false>, grid, p); } \
+                else { if (idelta) emu_launch(KERN<__VA_ARGS__, true, false, true>, grid, p); else emu_launch(KERN<__VA_ARGS__, true, false, false>, grid, p); } } \
+    else { if (loss) { if (idelta) emu_launch(KERN<__VA_ARGS__, false, true, true>, grid, p); else emu_launch(KERN<__VA_ARGS__, false, true, false>, grid, p); } \
+           else { if (idelta) emu_launch(KERN<__VA_ARGS__, false, false, true>, grid, p); else emu_launch(KERN<__VA_ARGS__, false, false, false>, grid, p); } }
+    if (kind == 1) { PICK(bpr_step_fast_kernel, 1) return 0; }
+    p.chunk = 32; p.n_chunks = ((int64_t)a.B + 31) / 32;
+    if (kind == 2) { PICK(bpr_step_group_kernel, 8, 32, 0) return 0; }
+    if (kind == 3) { PICK(bpr_step_group_kernel, 16, 32, 1) return 0; }
+#undef PICK
+    return -1;
+}
+
+// <<<grid, 256>>> bpr_apply_kernel: no warp collectives, plain thread loop
+void emu_bpr_apply(float *U, float *V, int ld, const int32_t *users, const int32_t *pos, const int32_t *neg, int B,
+                   const float *stage, int grid) {
+    emu_launch([=](int) { b200::bpr_apply_kernel(U, V, ld, users, pos, neg, B, stage); }, grid, 0);
+}
+}
+'''
+
+
+def _braces(src, start):
+    k = src.index("{", start)
+    depth, e = 0, k
+    while True:
+        depth += {"{": 1, "}": -1}.get(src[e], 0)
+        e += 1
+        if depth == 0:
+            return e
+
+
+def _definition(src, pattern):
+    """Text of the definition whose header matches `pattern` (incl. a `template <...>` line right above it)."""
+    m = re.search(pattern, src)
+    assert m, pattern
+    start = m.start()
+    prev_nl = src.rfind("\n", 0, start - 1)
+    prev_line = src[prev_nl + 1:start]
+    if prev_line.lstrip().startswith("template"):
+        start = prev_nl + 1
+    end = _braces(src, m.end())
+    text = src[start:end]
+    return text + (";" if re.match(r"\s*(template[^\n]*\n)?\s*struct", text) else "")
+
+
+def build(out_dir):
+    common = open(os.path.join(CSRC, "common.cuh")).read()
+    sampler = open(os.path.join(CSRC, "sampler.cuh")).read()
+    step = open(os.path.join(CSRC, "bpr_step.cu")).read()
+    dev = r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\("
+    glob = r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+%s\s*\("
+    pieces = [
+        "namespace b200 {",
+        _definition(common, dev % "mix64"), _definition(common, dev % "rng_u32"), "}",
+        sampler[sampler.index("namespace b200 {"):],
+        "namespace b200 {",
+        _definition(step, r"struct BprParams\s*"),
+        _definition(step, dev % "bpr_grad"), _definition(step, dev % "softplus_neg"),
+        _definition(step, dev % "group_sum"), _definition(step, dev % "sink_chunk"),
+        _definition(step, glob % "bpr_step_ldg_kernel"),
+        _definition(step, r"struct RowSet\s*"), _definition(step, glob % "bpr_step_fast_kernel"),
+        _definition(step, r"struct GroupSet\s*"), _definition(step, glob % "bpr_step_group_kernel"),
+        _definition(step, glob % "bpr_apply_kernel"),
+        "}",
+    ]
+    text = _PRELUDE + "\n".join(pieces) + _LAUNCH
+    text = re.sub(r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+(?=\w+\s*\()", "static void ", text)
+    text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
+    text = text.replace("#pragma unroll", "// unroll")
+    text = re.sub(r"\b__(expf|logf|frcp_rn)\(", r"emu_\1(", text)
+    src = os.path.join(out_dir, "simt_bpr.cpp")
+    lib = os.path.join(out_dir, "libsimt_bpr.so")
+    with open(src, "w") as f:
+        f.write(text)
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I",
+                        os.path.join(ROOT, "include"), src, "-o", lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    h = C.CDLL(lib)
+    h.emu_bpr_step.restype = C.c_int
+    h.emu_bpr_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    h.emu_bpr_apply.restype = None
+    h.emu_bpr_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return h
