@@ -39,9 +39,13 @@ struct Dim3 { int x; };
 static thread_local Dim3 blockIdx, blockDim, threadIdx, gridDim;
 
 struct WarpCtx { pthread_barrier_t bar; uint64_t xchg[32]; };
+struct BlockCtx { pthread_barrier_t bar; };
 static thread_local WarpCtx *t_warp;
+static thread_local BlockCtx *t_block;
 static thread_local int t_lane;
 static inline void warp_bar() { pthread_barrier_wait(&t_warp->bar); }
+static inline void __syncthreads() { pthread_barrier_wait(&t_block->bar); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
     uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
@@ -56,8 +60,29 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     warp_bar(); return r;
 }
 static inline void __syncwarp() { warp_bar(); }
+// lanes holding the same value (the kernels only pass full masks)
+static inline unsigned __match_any_sync(unsigned, int v) {
+    t_warp->xchg[t_lane] = (uint64_t)(uint32_t)v; warp_bar();
+    unsigned r = 0; for (int l = 0; l < 32; ++l) r |= (unsigned)(t_warp->xchg[l] == (uint64_t)(uint32_t)v) << l;
+    warp_bar(); return r;
+}
+static inline int __reduce_max_sync(unsigned, int v) {
+    t_warp->xchg[t_lane] = (uint64_t)(int64_t)v; warp_bar();
+    int r = v; for (int l = 0; l < 32; ++l) { const int o = (int)(int64_t)t_warp->xchg[l]; r = o > r ? o : r; }
+    warp_bar(); return r;
+}
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+// position of the offset-th set bit of mask at or above `base` (offset > 0), 0xffffffff when there is none (CUDA __fns)
+static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
+    if (offset <= 0) { fprintf(stderr, "simt_host: __fns only emulated for offset > 0\n"); abort(); }
+    for (unsigned b = base; b < 32; ++b) if ((mask >> b) & 1u) { if (--offset == 0) return b; }
+    return 0xffffffffu;
+}
+static inline int min(int a, int b) { return a < b ? a : b; }
 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline void atomic_addf(float *p, float v) {
     uint32_t *u = reinterpret_cast<uint32_t *>(p), old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
     do { float f; memcpy(&f, &old, 4); f += v; memcpy(&neu, &f, 4); }
@@ -90,26 +115,32 @@ static inline void red4_bf16(__nv_bfloat16 *, float4) { fprintf(stderr, "simt_ho
 }
 '''
 
-_LAUNCH = r'''
+_LAUNCHER = r'''
 namespace {
 // <<<grid, 256>>>: CTAs one after another, the 8 warps of a CTA concurrently, every lane a host thread
 template <class K, class P> void emu_launch(K kern, int grid, const P &p) {
     for (int b = 0; b < grid; ++b) {
         std::vector<WarpCtx> warps(8);
+        BlockCtx block;
+        pthread_barrier_init(&block.bar, nullptr, 256);
         for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
         std::vector<std::thread> th;
         for (int t = 0; t < 256; ++t)
             th.emplace_back([&, t, b]() {
                 blockIdx.x = b; blockDim.x = 256; gridDim.x = grid; threadIdx.x = t;
-                t_warp = &warps[t >> 5]; t_lane = t & 31;
+                t_warp = &warps[t >> 5]; t_block = &block; t_lane = t & 31;
                 kern(p);
             });
         for (auto &x : th) x.join();
         for (auto &w : warps) pthread_barrier_destroy(&w.bar);
+        pthread_barrier_destroy(&block.bar);
     }
 }
 }
 
+'''
+
+_LAUNCH = r'''
 extern "C" {
 // kind: 0 = bpr_step_ldg_kernel (any ld <= 128*4, any sink), 1 = bpr_step_fast_kernel (ld = 128, SINK_UPDATE),
 //       2 = bpr_step_group_kernel<8,32,0,...> (ld = 128, SINK_UPDATE; the default training kernel)
@@ -210,7 +241,7 @@ def build(out_dir):
         _definition(step, glob % "bpr_apply_kernel"),
         "}",
     ]
-    text = _PRELUDE + "\n".join(pieces) + _LAUNCH
+    text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _LAUNCH
     text = re.sub(r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+(?=\w+\s*\()", "static void ", text)
     text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
     text = text.replace("#pragma unroll", "// unroll")
@@ -227,4 +258,80 @@ def build(out_dir):
     h.emu_bpr_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     h.emu_bpr_apply.restype = None
     h.emu_bpr_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the multi-GPU kernels of csrc/p2p.cu: route (sample + bucket by owner) and the fused P2P step, W ranks in one process
+# ---------------------------------------------------------------------------------------------------------------------
+_P2P_WRAP = r"""
+extern "C" {
+void emu_p2p_route(const b200rec_p2p_route_args *a, int grid) {
+    memset(a->out_cnt, 0, sizeof(int32_t) * a->world);               // b200rec_p2p_route: cudaMemsetAsync(out_cnt)
+    if (a->B == 0) return;
+    emu_launch(b200::p2p_route_kernel, grid, *a);
+}
+// variant: 0 = p2p_step_kernel (warp per row, any ld), 8 / 16 = p2p_step_group_kernel<G> (ld = 128; 16 is the default)
+int emu_p2p_step(const b200rec_p2p_step_args *a, int variant, int grid) {
+    using namespace b200;
+    P2PParams p; p.a = *a; unsigned work = 0; p.work = &work;
+    const int cpl = (a->ld / 4 + 31) / 32;
+    const bool uniq = (a->flags & B200REC_F_USERS_UNIQUE) != 0, loss = a->loss_sum != nullptr;
+#define PICK2(KERN, X)                                                                                     \
+    if (uniq) { if (loss) emu_launch(KERN<X, true, true>, grid, p); else emu_launch(KERN<X, true, false>, grid, p); } \
+    else { if (loss) emu_launch(KERN<X, false, true>, grid, p); else emu_launch(KERN<X, false, false>, grid, p); }
+    if (variant > 0) {
+        if (a->ld != 128) return -1;
+        if (variant == 16) { PICK2(p2p_step_group_kernel, 16) } else { PICK2(p2p_step_group_kernel, 8) }
+        return 0;
+    }
+    switch (cpl) {
+        case 1: PICK2(p2p_step_kernel, 1) break;
+        case 2: PICK2(p2p_step_kernel, 2) break;
+        case 3: PICK2(p2p_step_kernel, 3) break;
+        default: PICK2(p2p_step_kernel, 4) break;
+    }
+#undef PICK2
+    return 0;
+}
+}
+"""
+
+
+def build_p2p(out_dir):
+    common = open(os.path.join(CSRC, "common.cuh")).read()
+    sampler = open(os.path.join(CSRC, "sampler.cuh")).read()
+    p2p = open(os.path.join(CSRC, "p2p.cu")).read()
+    dev = r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\("
+    glob = r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+%s\s*\("
+    pieces = [
+        "namespace b200 {",
+        _definition(common, dev % "mix64"), _definition(common, dev % "rng_u32"), "}",
+        sampler[sampler.index("namespace b200 {"):],
+        "namespace b200 {",
+        "constexpr int kRouteThreads = 256;", "constexpr int kRouteTilesPerCta = 4;",
+        _definition(p2p, dev % "owner_of"), _definition(p2p, glob % "p2p_route_kernel"),
+        _definition(p2p, dev % "chunk_of"),
+        _definition(p2p, r"struct P2PRows\s*"), _definition(p2p, r"struct P2PParams\s*"),
+        _definition(p2p, glob % "p2p_step_kernel"), _definition(p2p, glob % "p2p_step_group_kernel"),
+        "}",
+    ]
+    text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _P2P_WRAP
+    text = re.sub(r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+(?=\w+\s*\()", "static void ", text)
+    text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
+    text = text.replace("__grid_constant__", "").replace("__shared__", "static")     # CTAs run one at a time
+    text = re.sub(r"#pragma unroll( 1)?", "// unroll", text)
+    text = re.sub(r"\b__(expf|logf|frcp_rn)\(", r"emu_\1(", text)
+    src = os.path.join(out_dir, "simt_p2p.cpp")
+    lib = os.path.join(out_dir, "libsimt_p2p.so")
+    with open(src, "w") as f:
+        f.write(text)
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I",
+                        os.path.join(ROOT, "include"), src, "-o", lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    h = C.CDLL(lib)
+    h.emu_p2p_route.restype = None
+    h.emu_p2p_route.argtypes = [C.c_void_p, C.c_int]
+    h.emu_p2p_step.restype = C.c_int
+    h.emu_p2p_step.argtypes = [C.c_void_p, C.c_int, C.c_int]
     return h
