@@ -35,7 +35,7 @@ _PRELUDE = r'''
 
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
-struct Dim3 { int x; };
+struct Dim3 { int x, y; };
 static thread_local Dim3 blockIdx, blockDim, threadIdx, gridDim;
 
 struct WarpCtx { pthread_barrier_t bar; uint64_t xchg[32]; };
@@ -118,7 +118,8 @@ static inline void red4_bf16(__nv_bfloat16 *, float4) { fprintf(stderr, "simt_ho
 _LAUNCHER = r'''
 namespace {
 // <<<grid, 256>>>: CTAs one after another, the 8 warps of a CTA concurrently, every lane a host thread
-template <class K, class P> void emu_launch(K kern, int grid, const P &p) {
+template <class K, class P> void emu_launch(K kern, int grid, const P &p, int grid_y = 1) {
+    for (int by = 0; by < grid_y; ++by)
     for (int b = 0; b < grid; ++b) {
         std::vector<WarpCtx> warps(8);
         BlockCtx block;
@@ -126,8 +127,9 @@ template <class K, class P> void emu_launch(K kern, int grid, const P &p) {
         for (auto &w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
         std::vector<std::thread> th;
         for (int t = 0; t < 256; ++t)
-            th.emplace_back([&, t, b]() {
-                blockIdx.x = b; blockDim.x = 256; gridDim.x = grid; threadIdx.x = t;
+            th.emplace_back([&, t, b, by]() {
+                blockIdx.x = b; blockIdx.y = by; blockDim.x = 256; blockDim.y = 1; gridDim.x = grid; gridDim.y = grid_y;
+                threadIdx.x = t; threadIdx.y = 0;
                 t_warp = &warps[t >> 5]; t_block = &block; t_lane = t & 31;
                 kern(p);
             });
@@ -334,4 +336,78 @@ def build_p2p(out_dir):
     h.emu_p2p_route.argtypes = [C.c_void_p, C.c_int]
     h.emu_p2p_step.restype = C.c_int
     h.emu_p2p_step.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# exact scoring + masked top-K (csrc/score_exact.cu + topk_list.cuh): the exactness anchor of the scoring path
+# ---------------------------------------------------------------------------------------------------------------------
+_SCORE_WRAP = r"""
+extern "C" {
+// score_topk_exact as launch_exact<TM> drives it: TM = 64 for k <= 256, else 16; splits > 1 = item-split + merge form
+int emu_score_topk_exact(const float *U, const float *V, int ld, int d, const int32_t *users, int n_users, int num_items,
+                         const int64_t *mi, const int32_t *mx, int k, int32_t *oi, float *os, float *dense, int splits) {
+    using namespace b200;
+    const bool small = k <= 256;
+    const int TM = small ? 64 : 16, TN = 4096 / TM;
+    const int grid = (n_users + TM - 1) / TM, n_tiles = (num_items + TN - 1) / TN;
+    auto run = [&](int gy, int items_per_split, int32_t *o_i, float *o_s, float *dn, uint64_t *part) {
+        if (small) emu_launch([=](int) { score_topk_exact_kernel<64>(U, V, ld, d, users, n_users, num_items, mi, mx, k, o_i, o_s, dn, items_per_split, part); }, grid, 0, gy);
+        else emu_launch([=](int) { score_topk_exact_kernel<16>(U, V, ld, d, users, n_users, num_items, mi, mx, k, o_i, o_s, dn, items_per_split, part); }, grid, 0, gy);
+    };
+    if (splits > n_tiles) splits = n_tiles;
+    if (splits <= 1 || k <= 0 || dense) { run(1, num_items, oi, os, dense, nullptr); return 1; }
+    const int tiles_per_split = (n_tiles + splits - 1) / splits;
+    splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    std::vector<uint64_t> part((size_t)n_users * splits * k);
+    run(splits, tiles_per_split * TN, nullptr, nullptr, nullptr, part.data());
+    const uint64_t *pp = part.data();
+    emu_launch([=](int) { merge_topk_kernel(pp, n_users, splits, k, oi, os); }, (n_users + 7) / 8 < 2 ? (n_users + 7) / 8 : 2, 0);
+    return splits;
+}
+void emu_topk_rows(const float *scores, int64_t row_stride, int rows, int cols, int k, int32_t *out_idx) {
+    emu_launch([=](int) { b200::topk_rows_kernel(scores, row_stride, rows, cols, k, out_idx); }, 2, 0);
+}
+}
+"""
+
+
+def build_score(out_dir):
+    common = open(os.path.join(CSRC, "common.cuh")).read()
+    topk = open(os.path.join(CSRC, "topk_list.cuh")).read()
+    ex = open(os.path.join(CSRC, "score_exact.cu")).read()
+    dev = r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\("
+    glob = r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+%s\s*\("
+    pieces = [
+        "static inline uint32_t __float_as_uint(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }",
+        "static inline float __uint_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }",
+        "namespace b200 {",
+        "\n".join(_definition(common, dev % n) for n in ("f2ord", "ord2f", "make_key", "key_id", "key_score")), "}",
+        topk[topk.index("namespace b200 {"):],
+        "namespace b200 {",
+        "constexpr int kKSlab = 32;", "constexpr int kPad = kKSlab + 4;",
+        _definition(ex, r"struct ExactCfg\s*"),
+        _definition(ex, glob % "score_topk_exact_kernel"), _definition(ex, glob % "merge_topk_kernel"),
+        _definition(ex, glob % "topk_rows_kernel"),
+        "}",
+    ]
+    text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _SCORE_WRAP
+    text = re.sub(r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+(?=\w+\s*\()", "static void ", text)
+    text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
+    text = text.replace("extern __shared__ __align__(16) unsigned char smem_raw[];",
+                        "alignas(16) static unsigned char smem_raw[227 * 1024];")       # CTAs run one at a time
+    text = re.sub(r"#pragma unroll( \d+)?", "// unroll", text)
+    src = os.path.join(out_dir, "simt_score.cpp")
+    lib = os.path.join(out_dir, "libsimt_score.so")
+    with open(src, "w") as f:
+        f.write(text)
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I",
+                        os.path.join(ROOT, "include"), src, "-o", lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    h = C.CDLL(lib)
+    P, I = C.c_void_p, C.c_int
+    h.emu_score_topk_exact.restype = I
+    h.emu_score_topk_exact.argtypes = [P, P, I, I, P, I, I, P, P, I, P, P, P, I]
+    h.emu_topk_rows.restype = None
+    h.emu_topk_rows.argtypes = [P, C.c_int64, I, I, I, P]
     return h
