@@ -112,7 +112,10 @@ static inline float4 ld4_hint(const float *p, uint64_t) { return ld4(p); }
 static inline void st4_hint(float *p, float4 v, uint64_t) { st4(p, v); }
 static inline void red4_hint(float *p, float4 v, uint64_t) { red4(p, v); }
 static inline void red4_bf16(__nv_bfloat16 *, float4) { fprintf(stderr, "simt_host: bf16 sink not emulated\n"); abort(); }
+static inline float4 ldg4(const float *p) { return ld4(p); }
 }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 '''
 
 _LAUNCHER = r'''
@@ -365,6 +368,18 @@ int emu_score_topk_exact(const float *U, const float *V, int ld, int d, const in
     emu_launch([=](int) { merge_topk_kernel(pp, n_users, splits, k, oi, os); }, (n_users + 7) / 8 < 2 ? (n_users + 7) / 8 : 2, 0);
     return splits;
 }
+// the exact fp32 re-rank of the tensor-core path (csrc/score_tc.cu): staged = 1 selects rerank_staged_kernel
+void emu_rerank(const float *U, const float *V, int ld, int d, const int32_t *users, int n_rows, int k, const int64_t *mi,
+                const int32_t *mx, const int32_t *item_of_pos, const uint64_t *cand, const int32_t *cnt, int32_t *oi,
+                float *os, int32_t *redo, int32_t *redo_n, int staged) {
+    const int grid = (n_rows + 7) / 8 < 3 ? (n_rows + 7) / 8 : 3;
+    if (staged) emu_launch([=](int) { b200::rerank_staged_kernel(U, V, ld, d, users, n_rows, k, mi, mx, item_of_pos, cand, cnt, oi, os, redo, redo_n); }, grid, 0);
+    else emu_launch([=](int) { b200::rerank_kernel(U, V, ld, d, users, n_rows, k, mi, mx, item_of_pos, cand, cnt, oi, os, redo, redo_n); }, grid, 0);
+}
+void emu_bloom(const int32_t *users, int n_rows, const int64_t *mi, const int32_t *mx, const int32_t *inv_perm,
+               unsigned long long *wide) {
+    emu_launch([=](int) { b200::bloom_kernel(users, n_rows, mi, mx, inv_perm, wide); }, (n_rows + 7) / 8, 0);
+}
 void emu_topk_rows(const float *scores, int64_t row_stride, int rows, int cols, int k, int32_t *out_idx) {
     emu_launch([=](int) { b200::topk_rows_kernel(scores, row_stride, rows, cols, k, out_idx); }, 2, 0);
 }
@@ -376,6 +391,7 @@ def build_score(out_dir):
     common = open(os.path.join(CSRC, "common.cuh")).read()
     topk = open(os.path.join(CSRC, "topk_list.cuh")).read()
     ex = open(os.path.join(CSRC, "score_exact.cu")).read()
+    tc = open(os.path.join(CSRC, "score_tc.cu")).read()
     dev = r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\("
     glob = r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+%s\s*\("
     pieces = [
@@ -389,8 +405,12 @@ def build_score(out_dir):
         _definition(ex, r"struct ExactCfg\s*"),
         _definition(ex, glob % "score_topk_exact_kernel"), _definition(ex, glob % "merge_topk_kernel"),
         _definition(ex, glob % "topk_rows_kernel"),
+        "constexpr int kCand = 512;", "constexpr int kRerankRC = 8;", "constexpr int kWideWords = 33;",
+        _definition(tc, glob % "rerank_kernel"), _definition(tc, glob % "rerank_staged_kernel"),
+        _definition(tc, dev % "wide_hash"), _definition(tc, glob % "bloom_kernel"),
         "}",
     ]
+    assert "constexpr int kCand = 512;" in tc and "constexpr int kRerankRC = 8;" in tc and "constexpr int kWideWords = 33;" in tc
     text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _SCORE_WRAP
     text = re.sub(r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+(?=\w+\s*\()", "static void ", text)
     text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
@@ -410,4 +430,8 @@ def build_score(out_dir):
     h.emu_score_topk_exact.argtypes = [P, P, I, I, P, I, I, P, P, I, P, P, P, I]
     h.emu_topk_rows.restype = None
     h.emu_topk_rows.argtypes = [P, C.c_int64, I, I, I, P]
+    h.emu_rerank.restype = None
+    h.emu_rerank.argtypes = [P, P, I, I, P, I, I, P, P, P, P, P, P, P, P, P, I]
+    h.emu_bloom.restype = None
+    h.emu_bloom.argtypes = [P, I, P, P, P, P]
     return h

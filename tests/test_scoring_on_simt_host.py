@@ -109,3 +109,72 @@ def test_topk_rows_kernel_vs_oracle(simt, oracle_c):
         out = np.zeros((11, k), np.int32)
         simt.emu_topk_rows(S.ctypes.data, 170, 11, 170, k, out.ctypes.data)
         np.testing.assert_array_equal(out, oracle_c.topk(S, k))
+
+
+# ---- the CUDA-core half of the tensor-core path (csrc/score_tc.cu): exact re-rank of candidate lists, mask filters --------
+@pytest.mark.parametrize("staged", [0, 1])
+@pytest.mark.parametrize("d", [20, 128, 200])
+def test_rerank_kernels_turn_candidate_lists_into_the_exact_topk(simt, oracle_c, d, staged):
+    """rerank_kernel / rerank_staged_kernel: given candidate lists that CONTAIN the exact top-k (what the tcgen05 pass
+    guarantees) plus anything else - masked items, duplicates of the approximate-score word, the maybe-masked flag bit -
+    the output is the exact masked top-k, bit-identical to the C oracle; rows flagged cnt = -1 and rows with fewer than k
+    unmasked candidates go to the redo list (the exact kernel finishes them)."""
+    rng = np.random.default_rng(d + staged)
+    nu, ni, k, n_rows = 60, 500, 10, 37
+    U, V, ld = _tables(rng, nu, ni, d)
+    mask = _mask(rng, nu, ni, 0, 40)
+    users = rng.permutation(nu)[:n_rows].astype(np.int32)
+    order = rng.permutation(ni).astype(np.int32)                            # item at visiting position p
+    pos_of = np.empty(ni, np.int64); pos_of[order] = np.arange(ni)
+    ref_idx, ref_sc = oracle_c.score_topk(U, V, d, users, ni, mask[0], mask[1], k)
+    S = U[users, :d].astype(np.float64) @ V[:, :d].astype(np.float64).T
+    cand = np.zeros((n_rows, 512), np.uint64); cnt = np.zeros(n_rows, np.int32)
+    starved = 5                                                             # this row gets fewer than k unmasked candidates
+    for r in range(n_rows):
+        best = np.argsort(-S[r])[: k + 25]                                  # incl. masked ones: the re-rank must drop them
+        extra = rng.choice(ni, 120, replace=False)
+        items = np.unique(np.concatenate([best, extra]))
+        if r == starved:
+            m = mask[1][mask[0][users[r]]:mask[0][users[r] + 1]]
+            items = np.concatenate([m, np.setdiff1d(np.arange(ni), m)[: k - 3]])
+        rng.shuffle(items)
+        words = pos_of[items].astype(np.uint64) | (rng.integers(0, 2, len(items)).astype(np.uint64) << np.uint64(31)) \
+            | (rng.integers(0, 2**32, len(items)).astype(np.uint64) << np.uint64(32))
+        cand[r, :len(items)] = words; cnt[r] = len(items)
+    overflow = [3, 20]
+    cnt[overflow] = -1
+    oi = np.full((n_rows, k), -5, np.int32); os_ = np.full((n_rows, k), np.nan, np.float32)
+    redo = np.full(n_rows, -1, np.int32); redo_n = np.zeros(1, np.int32)
+    P = lambda a: a.ctypes.data
+    simt.emu_rerank(P(U), P(V), ld, d, P(users), n_rows, k, P(mask[0]), P(mask[1]), P(order), P(cand), P(cnt), P(oi), P(os_),
+                    P(redo), P(redo_n), staged)
+    assert sorted(redo[:redo_n[0]].tolist()) == sorted(overflow + [starved])
+    done = np.setdiff1d(np.arange(n_rows), overflow + [starved])
+    np.testing.assert_array_equal(oi[done], ref_idx[done])
+    np.testing.assert_array_equal(os_[done], ref_sc[done])                  # same k-ascending fp32 FMA chain: bit for bit
+    assert (oi[overflow + [starved]] == -5).all()                           # redo rows are left to the exact kernel
+
+
+def test_mask_filters_have_no_false_negatives(simt):
+    """bloom_kernel: per scored row an EXACT bitmap of visiting positions 0..63 and a 2048-bit filter over all positions
+    of the row's masked items - the candidate pass may call an item 'certainly unmasked' only when its bit is clear, so a
+    set of masked positions must never read clear (no false negatives); the bitmap has no false positives either."""
+    rng = np.random.default_rng(3)
+    nu, ni, n_rows = 50, 3000, 21
+    mask = _mask(rng, nu, ni, 0, 200)
+    users = rng.permutation(nu)[:n_rows].astype(np.int32)
+    inv_perm = rng.permutation(ni).astype(np.int32)                         # item id -> visiting position
+    wide = np.full((n_rows, 33), 0xFFFFFFFFFFFFFFFF, np.uint64)             # the kernel must clear its rows first
+    P = lambda a: a.ctypes.data
+    simt.emu_bloom(P(users), n_rows, P(mask[0]), P(mask[1]), P(inv_perm), P(wide))
+    for r, u in enumerate(users):
+        pos = inv_perm[mask[1][mask[0][u]:mask[0][u + 1]]].astype(np.uint32)
+        exact = 0
+        for p_ in pos[pos < 64]:
+            exact |= 1 << int(p_)
+        assert int(wide[r, 0]) == exact                                     # exact head bitmap
+        h = ((pos.astype(np.uint64) * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) >> np.uint64(21)
+        for hh in h:
+            assert (int(wide[r, 1 + (int(hh) >> 6)]) >> (int(hh) & 63)) & 1  # every masked position is flagged
+        bits = sum(bin(int(w)).count("1") for w in wide[r, 1:])
+        assert bits <= len(pos)                                             # and nothing else was set
