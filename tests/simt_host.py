@@ -31,6 +31,8 @@ _PRELUDE = r'''
 #include <pthread.h>
 #include <thread>
 #include <vector>
+#include <map>
+#include <mutex>
 #include "b200rec.h"
 
 struct float4 { float x, y, z, w; };
@@ -38,7 +40,19 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 v 
 struct Dim3 { int x, y; };
 static thread_local Dim3 blockIdx, blockDim, threadIdx, gridDim;
 
-struct WarpCtx { pthread_barrier_t bar; uint64_t xchg[32]; };
+struct WarpCtx {
+    pthread_barrier_t bar; uint64_t xchg[32];
+    std::mutex mu; std::map<unsigned, pthread_barrier_t *> sub;          // rendezvous of a sub-warp group (partial member mask)
+    pthread_barrier_t *group(unsigned mask) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = sub.find(mask);
+        if (it != sub.end()) return it->second;
+        pthread_barrier_t *b = new pthread_barrier_t;
+        pthread_barrier_init(b, nullptr, __builtin_popcount(mask));
+        sub[mask] = b; return b;
+    }
+    ~WarpCtx() { for (auto &kv : sub) { pthread_barrier_destroy(kv.second); delete kv.second; } }
+};
 struct BlockCtx { pthread_barrier_t bar; };
 static thread_local WarpCtx *t_warp;
 static thread_local BlockCtx *t_block;
@@ -47,10 +61,12 @@ static inline void warp_bar() { pthread_barrier_wait(&t_warp->bar); }
 static inline void __syncthreads() { pthread_barrier_wait(&t_block->bar); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
-template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+// member mask = the whole warp, or one sub-warp group whose lanes (and only they) all make the call (csrc/spmm.cu)
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) {
     uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
-    t_warp->xchg[t_lane] = raw; warp_bar();
-    const uint64_t r = t_warp->xchg[src & 31]; warp_bar();
+    pthread_barrier_t *b = (mask == 0xffffffffu) ? &t_warp->bar : ((mask & (mask - 1)) ? t_warp->group(mask) : nullptr);
+    t_warp->xchg[t_lane] = raw; if (b) pthread_barrier_wait(b);
+    const uint64_t r = t_warp->xchg[src & 31]; if (b) pthread_barrier_wait(b);
     T out; memcpy(&out, &r, sizeof(T)); return out;
 }
 template <class T> static inline T __shfl_xor_sync(unsigned m, T v, int o) { return __shfl_sync(m, v, t_lane ^ o); }
@@ -434,4 +450,61 @@ def build_score(out_dir):
     h.emu_rerank.argtypes = [P, P, I, I, P, I, I, P, P, P, P, P, P, P, P, P, I]
     h.emu_bloom.restype = None
     h.emu_bloom.argtypes = [P, I, P, P, P, P]
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LightGCN / NGCF propagation: CSR SpMM (csrc/spmm.cu), plain and long-row split form
+# ---------------------------------------------------------------------------------------------------------------------
+_SPMM_WRAP = r"""
+extern "C" {
+// spmm_dispatch + launch_spmm: G lanes per row, CPL float4 per lane; n_seg > 0 = split plan for the long rows
+int emu_spmm(const int64_t *indptr, const int32_t *indices, const float *values, int n_rows, const float *X, int ldx, int d,
+             float *Y, int ldy, float *acc, int ldacc, float sc, int acc_init, int64_t seg_len, const int64_t *seg_begin,
+             const int64_t *seg_end, int n_seg, const int32_t *long_rows, const int32_t *long_seg_ptr, int n_long,
+             float *partial, int grid) {
+    using namespace b200;
+    const int d4 = (d + 3) / 4;
+    int G = 1; while (G < d4 && G < 32) G <<= 1;
+    const int CPL = (d4 + G - 1) / G;
+    const int64_t skip = n_seg > 0 ? seg_len : (int64_t)-1;
+    const int ldp = d4 * 4;
+#define RUN(GG, CC)                                                                                                   \
+    {   emu_launch([=](int) { spmm_csr_kernel<GG, CC>(indptr, indices, values, n_rows, X, ldx, d4, Y, ldy, acc, ldacc, sc, acc_init, skip); }, grid, 0); \
+        if (n_seg > 0) {                                                                                              \
+            emu_launch([=](int) { spmm_segment_kernel<GG, CC>(indices, values, seg_begin, seg_end, n_seg, X, ldx, d4, partial, ldp); }, grid, 0); \
+            emu_launch([=](int) { spmm_long_rows_kernel<GG, CC>(long_rows, long_seg_ptr, n_long, partial, ldp, X, ldx, d4, Y, ldy, acc, ldacc, sc, acc_init); }, 1, 0); \
+        } return G * 100 + CPL; }
+    switch (G) {
+        case 1: RUN(1, 1) case 2: RUN(2, 1) case 4: RUN(4, 1) case 8: RUN(8, 1) case 16: RUN(16, 1)
+        default: switch (CPL) { case 1: RUN(32, 1) case 2: RUN(32, 2) case 3: RUN(32, 3) default: RUN(32, 4) }
+    }
+#undef RUN
+}
+}
+"""
+
+
+def build_spmm(out_dir):
+    sp = open(os.path.join(CSRC, "spmm.cu")).read()
+    dev = r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\("
+    glob = r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+%s\s*\("
+    pieces = ["namespace b200 {", _definition(sp, dev % "accumulate_range"), _definition(sp, dev % "store_row"),
+              _definition(sp, glob % "spmm_csr_kernel"), _definition(sp, glob % "spmm_segment_kernel"),
+              _definition(sp, glob % "spmm_long_rows_kernel"), "}"]
+    text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _SPMM_WRAP
+    text = re.sub(r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+(?=\w+\s*\()", "static void ", text)
+    text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
+    text = re.sub(r"#pragma unroll( \d+)?", "// unroll", text)
+    src = os.path.join(out_dir, "simt_spmm.cpp")
+    lib = os.path.join(out_dir, "libsimt_spmm.so")
+    with open(src, "w") as f:
+        f.write(text)
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I",
+                        os.path.join(ROOT, "include"), src, "-o", lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    h = C.CDLL(lib)
+    P, I, L = C.c_void_p, C.c_int, C.c_int64
+    h.emu_spmm.restype = I
+    h.emu_spmm.argtypes = [P, P, P, I, P, I, I, P, I, P, I, C.c_float, I, L, P, P, I, P, P, I, P, I]
     return h
