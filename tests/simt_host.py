@@ -99,6 +99,8 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline void atomic_addf(float *p, float v);
+static inline float atomicAdd(float *p, float v) { atomic_addf(p, v); return 0.f; }
 static inline void atomic_addf(float *p, float v) {
     uint32_t *u = reinterpret_cast<uint32_t *>(p), old = __atomic_load_n(u, __ATOMIC_RELAXED), neu;
     do { float f; memcpy(&f, &old, 4); f += v; memcpy(&neu, &f, 4); }
@@ -507,4 +509,94 @@ def build_spmm(out_dir):
     P, I, L = C.c_void_p, C.c_int, C.c_int64
     h.emu_spmm.restype = I
     h.emu_spmm.argtypes = [P, P, P, I, P, I, I, P, I, P, I, C.c_float, I, L, P, P, I, P, P, I, P, I]
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# pointwise MF step (csrc/pointwise_step.cu) and the NGCF layer kernels (csrc/ngcf.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+_PW_NGCF_WRAP = r"""
+extern "C" {
+int emu_pointwise_step(float *U, float *V, int ld, int d, const int32_t *users, const int32_t *items, const float *ratings,
+                       int B, int loss_kind, float lr, float reg, int sink, float *gU, float *gV, double *loss_sum,
+                       float inv_batch, int grid) {
+    using namespace b200;
+    PwParams p;                                                     // b200rec_pointwise_step, field for field
+    p.U = U; p.V = V; p.ld = ld; p.B = B; p.loss_kind = loss_kind; p.sink = sink;
+    p.users = users; p.items = items; p.ratings = ratings;
+    p.invB = inv_batch > 0.f ? inv_batch : 1.0f / (float)B;
+    p.lr = lr; p.regB = reg * p.invB; p.gU = gU; p.gV = gV; p.loss_sum = loss_sum;
+    const int d4 = ld / 4;
+    int G = 1; while (G < d4 && G < 32) G <<= 1;
+    const int CPL = (d4 + G - 1) / G;
+#define RUN(GG, CC) { emu_launch(pointwise_step_kernel<GG, CC>, grid, p); return GG * 100 + CC; }
+    switch (G) {
+        case 1: RUN(1, 1) case 2: RUN(2, 1) case 4: RUN(4, 1) case 8: RUN(8, 1) case 16: RUN(16, 1)
+        default: switch (CPL) { case 1: RUN(32, 1) case 2: RUN(32, 2) case 3: RUN(32, 3) default: RUN(32, 4) }
+    }
+#undef RUN
+}
+void emu_ngcf_forward(const float *ego, const float *side, const float *Wg, const float *bg, const float *Wb, const float *bb,
+                      int n_rows, int ld, int d, int layer, float p_drop, uint64_t seed, uint64_t step, float *ego_next,
+                      float *nrm, float *acc, float acc_scale, int grid) {
+    using namespace b200;
+    NgcfFwd a;
+    a.ego = ego; a.side = side; a.Wg = Wg; a.bg = bg; a.Wb = Wb; a.bb = bb; a.ego_next = ego_next; a.nrm = nrm;
+    a.acc = acc; a.acc_scale = acc_scale; a.N = n_rows; a.ld = ld; a.d = d; a.layer = layer; a.p_drop = p_drop;
+    a.seed = seed; a.step = step;
+    emu_launch(ngcf_fwd_kernel, grid, a);
+}
+void emu_ngcf_backward(const float *g_out, const float *g_next, const float *ego, const float *side, const float *ego_next,
+                       const float *nrm, const float *Wg, const float *Wb, int n_rows, int ld, int d, int layer, float p_drop,
+                       uint64_t seed, uint64_t step, float acc_scale, float *g_z, float *g_side, float *g_ego, float *dWg,
+                       float *dWb, float *db, int grid) {
+    using namespace b200;
+    NgcfBwd a;
+    a.gout = g_out; a.gnext = g_next; a.ego = ego; a.side = side; a.ego_next = ego_next; a.nrm = nrm; a.Wg = Wg; a.Wb = Wb;
+    a.gz = g_z; a.gside = g_side; a.gego = g_ego; a.acc_scale = acc_scale; a.N = n_rows; a.ld = ld; a.d = d; a.layer = layer;
+    a.p_drop = p_drop; a.seed = seed; a.step = step;
+    emu_launch(ngcf_bwd_row_kernel, grid, a);
+    int rows_per_cta = (n_rows + grid - 1) / grid;
+    rows_per_cta = (rows_per_cta + 31) / 32 * 32;
+    const int g2 = (n_rows + rows_per_cta - 1) / rows_per_cta;
+    emu_launch([=](int) { ngcf_wgrad_kernel(ego, side, g_z, n_rows, ld, d, rows_per_cta, dWg, dWb, db); }, g2, 0);
+}
+}
+"""
+
+
+def build_pw_ngcf(out_dir):
+    common = open(os.path.join(CSRC, "common.cuh")).read()
+    pw = open(os.path.join(CSRC, "pointwise_step.cu")).read()
+    ng = open(os.path.join(CSRC, "ngcf.cu")).read()
+    dev = r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\("
+    glob = r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+%s\s*\("
+    pieces = ["namespace b200 {", _definition(common, dev % "mix64"), _definition(common, dev % "rng_u32"),
+              _definition(pw, r"struct PwParams\s*"), _definition(pw, dev % "pw_group_sum"),
+              _definition(pw, glob % "pointwise_step_kernel"),
+              "constexpr int kNgcfMaxD = 64;", _definition(ng, dev % "ngcf_keep"),
+              _definition(ng, r"struct NgcfFwd\s*"), _definition(ng, glob % "ngcf_fwd_kernel"),
+              _definition(ng, r"struct NgcfBwd\s*"), _definition(ng, glob % "ngcf_bwd_row_kernel"),
+              _definition(ng, glob % "ngcf_wgrad_kernel"), "}"]
+    text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _PW_NGCF_WRAP
+    text = re.sub(r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+(?=\w+\s*\()", "static void ", text)
+    text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
+    text = text.replace("extern __shared__ float sm[];", "alignas(16) static float sm[56 * 1024];")
+    text = text.replace("__shared__", "static")
+    text = re.sub(r"#pragma unroll( \d+)?", "// unroll", text)
+    src = os.path.join(out_dir, "simt_pw_ngcf.cpp")
+    lib = os.path.join(out_dir, "libsimt_pw_ngcf.so")
+    with open(src, "w") as f:
+        f.write(text)
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I",
+                        os.path.join(ROOT, "include"), src, "-o", lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    h = C.CDLL(lib)
+    P, I, F, U64 = C.c_void_p, C.c_int, C.c_float, C.c_uint64
+    h.emu_pointwise_step.restype = I
+    h.emu_pointwise_step.argtypes = [P, P, I, I, P, P, P, I, I, F, F, I, P, P, P, F, I]
+    h.emu_ngcf_forward.restype = None
+    h.emu_ngcf_forward.argtypes = [P, P, P, P, P, P, I, I, I, I, F, U64, U64, P, P, P, F, I]
+    h.emu_ngcf_backward.restype = None
+    h.emu_ngcf_backward.argtypes = [P, P, P, P, P, P, P, P, I, I, I, I, F, U64, U64, F, P, P, P, P, P, P, I]
     return h
