@@ -99,6 +99,7 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 static inline void atomic_addf(float *p, float v);
 static inline float atomicAdd(float *p, float v) { atomic_addf(p, v); return 0.f; }
 static inline void atomic_addf(float *p, float v) {
@@ -211,6 +212,48 @@ int emu_bpr_step(const b200rec_bpr_args *args, int kind, int chunk, int grid) {
     return -1;
 }
 
+void emu_mf_forward(const float *U, const float *V, int ld, int d, const int32_t *users, const int32_t *items, int n, float *out) {
+    emu_launch([=](int) { b200::mf_forward_kernel(U, V, ld, d, users, items, n, out); }, 2, 0);
+}
+void emu_sgd_dense(float *p, const float *g, int64_t n, float lr) {
+    emu_launch([=](int) { b200::sgd_dense_kernel(p, g, n, lr); }, 2, 0);
+}
+// b200rec_adam_dense: bias corrections in double on the host, exactly as the C ABI entry point computes them
+void emu_adam_dense(float *p, const float *g, float *m, float *v, int64_t n, float lr, float b1, float b2, float eps, int step) {
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    const float step_size = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
+    emu_launch([=](int) { b200::adam_dense_kernel(p, g, m, v, n, b1, b2, eps, step_size, bc2s); }, 3, 0);
+}
+// b200rec_adam_rows (row-wise / lazy Adam)
+int emu_adam_rows(float *W, float *g, float *m, float *v, int32_t *stamp, int ld, const int32_t *ids, int n, float lr, float b1,
+                  float b2, float eps, int step) {
+    using namespace b200;
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+    const int d4 = ld / 4;
+    int G = 1; while (G < d4 && G < 32) G <<= 1;
+    const int CPL = (d4 + G - 1) / G;
+#define RUN(GG, CC) { emu_launch([=](int) { adam_rows_kernel<GG, CC>(W, g, m, v, stamp, ld, ids, n, b1, b2, eps, step_size, step); }, 2, 0); return GG * 100 + CC; }
+    switch (G) {
+        case 1: RUN(1, 1) case 2: RUN(2, 1) case 4: RUN(4, 1) case 8: RUN(8, 1) case 16: RUN(16, 1)
+        default: switch (CPL) { case 1: RUN(32, 1) case 2: RUN(32, 2) case 3: RUN(32, 3) default: RUN(32, 4) }
+    }
+#undef RUN
+}
+void emu_rows_add(float *W, int ld, const int32_t *ids, int n, const float *delta, int ldd, float scale) {
+    emu_launch([=](int) { b200::rows_add_kernel(W, ld, ids, n, delta, ldd, scale); }, 2, 0);
+}
+// the "update in place, exchange the difference" helpers of the multi-GPU layouts (n = number of floats, multiple of 4)
+void emu_delta_diff(const float *W, const float *snap, float *d_wire, float *d_own, int64_t n) {
+    emu_launch([=](int) { b200::delta_diff_kernel((const float4 *)W, (const float4 *)snap, (float4 *)d_wire, (float4 *)d_own, n / 4); }, 2, 0);
+}
+void emu_delta_apply(float *W, const float *d_sum, const float *d_own, int64_t n) {
+    emu_launch([=](int) { b200::delta_apply_kernel((float4 *)W, (const float4 *)d_sum, (const float4 *)d_own, n / 4); }, 2, 0);
+}
+void emu_add_clear(float *W, float *d, int64_t n) { emu_launch([=](int) { b200::add_clear_kernel((float4 *)W, (float4 *)d, n / 4); }, 2, 0); }
+void emu_snap_apply(float *W, const float *snap, const float *d, float scale, int64_t n) {
+    emu_launch([=](int) { b200::snap_apply_kernel((float4 *)W, (const float4 *)snap, (const float4 *)d, scale, n / 4); }, 2, 0);
+}
 // <<<grid, 256>>> bpr_apply_kernel: no warp collectives, plain thread loop
 void emu_bpr_apply(float *U, float *V, int ld, const int32_t *users, const int32_t *pos, const int32_t *neg, int B,
                    const float *stage, int grid) {
@@ -261,7 +304,11 @@ def build(out_dir):
         _definition(step, glob % "bpr_step_ldg_kernel"),
         _definition(step, r"struct RowSet\s*"), _definition(step, glob % "bpr_step_fast_kernel"),
         _definition(step, r"struct GroupSet\s*"), _definition(step, glob % "bpr_step_group_kernel"),
-        _definition(step, glob % "bpr_apply_kernel"),
+        _definition(step, glob % "bpr_apply_kernel"), _definition(step, glob % "rows_add_kernel"),
+        _definition(step, glob % "mf_forward_kernel"), _definition(step, glob % "sgd_dense_kernel"),
+        _definition(step, glob % "adam_dense_kernel"), _definition(step, glob % "adam_rows_kernel"),
+        _definition(step, glob % "delta_diff_kernel"), _definition(step, glob % "delta_apply_kernel"),
+        _definition(step, glob % "add_clear_kernel"), _definition(step, glob % "snap_apply_kernel"),
         "}",
     ]
     text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _LAUNCH
@@ -281,6 +328,15 @@ def build(out_dir):
     h.emu_bpr_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     h.emu_bpr_apply.restype = None
     h.emu_bpr_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    P, I, L, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    for name, res, args in (("emu_mf_forward", None, [P, P, I, I, P, P, I, P]), ("emu_sgd_dense", None, [P, P, L, F]),
+                            ("emu_adam_dense", None, [P, P, P, P, L, F, F, F, F, I]),
+                            ("emu_adam_rows", I, [P, P, P, P, P, I, P, I, F, F, F, F, I]),
+                            ("emu_rows_add", None, [P, I, P, I, P, I, F]), ("emu_delta_diff", None, [P, P, P, P, L]),
+                            ("emu_delta_apply", None, [P, P, P, L]), ("emu_add_clear", None, [P, P, L]),
+                            ("emu_snap_apply", None, [P, P, P, F, L])):
+        fn = getattr(h, name)
+        fn.restype, fn.argtypes = res, args
     return h
 
 
