@@ -276,6 +276,19 @@ void emu_bpr_apply(float *U, float *V, int ld, const int32_t *users, const int32
 '''
 
 
+_BUILT = {}
+
+
+def _once(fn):
+    """One compile per process and library: the test modules share the handles."""
+    def wrapper(out_dir):
+        if fn.__name__ not in _BUILT:
+            _BUILT[fn.__name__] = fn(out_dir)
+        return _BUILT[fn.__name__]
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    return wrapper
+
+
 def _braces(src, start):
     k = src.index("{", start)
     depth, e = 0, k
@@ -300,6 +313,7 @@ def _definition(src, pattern):
     return text + (";" if re.match(r"\s*(template[^\n]*\n)?\s*struct", text) else "")
 
 
+@_once
 def build(out_dir):
     common = open(os.path.join(CSRC, "common.cuh")).read()
     sampler = open(os.path.join(CSRC, "sampler.cuh")).read()
@@ -390,6 +404,7 @@ int emu_p2p_step(const b200rec_p2p_step_args *a, int variant, int grid) {
 """
 
 
+@_once
 def build_p2p(out_dir):
     common = open(os.path.join(CSRC, "common.cuh")).read()
     sampler = open(os.path.join(CSRC, "sampler.cuh")).read()
@@ -474,6 +489,7 @@ void emu_topk_rows(const float *scores, int64_t row_stride, int rows, int cols, 
 """
 
 
+@_once
 def build_score(out_dir):
     common = open(os.path.join(CSRC, "common.cuh")).read()
     topk = open(os.path.join(CSRC, "topk_list.cuh")).read()
@@ -556,6 +572,7 @@ int emu_spmm(const int64_t *indptr, const int32_t *indices, const float *values,
 """
 
 
+@_once
 def build_spmm(out_dir):
     sp = open(os.path.join(CSRC, "spmm.cu")).read()
     dev = r"__device__\s+__forceinline__\s+[\w\s\*&:]+?\b%s\s*\("
@@ -634,6 +651,7 @@ void emu_ngcf_backward(const float *g_out, const float *g_next, const float *ego
 """
 
 
+@_once
 def build_pw_ngcf(out_dir):
     common = open(os.path.join(CSRC, "common.cuh")).read()
     pw = open(os.path.join(CSRC, "pointwise_step.cu")).read()
@@ -752,6 +770,7 @@ void emu_tc_epilogue(int n_rows, int num_items, int n_tiles, int k, int d, const
 """
 
 
+@_once
 def build_tc(out_dir):
     common = open(os.path.join(CSRC, "common.cuh")).read()
     tc = open(os.path.join(CSRC, "score_tc.cu")).read()

@@ -43,8 +43,8 @@ def _run(simt, U, V, ld, d, users, ni, mask, k, splits=1, dense=False):
 
 
 @pytest.mark.parametrize("d,k,nu,ni,splits", [(32, 10, 70, 333, 1), (128, 5, 64, 200, 1), (50, 100, 20, 450, 1),
-                                              (7, 1, 9, 65, 1), (64, 10, 40, 700, 4), (20, 300, 18, 600, 1),
-                                              (20, 300, 18, 600, 2)])
+                                              (7, 1, 9, 65, 1), (64, 10, 40, 700, 4), (20, 300, 18, 420, 1),
+                                              (20, 300, 18, 420, 2)])
 def test_exact_scoring_kernel_is_bitwise_the_oracle(simt, oracle_c, d, k, nu, ni, splits):
     rng = np.random.default_rng(d * 1000 + k)
     U, V, ld = _tables(rng, nu, ni, d)

