@@ -702,7 +702,7 @@ static inline __half __float2half_rn(float x) { return (__half)x; }
 static const float *g_acc = nullptr;          // [rows_pad, n_tiles * TILE] approximate scores, visiting order
 static int64_t g_acc_ld = 0;
 static thread_local int t_tile = -1;          // advanced by the epilogue's wait on the 'accumulator full' barrier
-static thread_local int t_row = 0, t_tilew = 0, t_half = 0;
+static thread_local int t_row = 0, t_tilew = 0, t_half = 0, t_staged = 0;   // t_staged: N = 128 kernel (two accumulator stages)
 """
 
 _TC_STUBS = r"""
@@ -713,7 +713,7 @@ static inline void mbar_arrive(uint32_t) {}
 static inline float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 // tcgen05.ld.32x32b.x64: 64 consecutive fp32 columns of this thread's TMEM lane, starting at column (taddr & 0xffff)
 static inline void tmem_ld64_async(uint32_t taddr, uint32_t (&r)[64]) {
-    const int col = (int)(taddr & 0xffffu) - t_half * t_tilew;
+    const int col = (int)(taddr & 0xffffu) - t_half * t_tilew - (t_staged ? (t_tile & 1) * 2 * t_tilew : 0);
     const float *src = g_acc + (int64_t)t_row * g_acc_ld + (int64_t)t_tile * t_tilew + col;
     memcpy(r, src, 256);
 }
@@ -728,8 +728,16 @@ static void tc_epilogue_host(const TcParams p) {
     const int warp = (threadIdx.x >> 5) + 2, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kBM;
     const int ew = warp - 2, q = warp & 3, h = ew >> 2;
-    t_tile = -1; t_row = row0 + h * 128 + q * 32 + lane; t_tilew = kPPN; t_half = h;
+    t_tile = -1; t_row = row0 + h * 128 + q * 32 + lane; t_tilew = kPPN; t_half = h; t_staged = 0;
     tc_epilogue<kPPN, true, false, false>(p, row0, p.n_tiles, warp, lane, 0u, nullptr, nullptr);
+}
+// ... and tc_candidate_kernel's (N = 128 tiles, d > 128: a pair of 128-column accumulators per stage, two stages)
+static void tc_epilogue_host_n128(const TcParams p) {
+    const int warp = (threadIdx.x >> 5) + 2, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kBM;
+    const int ew = warp - 2, q = warp & 3, h = ew >> 2;
+    t_tile = -1; t_row = row0 + h * 128 + q * 32 + lane; t_tilew = kBN; t_half = h; t_staged = 1;
+    tc_epilogue<kBN, false, false, false>(p, row0, p.n_tiles, warp, lane, 0u, nullptr, nullptr);
 }
 }
 extern "C" {
@@ -757,14 +765,15 @@ void emu_bloom(const int32_t *users, int n_rows, const int64_t *mi, const int32_
 void emu_tc_epilogue(int n_rows, int num_items, int n_tiles, int k, int d, const int32_t *users, const int64_t *mi,
                      const int32_t *mx, const int32_t *inv_perm, const unsigned long long *wide, const float *row_norm,
                      const float *tile_norm, const float *scale_u, const float *scale_v, uint64_t *cand, int32_t *cand_cnt,
-                     const float *acc, int64_t acc_ld) {
+                     const float *acc, int64_t acc_ld, int n128) {
     b200::TcParams p;
     memset(&p, 0, sizeof(p));
     p.n_rows = n_rows; p.num_items = num_items; p.n_tiles = n_tiles; p.k = k; p.d = d; p.users = users;
     p.mask_indptr = mi; p.mask_indices = mx; p.inv_perm = inv_perm; p.wide = wide; p.append_budget = 1536 + 8 * k;
     p.row_norm = row_norm; p.tile_norm = tile_norm; p.scale_u = scale_u; p.scale_v = scale_v; p.cand = cand; p.cand_cnt = cand_cnt;
     g_acc = acc; g_acc_ld = acc_ld;
-    emu_launch(b200::tc_epilogue_host, (n_rows + b200::kBM - 1) / b200::kBM, p);
+    if (n128) emu_launch(b200::tc_epilogue_host_n128, (n_rows + b200::kBM - 1) / b200::kBM, p);
+    else emu_launch(b200::tc_epilogue_host, (n_rows + b200::kBM - 1) / b200::kBM, p);
 }
 }
 """
@@ -810,7 +819,7 @@ def build_tc(out_dir):
     for name, args in (("emu_row_stats", [P, I, I, P, I, P, P]), ("emu_reorder", [P, P, I, I, I, I, P, P]),
                        ("emu_inverse_perm", [P, I, P]), ("emu_to_f16", [P, I, I, P, P, I, I, I, P, P, P]),
                        ("emu_tile_norm", [P, I, I, I, P]), ("emu_bloom", [P, I, P, P, P, P]),
-                       ("emu_tc_epilogue", [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, L])):
+                       ("emu_tc_epilogue", [I, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, L, I])):
         fn = getattr(h, name)
         fn.restype, fn.argtypes = None, args
     return h

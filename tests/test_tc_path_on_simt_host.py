@@ -17,7 +17,7 @@ import pytest
 
 pytestmark = pytest.mark.timeout(1500)
 P = lambda a: a.ctypes.data if a is not None else None
-TILE, KBM, KCAND = 256, 256, 512
+KBM, KCAND = 256, 512
 
 
 @pytest.fixture(scope="module")
@@ -35,6 +35,7 @@ def tc_score_topk(simt, U, V, ld, d, users, ni, mask, k, adversary=None):
     users = np.ascontiguousarray(users, np.int32)
     nr = len(users)
     up = lambda x, a: (x + a - 1) // a * a
+    TILE = 256 if d <= 128 else 128                                 # tc_layout: N = 256 ping-pong kernel for d <= 128, else N = 128
     dpad, items_pad, nr_pad = up(d, 64), up(ni, TILE), up(nr, KBM)
     n_tiles = items_pad // TILE
     # ---- item side, once per call ----
@@ -71,7 +72,7 @@ def tc_score_topk(simt, U, V, ld, d, users, ni, mask, k, adversary=None):
         acc = np.ascontiguousarray(acc + adversary.uniform(-0.9, 0.9, acc.shape).astype(np.float32) * bound, np.float32)
     cand = np.zeros((nr_pad, KCAND), np.uint64); cnt = np.full(nr_pad, -7, np.int32)
     tc.emu_tc_epilogue(nr, ni, n_tiles, k, d, P(users), P(mask[0]) if mask else None, P(mask[1]) if mask else None, P(inv_perm),
-                       P(wide), P(unorm), P(tnorm), P(scales[1:2]), P(scales[0:1]), P(cand), P(cnt), P(acc), items_pad)
+                       P(wide), P(unorm), P(tnorm), P(scales[1:2]), P(scales[0:1]), P(cand), P(cnt), P(acc), items_pad, 0 if TILE == 256 else 1)
     # ---- exact fp32 re-rank of the candidates; rows on the redo list go to the exact kernel ----
     oi = np.full((nr, k), -5, np.int32); os_ = np.full((nr, k), np.nan, np.float32)
     redo = np.full(nr, -1, np.int32); redo_n = np.zeros(1, np.int32)
@@ -117,7 +118,7 @@ def test_tc_path_equals_the_exact_oracle(simt, oracle_c, d, k, ni, sigma):
     ref_idx, ref_sc = oracle_c.score_topk(U, V, d, users, ni, mask[0], mask[1], k)
     np.testing.assert_array_equal(idx, ref_idx)
     np.testing.assert_array_equal(sc, ref_sc)
-    assert st["sample"] == (ni >= 8 * (256 + 4096))
+    assert st["sample"] == (ni >= 8 * (256 + 4096))                         # d <= 128 here: tile 256
     done = st["cnt"] >= 0
     assert (st["cnt"][done] >= k).all() and st["cnt"].max() < 512          # lists hold at least k, never overflow the slots
     assert st["kept"] < 0.25 * st["pairs"]                                 # the fp16 pass pruned the catalogue
@@ -209,3 +210,20 @@ def test_tc_path_exact_across_twelve_octaves_of_row_norms(simt, oracle_c):
     np.testing.assert_array_equal(sc, ref_sc)
     small = np.linalg.norm(U, axis=1) < 2.0 ** -8 * np.linalg.norm(U, axis=1).max()
     assert small.sum() > 20 and (st["cnt"][small] >= k).all()                # small users were served by the fp16 pass too
+
+
+@pytest.mark.parametrize("d,k,ni", [(200, 10, 3000), (256, 100, 2500), (136, 1, 17500)])
+def test_tc_path_wide_rows_n128_kernel(simt, oracle_c, d, k, ni):
+    """d > 128 takes the N = 128 kernel (tc_candidate_kernel): 128-item tiles, a pair of accumulators per stage and two
+    stages - same epilogue template with PP = false.  (17,500 items: the first size with a stratified sample at this tile.)"""
+    rng = np.random.default_rng(d + k)
+    nu = 200
+    U, V, ld = _tables(rng, nu, ni, d, item_norm_sigma=0.5, user_norm_sigma=0.3)
+    mask = _mask(rng, nu, ni, 0, 40)
+    users = rng.permutation(nu)[:170]
+    idx, sc, st = tc_score_topk(simt, U, V, ld, d, users, ni, mask, k)
+    ref_idx, ref_sc = oracle_c.score_topk(U, V, d, users, ni, mask[0], mask[1], k)
+    np.testing.assert_array_equal(idx, ref_idx)
+    np.testing.assert_array_equal(sc, ref_sc)
+    assert st["n_tiles"] == -(-ni // 128) and st["sample"] == (ni >= 8 * (128 + 2048))
+    assert st["kept"] < 0.3 * st["pairs"]
