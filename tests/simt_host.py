@@ -138,6 +138,17 @@ static inline void st4_hint(float *p, float4 v, uint64_t) { st4(p, v); }
 static inline void red4_hint(float *p, float4 v, uint64_t) { red4(p, v); }
 static inline void red4_bf16(__nv_bfloat16 *, float4) { fprintf(stderr, "simt_host: bf16 sink not emulated\n"); abort(); }
 static inline float4 ldg4(const float *p) { return ld4(p); }
+// asynchronous gathers of the step variants: the copy completes at issue (one valid schedule), barriers are no-ops
+alignas(128) static unsigned char g_tma_smem[112 * 1024];
+static inline uint32_t smem_u32(const void *p) { return (uint32_t)((const unsigned char *)p - g_tma_smem); }
+static inline void mbar_init(uint32_t, uint32_t) {}
+static inline void mbar_expect_tx(uint32_t, uint32_t) {}
+static inline void mbar_arrive(uint32_t) {}
+static inline void mbar_wait(uint32_t, uint32_t) {}
+static inline void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t) { memcpy(g_tma_smem + dst, src, bytes); }
+static inline void cp_async16(void *dst, const void *src) { memcpy(dst, src, 16); }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
@@ -208,6 +219,31 @@ int emu_bpr_step(const b200rec_bpr_args *args, int kind, int chunk, int grid) {
         else if (G == 8) { SINKS(8, 1) } else if (G == 16) { SINKS(16, 1) }
         else if (CPL == 1) { SINKS(32, 1) } else if (CPL == 2) { SINKS(32, 2) } else if (CPL == 3) { SINKS(32, 3) } else { SINKS(32, 4) }
 #undef SINKS
+        return 0;
+    }
+    if (kind == 5) {   // bpr_step_tma_kernel: stages per warp as launch_bpr computes them
+        const size_t per_stage = (size_t)kTmaWarps * a.ld * 4 * 3 * (32 / G);
+        const int st = (int)((96 * 1024) / per_stage);
+        p.stages = st < 2 ? 2 : (st > kTmaMaxStages ? kTmaMaxStages : st);
+#define SINKS_T(GG, CC)                                                                                     \
+        switch (a.sink) {                                                                                   \
+            case B200REC_SINK_UPDATE: emu_launch(bpr_step_tma_kernel<GG, CC, B200REC_SINK_UPDATE>, grid, p); break; \
+            case B200REC_SINK_STAGE: emu_launch(bpr_step_tma_kernel<GG, CC, B200REC_SINK_STAGE>, grid, p); break;   \
+            case B200REC_SINK_GRAD: emu_launch(bpr_step_tma_kernel<GG, CC, B200REC_SINK_GRAD>, grid, p); break;     \
+            default: emu_launch(bpr_step_tma_kernel<GG, CC, B200REC_SINK_NONE>, grid, p); break;                    \
+        }
+        if (G == 1) { SINKS_T(1, 1) } else if (G == 2) { SINKS_T(2, 1) } else if (G == 4) { SINKS_T(4, 1) }
+        else if (G == 8) { SINKS_T(8, 1) } else if (G == 16) { SINKS_T(16, 1) }
+        else if (CPL == 1) { SINKS_T(32, 1) } else if (CPL == 2) { SINKS_T(32, 2) } else if (CPL == 3) { SINKS_T(32, 3) } else { SINKS_T(32, 4) }
+#undef SINKS_T
+        return 0;
+    }
+    if (kind == 4) {   // bpr_step_async_kernel (cp.async ring): ld = 128 (S = 8) or 256 (S = 4), SINK_UPDATE
+        if (a.sink != B200REC_SINK_UPDATE || (a.ld != 128 && a.ld != 256) || idelta) return -1;
+        if (a.ld == 128) { if (uniq) { if (loss) emu_launch(bpr_step_async_kernel<1, true, true, 8>, grid, p); else emu_launch(bpr_step_async_kernel<1, true, false, 8>, grid, p); }
+                           else { if (loss) emu_launch(bpr_step_async_kernel<1, false, true, 8>, grid, p); else emu_launch(bpr_step_async_kernel<1, false, false, 8>, grid, p); } }
+        else { if (uniq) { if (loss) emu_launch(bpr_step_async_kernel<2, true, true, 4>, grid, p); else emu_launch(bpr_step_async_kernel<2, true, false, 4>, grid, p); }
+               else { if (loss) emu_launch(bpr_step_async_kernel<2, false, true, 4>, grid, p); else emu_launch(bpr_step_async_kernel<2, false, false, 4>, grid, p); } }
         return 0;
     }
     if (a.sink != B200REC_SINK_UPDATE || a.ld != 128) return -1;
@@ -331,6 +367,8 @@ def build(out_dir):
         _definition(step, glob % "bpr_step_ldg_kernel"),
         _definition(step, r"struct RowSet\s*"), _definition(step, glob % "bpr_step_fast_kernel"),
         _definition(step, r"struct GroupSet\s*"), _definition(step, glob % "bpr_step_group_kernel"),
+        "constexpr int kTmaWarps = 8;", "constexpr int kTmaMaxStages = 8;",
+        _definition(step, glob % "bpr_step_tma_kernel"), _definition(step, glob % "bpr_step_async_kernel"),
         _definition(step, glob % "bpr_apply_kernel"), _definition(step, glob % "rows_add_kernel"),
         _definition(step, glob % "mf_forward_kernel"), _definition(step, glob % "sgd_dense_kernel"),
         _definition(step, glob % "adam_dense_kernel"), _definition(step, glob % "adam_rows_kernel"),
@@ -343,6 +381,9 @@ def build(out_dir):
     text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
     text = text.replace("#pragma unroll", "// unroll")
     text = re.sub(r"\b__(expf|logf|frcp_rn)\(", r"emu_\1(", text)
+    text = text.replace("extern __shared__ __align__(128) unsigned char smem_raw[];", "unsigned char *smem_raw = g_tma_smem;")
+    text = text.replace("extern __shared__ __align__(16) float4 ring_all[];", "alignas(16) static float4 ring_all[8 * 8 * 3 * 32];")
+    text = text.replace('asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");', ";")
     src = os.path.join(out_dir, "simt_bpr.cpp")
     lib = os.path.join(out_dir, "libsimt_bpr.so")
     with open(src, "w") as f:

@@ -305,3 +305,48 @@ def test_dense_helpers_of_the_multi_gpu_layouts(simt):
     want = T0.astype(np.float64)
     np.add.at(want, ids, 0.5 * delta[:, :12].astype(np.float64))
     np.testing.assert_allclose(T, want, rtol=1e-5, atol=1e-6)
+
+
+# ---- the asynchronous-gather variants of the step (F_TMA_GATHER: cp.async.bulk rows + mbarriers; F_ASYNC_GATHER: cp.async ring)
+# The copy engines are not emulated: a copy completes when it is issued (one valid schedule) and the barriers are no-ops -
+# what runs from the source is the staging layout, the slot / phase bookkeeping and all the arithmetic.
+ASYNC, TMA = 4, 5
+
+
+@pytest.mark.parametrize("d,chunk", [(8, 32), (32, 8), (50, 32), (64, 4), (128, 32), (200, 16), (256, 32), (400, 8)])
+def test_tma_variant_exact_step_all_widths(simt, d, chunk):
+    nu, ni, B = 97, 61, 250 + d % 5
+    U0, V0, u, i, j = _problem(1000 + d, nu, ni, d, B)
+    s = Step(simt, U0, V0, d, u, i, j, lr=0.7, reg=0.02, sink=SINK_STAGE, want_x=True, kind=TMA, chunk=chunk)
+    s.apply(simt)
+    Ur, Vr, lref = O.sgd_step(U0, V0, u, i, j, 0.7, 0.02)
+    np.testing.assert_allclose(s.U[:, :d], Ur, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(s.V[:, :d], Vr, rtol=2e-5, atol=2e-6)
+    assert abs(s.loss[0] / B - float(lref)) < 2e-5 * max(1.0, float(lref))
+    g = Step(simt, U0, V0, d, u, i, j, reg=0.02, sink=SINK_GRAD, kind=TMA, chunk=chunk)
+    dU, dV, _, _ = O.bpr_grads(U0, V0, u, i, j, 0.02)
+    np.testing.assert_allclose(g.gU[:, :d], dU, rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(g.gV[:, :d], dV, rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind,d", [(TMA, 128), (ASYNC, 128), (ASYNC, 256)])
+@pytest.mark.parametrize("uniq", [0, F_USERS_UNIQUE])
+def test_async_gather_variants_in_place_update(simt, kind, d, uniq):
+    """smoke() and the device suite run the TMA variant beside the default: in-place update without collisions == exact
+    step; with in-kernel sampling the reported triples are the host mirror's."""
+    nu, ni, B = 500, 1100, 389
+    U0, V0, u, i, j = _problem(kind + d, nu, ni, d, B, std=0.3, unique_users=True, unique_items=True)
+    s = Step(simt, U0, V0, d, u, i, j, lr=0.9, reg=0.01, sink=SINK_UPDATE, flags=uniq, kind=kind, chunk=32)
+    Ur, Vr, lref = O.sgd_step(U0, V0, u, i, j, 0.9, 0.01)
+    np.testing.assert_allclose(s.U[:, :d], Ur, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(s.V[:, :d], Vr, rtol=2e-5, atol=2e-6)
+    assert abs(s.loss[0] / B - float(lref)) < 2e-5
+    rng = np.random.default_rng(3)
+    rows = [np.sort(rng.choice(ni, int(rng.integers(1, 25)), replace=False)).astype(np.int32) for _ in range(nu)]
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.concatenate(rows)
+    users = rng.permutation(nu)[:B]
+    t = Step(simt, U0, V0, d, users, csr=(indptr, indices), lr=0.0, sink=SINK_UPDATE, flags=F_USERS_UNIQUE, seed=2020, step=3,
+             kind=kind, chunk=32)
+    pos, neg = O.sample_triples_vec(2020, 3, users, indptr, indices, ni)
+    assert np.array_equal(t.out_pos, pos) and np.array_equal(t.out_neg, neg)
