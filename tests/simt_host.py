@@ -138,6 +138,20 @@ static inline void st4_hint(float *p, float4 v, uint64_t) { st4(p, v); }
 static inline void red4_hint(float *p, float4 v, uint64_t) { red4(p, v); }
 static inline void red4_bf16(__nv_bfloat16 *, float4) { fprintf(stderr, "simt_host: bf16 sink not emulated\n"); abort(); }
 static inline float4 ldg4(const float *p) { return ld4(p); }
+}
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+template <class T> static inline T atomicMax(T *p, T v) {
+    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline long long clock64() { return 0; }
+'''
+
+_ASYNC_STUBS = r'''
+namespace b200 {
 // asynchronous gathers of the step variants: the copy completes at issue (one valid schedule), barriers are no-ops
 alignas(128) static unsigned char g_tma_smem[112 * 1024];
 static inline uint32_t smem_u32(const void *p) { return (uint32_t)((const unsigned char *)p - g_tma_smem); }
@@ -150,15 +164,6 @@ static inline void cp_async16(void *dst, const void *src) { memcpy(dst, src, 16)
 static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}
 }
-template <class T> static inline T __ldg(const T *p) { return *p; }
-static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-template <class T> static inline T atomicMax(T *p, T v) {
-    T old = __atomic_load_n(p, __ATOMIC_RELAXED);
-    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-    return old;
-}
-static inline long long clock64() { return 0; }
 '''
 
 _LAUNCHER = r'''
@@ -376,7 +381,7 @@ def build(out_dir):
         _definition(step, glob % "add_clear_kernel"), _definition(step, glob % "snap_apply_kernel"),
         "}",
     ]
-    text = _PRELUDE + "\n".join(pieces) + _LAUNCHER + _LAUNCH
+    text = _PRELUDE + _ASYNC_STUBS + "\n".join(pieces) + _LAUNCHER + _LAUNCH
     text = re.sub(r"__global__\s+void\s+__launch_bounds__\([^\n]*?\)\s+(?=\w+\s*\()", "static void ", text)
     text = text.replace("__device__ __forceinline__", "static inline").replace("__restrict__", "")
     text = text.replace("#pragma unroll", "// unroll")
