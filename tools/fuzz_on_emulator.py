@@ -1,9 +1,11 @@
-"""Randomised exactness campaigns on the host SIMT emulator (tests/simt_host.py): the scoring kernels' own source text
-against the C oracle on random shapes - d, k, catalogue size, norm spread, ties, zero rows, heavy masks, anti-aligned
-users, item-split counts, and (tensor-core path) an adversarial accumulator in half of the cases.
+"""Randomised exactness campaigns on the host SIMT emulator (tests/simt_host.py): the kernels' own source text against the
+oracle on random shapes.  Scoring: d, k, catalogue size, norm spread, ties, zero rows, heavy masks, anti-aligned users,
+item-split counts, and (tensor-core path) an adversarial accumulator in half of the cases.  P2P step: world size up to 16,
+every row width, replicated head, random shard bounds, empty batches, the three visiting orders, fixed triples across shards.
 
-    python tools/fuzz_scoring_on_emulator.py tc    600 1000     # seconds, first seed  (round 2: 200 cases, 0 mismatches)
-    python tools/fuzz_scoring_on_emulator.py exact 300 5000     #                      (round 2: 105 cases, 0 mismatches)
+    python tools/fuzz_on_emulator.py tc    600 1000     # seconds, first seed  (round 2: 200 cases, 0 mismatches)
+    python tools/fuzz_on_emulator.py exact 300 5000     #                      (round 2: 105 cases, 0 mismatches)
+    python tools/fuzz_on_emulator.py p2p   300 100      #                      (round 2: 843 cases, 0 mismatches)
 """
 import os
 import sys
@@ -91,6 +93,48 @@ def fuzz_exact(seconds, seed):
     print("exact kernel: %d cases, %d mismatches, next seed %d" % (n, bad, seed))
 
 
+def fuzz_p2p(seconds, seed):
+    from oracle import bpr_oracle as O
+    from recsys_pytorch_b200._lib import F_P2P_PURE_SEQUENTIAL, F_P2P_ROUND_ROBIN, F_USERS_UNIQUE
+    from tests.test_p2p_on_simt_host import _make, _sync_head, _tables
+    simt = simt_host.build_p2p(tempfile.mkdtemp())
+    t_end, n, bad = time.time() + seconds, 0, 0
+    while time.time() < t_end:
+        rng = np.random.default_rng(seed); seed += 1
+        W = int(rng.choice([1, 2, 3, 4, 5, 8, 16])); d = int(rng.choice([128, 128, 128, 50, 64, 200, 256, 400, 8]))
+        variant = int(rng.choice([16, 8, 0])) if d == 128 else 0
+        head = int(rng.choice([0, 0, 17, 100]))
+        nu = int(rng.integers(max(W, 20), 400)); ni = int(rng.integers(head + 2 * nu + W + 10, head + 2 * nu + 1500))
+        bounds = None if W == 1 else sorted({head, ni} | set(rng.choice(np.arange(head + 1, ni), W - 1, replace=False).tolist()))
+        ranks, U0, V0, _, _, ib, ub = _make(W, nu, ni, d, seed=seed, bounds=bounds, head=head)
+        items = rng.permutation(ni); gu, gi, gj, k = [], [], [], 0
+        for r in ranks:
+            n_loc = ub[r.rank + 1] - ub[r.rank]
+            B = int(rng.integers(0, n_loc + 1))                              # empty batches included
+            ul = rng.permutation(n_loc)[:B].astype(np.int32)
+            pi, pj = items[k:k + B].astype(np.int32), items[k + B:k + 2 * B].astype(np.int32); k += 2 * B
+            gu.append(ul + ub[r.rank]); gi.append(pi); gj.append(pj)
+            r.route(simt, ul, 1, pos=pi, neg=pj)
+        gu, gi, gj = np.concatenate(gu), np.concatenate(gi), np.concatenate(gj)
+        Bg = max(len(gu), 1)
+        snap = ranks[0].Vh.copy()
+        flags = F_USERS_UNIQUE | int(rng.choice([0, F_P2P_ROUND_ROBIN, F_P2P_PURE_SEQUENTIAL]))
+        for r in ranks:
+            r.step(simt, ranks, Bg, variant, flags=flags)
+        _sync_head(ranks, snap)
+        ok = sum(int(r.n_processed[0]) for r in ranks) == len(gu)
+        if len(gu):
+            Ur, Vr, lref = O.sgd_step(U0, V0, gu, gi, gj, 0.9, 0.01)
+            U, V = _tables(ranks, d)
+            ok = ok and np.allclose(U, Ur, rtol=2e-5, atol=2e-6) and np.allclose(V, Vr, rtol=2e-5, atol=2e-6) and \
+                abs(sum(r.loss[0] for r in ranks) / Bg - float(lref)) < 2e-5 * max(1, float(lref))
+        n += 1
+        if not ok:
+            bad += 1
+            print("MISMATCH seed", seed - 1, dict(W=W, d=d, variant=variant, head=head, nu=nu, ni=ni, flags=flags), flush=True)
+    print("P2P step: %d cases, %d mismatches, next seed %d" % (n, bad, seed))
+
+
 if __name__ == "__main__":
     which, seconds, seed = sys.argv[1], float(sys.argv[2]), int(sys.argv[3])
-    {"tc": fuzz_tc, "exact": fuzz_exact}[which](seconds, seed)
+    {"tc": fuzz_tc, "exact": fuzz_exact, "p2p": fuzz_p2p}[which](seconds, seed)
